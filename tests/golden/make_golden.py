@@ -1,0 +1,193 @@
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Only runnable where /root/reference exists (the build container).  The GPU box never runs this; it
+consumes the committed fixtures.  Usage:
+
+    python tests/golden/make_golden.py det      # detection goldens (about 1 min)
+    python tests/golden/make_golden.py rec      # recognition goldens (needs MSERTrain.val: about 7 min first time)
+
+Everything stored here is an output of the reference's own functions (DET/source.py, REC/source.py)
+called through tests/golden/refload.py; the oracle (oracle/) is NOT involved in producing them.
+
+Files written
+  det_templates.npz        red6/blue6 template masks from calculateMeanMasks (DET/source.py:24-59)
+  det_frame_<name>.png     three real test frames (decoded BGR, lossless)
+  det_frames.npz           per stored frame: MSER boxes, K1 coords, K2 windows, survivors after each
+                           de-duplication pass, red/blue masks, per-template scores, final detections
+  det_windows50.npz        first 50 test frames (sorted): post-resize windows+coords (input of the fold),
+                           survivors and final detection tuples (the resultado.txt content)
+  det_resultado150.txt     the reference's resultado.txt lines for all 150 frames in sorted file order
+  rec_golden.npz           LDA/KNN weights, grey 32x32 windows, HOG descriptors, logits, probabilities, labels
+  rec_frames.npz           recognition-flavour (x1.15, 32x32) window extraction for the stored frames
+"""
+import hashlib
+import os
+import random
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refload  # noqa: E402
+
+STORED_FRAMES = ["00604.jpg", "00639.jpg", "00719.jpg"]
+
+
+def _silence_tqdm(mod):
+    mod.tqdm = lambda it=None, *a, **k: it
+
+
+def make_det():
+    src, const = refload.load_det()
+    _silence_tqdm(src)
+    const.TRAIN_PATH = os.path.join(refload.DET_DIR, "train_jpg")
+    const.TEST_PATH = os.path.join(refload.DET_DIR, "test_alumnos_jpg")
+    red, blue = src.calculateMeanMasks()
+    red6 = np.stack([m for m, _ in red])
+    blue6 = np.stack([m for m, _ in blue])
+    names = [n for _, n in red]
+    np.savez_compressed(os.path.join(HERE, "det_templates.npz"), red6=red6, blue6=blue6, names=np.array(names))
+
+    mser = cv2.MSER_create(delta=7, min_area=200, max_area=2000, max_variation=0.15)
+    files = sorted(f for f in os.listdir(const.TEST_PATH) if f.endswith(".jpg"))
+
+    lines = []
+    w50 = dict(files=[], offsets=[0], windows=[], coords=[], boxes=[], box_offsets=[0], surv_offsets=[0], surv_windows=[],
+               surv_coords=[], p1_offsets=[0], p1_coords=[], det_offsets=[0], det_coords=[], det_ids=[], det_scores=[])
+    fr = {}
+    stage = np.zeros(4, np.int64)
+    for fi, f in enumerate(files):
+        img = cv2.imread(os.path.join(const.TEST_PATH, f))
+        boxes = np.asarray(mser.detectRegions(src.grayAndEnhanceContrast(img))[1], np.int32).reshape(-1, 4)
+        # --- reference stage functions, in the order of MSERTrafficSignDetector (DET/source.py:111-131)
+        coords = [src.makeWindowBiggerOrDiscardFakeDetections(b, 1.30) for b in boxes]
+        items = [(cv2.resize(src.cropImageByCoords(c, img), (25, 25)), c, f) for c in coords if c is not None]
+        p1 = src.cleanDuplicatedDetections(list(items), False, 0.85)
+        p2 = src.cleanDuplicatedDetections(list(p1), True, 0.95)
+        ref_direct = src.MSERTrafficSignDetector(img, mser, f)
+        assert len(ref_direct) == len(p2) and all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(ref_direct, p2))
+        dets = [src.detectionsMaskCorrelation(d, red, blue, 0.55) for d in p2]
+        dets = [d for d in dets if d is not None]
+        lines.extend(src.createDetectionsStrings(dets))
+        stage += (len(boxes), len(items), len(p2), len(dets))
+        if fi < 50:
+            w50["files"].append(f)
+            w50["boxes"].append(boxes); w50["box_offsets"].append(w50["box_offsets"][-1] + len(boxes))
+            w50["windows"].extend(i[0] for i in items); w50["coords"].extend(i[1] for i in items)
+            w50["offsets"].append(w50["offsets"][-1] + len(items))
+            w50["p1_coords"].extend(i[1] for i in p1); w50["p1_offsets"].append(w50["p1_offsets"][-1] + len(p1))
+            w50["surv_windows"].extend(i[0] for i in p2); w50["surv_coords"].extend(i[1] for i in p2)
+            w50["surv_offsets"].append(w50["surv_offsets"][-1] + len(p2))
+            w50["det_coords"].extend(d[1:5] for d in dets); w50["det_ids"].extend(d[5] for d in dets)
+            w50["det_scores"].extend(d[6] for d in dets); w50["det_offsets"].append(w50["det_offsets"][-1] + len(dets))
+        if f in STORED_FRAMES:
+            cv2.imwrite(os.path.join(HERE, "det_frame_" + f[:-4] + ".png"), img, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+            k = f[:-4]
+            fr[k + "_boxes"] = boxes
+            fr[k + "_valid"] = np.array([c is not None for c in coords])
+            fr[k + "_coords"] = np.array([c if c is not None else (0, 0, 0, 0) for c in coords], np.int32).reshape(-1, 4)
+            fr[k + "_windows"] = np.stack([i[0] for i in items]) if items else np.zeros((0, 25, 25, 3), np.uint8)
+            fr[k + "_p1_windows"] = np.stack([i[0] for i in p1]); fr[k + "_p1_coords"] = np.array([i[1] for i in p1], np.int32)
+            fr[k + "_p2_windows"] = np.stack([i[0] for i in p2]); fr[k + "_p2_coords"] = np.array([i[1] for i in p2], np.int32)
+            fr[k + "_hsv"] = np.stack([cv2.cvtColor(i[0], cv2.COLOR_BGR2HSV) for i in p2])
+            fr[k + "_red"] = np.stack([src.getColorMaskRedOrBlue(i[0], "r") for i in p2])
+            fr[k + "_blue"] = np.stack([src.getColorMaskRedOrBlue(i[0], "b") for i in p2])
+            sc = np.zeros((len(p2), 2, 6), np.float64)
+            for wi, it in enumerate(p2):
+                for ci, (mask, tm) in enumerate(((fr[k + "_red"][wi], red), (fr[k + "_blue"][wi], blue))):
+                    for ti, (t, _) in enumerate(tm):
+                        sc[wi, ci, ti] = src.calculateScoreBetweenMatrixs(mask * t, t)
+            fr[k + "_scores"] = sc
+            fr[k + "_hists"] = np.stack([src.calculateHistAndNormalize(i[0]) for i in items])
+            fr[k + "_det_coords"] = np.array([d[1:5] for d in dets], np.int32).reshape(-1, 4)
+            fr[k + "_det_ids"] = np.array([d[5] for d in dets], np.int32)
+            fr[k + "_det_scores"] = np.array([d[6] for d in dets], np.float64)
+    np.savez_compressed(os.path.join(HERE, "det_frames.npz"), **fr)
+    np.savez_compressed(
+        os.path.join(HERE, "det_windows50.npz"), files=np.array(w50["files"]),
+        boxes=np.concatenate(w50["boxes"]).astype(np.int32), box_offsets=np.array(w50["box_offsets"], np.int32),
+        offsets=np.array(w50["offsets"], np.int32), windows=np.stack(w50["windows"]), coords=np.array(w50["coords"], np.int32),
+        p1_offsets=np.array(w50["p1_offsets"], np.int32), p1_coords=np.array(w50["p1_coords"], np.int32),
+        surv_offsets=np.array(w50["surv_offsets"], np.int32), surv_windows=np.stack(w50["surv_windows"]),
+        surv_coords=np.array(w50["surv_coords"], np.int32), det_offsets=np.array(w50["det_offsets"], np.int32),
+        det_coords=np.array(w50["det_coords"], np.int32).reshape(-1, 4), det_ids=np.array(w50["det_ids"], np.int32),
+        det_scores=np.array(w50["det_scores"], np.float64))
+    with open(os.path.join(HERE, "det_resultado150.txt"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    sha = hashlib.sha1("\n".join(sorted(lines)).encode()).hexdigest()
+    print("stage counts raw/aspect/survivors/detections:", stage.tolist(), "lines", len(lines), "sha1(sorted)", sha)
+
+
+def make_rec(workdir="/tmp/o_rec"):
+    src, const = refload.load_rec()
+    _silence_tqdm(src)
+    os.makedirs(workdir, exist_ok=True)
+    cwd = os.getcwd()
+    os.chdir(workdir)   # MSERTrain.val is looked up relative to the cwd (REC/source.py:381)
+    try:
+        if not os.path.exists("train_jpg"):
+            os.symlink(os.path.join(refload.REC_DIR, "train_jpg"), "train_jpg")
+        random.seed(0); np.random.seed(0)
+        const.TRAIN_PATH = "train_jpg"; const.TRAIN_PATH_REAL_RESULTS = "train_jpg/gt.txt"
+        mser = src.initializeMSER((7, 200, 2000, 1.0))
+        desc = src.initializeFeatureDescriptor("HOG")
+        data, imgs = src.loadTrainData(mser)
+        tr, te = src.extractEvaluationTestResults(data, 0.1)
+        trd, ted = src.calculateDescriptors(tr, desc), src.calculateDescriptors(te, desc)
+        cl = src.createClassifiers("LDABAYES")
+        src.fitClassifiers(cl, "LDA", trd)
+        flat = src.flatData(list(ted.values())); random.shuffle(flat)
+        flat_img = {id(d): None for d in flat}
+        # descriptor tuples lost the image; rebuild (image, descriptor) pairs in the same order
+        te_flat = src.flatData(list(te.values()))
+        by_key = {}
+        for im_t, d_t in zip(te_flat, src.flatData(list(ted.values()))):
+            by_key[id(d_t)] = im_t[0]
+        gray = np.stack([by_key[id(d)] for d in flat])
+        hog = np.stack([d[0] for d in flat]).astype(np.float32)
+        pred, true = src.predictProbability(cl, None, flat, 0.5)
+        proba = np.stack([c.predict_proba([d[0] for d in flat]) for c in cl[0]], 1)      # [n,6,2]
+        W = np.stack([c.coef_[0] for c in cl[0]], 1)                                      # [324,6] f64
+        b = np.array([c.intercept_[0] for c in cl[0]])
+        logits = np.stack([c.decision_function([d[0] for d in flat]) for c in cl[0]], 1)
+        # KNN flavour
+        random.seed(0); np.random.seed(0)
+        clk = src.createClassifiers("KNN")
+        reducer, Z, tags = src.fitClassifiers(clk, "LDA", trd)
+        predk, truek = src.predictProbability(clk, reducer, flat, 0.5)
+        Zq = reducer[0].transform([d[0] for d in flat])
+        sel = np.arange(len(flat))
+        np.savez_compressed(
+            os.path.join(HERE, "rec_golden.npz"), gray=gray[sel], hog=hog[sel], lda_W=W, lda_b=b, logits=logits[sel],
+            proba=proba[sel], pred_lda=np.array(pred, np.int32)[sel], true=np.array(true, np.int32)[sel],
+            knn_xbar=reducer[0].xbar_, knn_scalings=reducer[0].scalings_[:, :6], knn_Ztrain=np.asarray(Z, np.float64),
+            knn_ytrain=np.array(tags, np.int32), knn_Zq=Zq[sel], pred_knn=np.array(list(predk), np.int32)[sel])
+        print("rec: n =", len(flat), "acc lda", np.mean(np.array(pred) == np.array(true)), "acc knn",
+              np.mean(np.array(list(predk)) == np.array(true)))
+        # recognition-flavour window extraction on the stored frames (REC/source.py:47-64 + :388)
+        fr = {}
+        test_dir = os.path.join(refload.REC_DIR, "test_alumnos_jpg")
+        for f in STORED_FRAMES:
+            img = cv2.imread(os.path.join(test_dir, f))
+            k = f[:-4]
+            boxes = np.asarray(mser.detectRegions(src.grayAndEnhanceContrast(img))[1], np.int32).reshape(-1, 4)
+            dets = src.MSERTrafficSignDetector(img, mser, f)
+            fr[k + "_boxes"] = boxes
+            fr[k + "_windows"] = np.stack([d[0] for d in dets])
+            fr[k + "_coords"] = np.array([d[1] for d in dets], np.int32)
+            fr[k + "_gray"] = np.stack([cv2.cvtColor(d[0], cv2.COLOR_BGR2GRAY) for d in dets])
+            fr[k + "_hog"] = np.stack([desc[0].compute(g) for g in fr[k + "_gray"]])
+            fr[k + "_pred_lda"] = np.array(src.predictProbability(cl, None, [(h, None, None, 0) for h in fr[k + "_hog"]], 0.5)[0], np.int32)
+        np.savez_compressed(os.path.join(HERE, "rec_frames.npz"), **fr)
+    finally:
+        os.chdir(cwd)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "det"
+    if what in ("det", "all"):
+        make_det()
+    if what in ("rec", "all"):
+        make_rec()
