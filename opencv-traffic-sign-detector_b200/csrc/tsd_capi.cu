@@ -1,0 +1,818 @@
+// tsd_capi.cu -- C-ABI shared library (include/tsd_b200.h) over the sm_100a kernels in tsd_kernels.cuh.
+// Host side: context, grow-only device scratch, stream-ordered staging for host-pointer calls, the batched chain.
+// There is no CPU fallback anywhere in this file: every entry point launches CUDA kernels or fails.
+#include "../../include/tsd_b200.h"
+#include "tsd_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using namespace tsd;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(TSD_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(call)                 \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != TSD_OK) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct tsd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    tsd_config cfg;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // constant state
+    Tables* d_tab = nullptr;
+    ScoreTemplates* d_tmpl = nullptr;
+    bool have_templates = false;
+    int tmpl_D = 0;
+    double* d_simtab = nullptr;
+    int simtab_n = 0;
+    double* d_ldaW = nullptr; double* d_ldab = nullptr; int lda_nfeat = 0;
+    double* d_xbar = nullptr; double* d_scal = nullptr; double* d_Zt = nullptr; int32_t* d_yt = nullptr;
+    int knn_nfeat = 0, knn_ntrain = 0, knn_k = 4;
+    HogConst hog;
+    // grow-only scratch
+    DevBuf b_coords, b_winframe, b_windows, b_entries, b_meta, b_list, b_flags, b_cnt, b_winoff, b_survcnt, b_survoff,
+        b_slots, b_red, b_blue, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
+    // last enqueue
+    int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> ev_names;
+    int ev_used = 0;
+};
+
+static int ensure(tsd_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return TSD_OK;
+    if (b.p) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return TSD_OK;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+static int check_launch(tsd_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TSD_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return TSD_OK;
+}
+
+static void mark(tsd_ctx* c, const char* name) {
+    if (!c->profiling) return;
+    if (c->ev_used >= (int)c->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev.push_back(e);
+        c->ev_names.push_back("");
+    }
+    c->ev_names[c->ev_used] = name;
+    cudaEventRecord(c->ev[c->ev_used], c->stream);
+    c->ev_used++;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* tsd_last_error(void) { return g_err; }
+const char* tsd_version(void) { return "tsd_b200 0.1 (sm_100a)"; }
+
+int tsd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tsd_config_default(tsd_config* cfg, int flavour) {
+    if (!cfg) return fail(TSD_E_INVALID, "cfg is NULL");
+    memset(cfg, 0, sizeof *cfg);
+    cfg->enlarge = flavour == 1 ? 1.15 : 1.30;
+    cfg->aspect_lo = 0.8; cfg->aspect_hi = 1.20;
+    cfg->window = flavour == 1 ? 32 : 25;
+    cfg->score_tol_hundredths = 55;
+    cfg->hist_tol = 0.85; cfg->coord_tol = 0.95; cfg->merge_factor = 0.8823;
+    const uint8_t rl[2][3] = {{0, 50, 10}, {160, 50, 10}}, rh[2][3] = {{10, 255, 255}, {179, 255, 255}};
+    memcpy(cfg->red_lo, rl, 6); memcpy(cfg->red_hi, rh, 6);
+    const uint8_t bl[3] = {90, 70, 10}, bh[3] = {128, 255, 255};
+    memcpy(cfg->blue_lo, bl, 3); memcpy(cfg->blue_hi, bh, 3);
+    cfg->proba_tol = 0.5; cfg->knn_k = 4;
+    return TSD_OK;
+}
+
+static double eucl_similarity_d2(long long d2) {             // DET:459-462 with libm
+    if (d2 <= 0) return 1.0;
+    double d = sqrt((double)d2);
+    return 1.0 / (1.0 + pow(M_E, ((0.154 * pow(d, 1.2)) - 31.8) / (0.2 * d)));
+}
+
+int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
+    if (!out) return fail(TSD_E_INVALID, "ctx out pointer is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(TSD_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (device < 0 || device >= ndev) return fail(TSD_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    tsd_ctx* c = new tsd_ctx();
+    c->device = device;
+    if (cfg) c->cfg = *cfg; else tsd_config_default(&c->cfg, 0);
+    if (c->cfg.window < 2 || c->cfg.window > kMaxD) { delete c; return fail(TSD_E_INVALID, "window %d not in [2,%d]", c->cfg.window, kMaxD); }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    // tables
+    Tables t;
+    t.sdiv[0] = t.hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+        t.sdiv[i] = (int32_t)lrint((255 << 12) / (1. * i));
+        t.hdiv[i] = (int32_t)lrint((180 << 12) / (6. * i));
+    }
+    const double a_h = 50 / (180. - 0.), a_s = 60 / (256. - 0.);
+    for (int i = 0; i < 256; i++) {
+        int hb = (int)floor(i * a_h + (-0. * a_h)), sb = (int)floor(i * a_s + (-0. * a_s));
+        t.hbin[i] = (uint8_t)(hb < kHistH ? hb : kHistH - 1);
+        t.sbin[i] = (uint8_t)(sb < kHistS ? sb : kHistS - 1);
+    }
+    CU(cudaMalloc(&c->d_tab, sizeof(Tables)));
+    CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_tmpl, sizeof(ScoreTemplates)));
+    // default corner-similarity table
+    const int n = 1 << 16;
+    std::vector<double> f(n);
+    for (int i = 0; i < n; i++) f[i] = eucl_similarity_d2(i);
+    CU(cudaMalloc(&c->d_simtab, sizeof(double) * n));
+    CU(cudaMemcpy(c->d_simtab, f.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    c->simtab_n = n;
+    {   // HOG Gaussian window, sigma = (16+16)/8 = 4  (OpenCV HOGCache::init)
+        float sigma = 4.f, sc = 1.f / (sigma * sigma * 2);
+        for (int i = 0; i < 16; i++) { float di = i - 16 * 0.5f; c->hog.gauss[i] = expf(-di * di * sc); }
+    }
+    *out = c;
+    return TSD_OK;
+}
+
+int tsd_destroy(tsd_ctx* c) {
+    if (!c) return TSD_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
+                      &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_red, &c->b_blue, &c->b_id, &c->b_hund,
+                      &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return TSD_OK;
+}
+
+void* tsd_stream(tsd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int tsd_synchronize(tsd_ctx* c) {
+    if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int64_t tsd_launch_count(tsd_ctx* c) { return c ? c->launches : 0; }
+
+int tsd_set_profiling(tsd_ctx* c, int on) {
+    if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    c->profiling = on != 0;
+    return TSD_OK;
+}
+
+int tsd_stage_times(tsd_ctx* c, const char** names, float* ms, int cap) {
+    if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    int n = 0;
+    for (int i = 1; i < c->ev_used && n < cap; i++, n++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->ev[i - 1], c->ev[i]);
+        names[n] = c->ev_names[i].c_str();
+        ms[n] = t;
+    }
+    return n;
+}
+
+// ---- state ------------------------------------------------------------------------------------------------------
+static int round2_hundredths(double v) {                     // Python round(v, 2): exactly rounded decimal (DET:567)
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.2f", v);
+    return (int)lrint(strtod(buf, NULL) * 100.0);
+}
+
+int tsd_set_templates(tsd_ctx* c, const uint8_t* red6, const uint8_t* blue6) {
+    if (!c || !red6 || !blue6) return fail(TSD_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int D = c->cfg.window, npx = D * D;
+    ScoreTemplates* h = new ScoreTemplates();
+    memset(h, 0, sizeof *h);
+    for (int k = 0; k < 12; k++) {
+        const uint8_t* t = (k < 6 ? red6 : blue6) + (size_t)(k % 6) * npx;
+        int T = 0;
+        for (int p = 0; p < npx; p++) {
+            // matrix2 = template // 255 (DET:552): only the value 255 counts
+            if (t[p] == 255) { h->bits[k][p >> 5] |= 1u << (p & 31); T++; }
+            else if (t[p] != 0) { delete h; return fail(TSD_E_INVALID, "template %d pixel %d = %d, expected 0 or 255", k, p, t[p]); }
+        }
+        const double shape = (double)npx;
+        const int tn = npx - T;                              // FP == 0 always (mask*template wraps to {0,1}, DET:254)
+        const bool degenerate = (shape + shape * 0.01 >= (double)tn) && ((double)tn >= shape - shape * 0.01);   // DET:563-565
+        for (int tp = 0; tp <= npx; tp++) {
+            int v = 0;
+            if (!degenerate && tp <= T && (tp + T) > 0) v = round2_hundredths((2.0 * tp) / (double)((2 * tp) + 0 + (T - tp)));
+            h->lut[k][tp] = (uint8_t)v;
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync(c->d_tmpl, h, sizeof *h, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    delete h;
+    if (e != cudaSuccess) return fail(TSD_E_CUDA, "template upload: %s", cudaGetErrorString(e));
+    c->have_templates = true;
+    c->tmpl_D = D;
+    return TSD_OK;
+}
+
+int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
+    if (!c || !f || n < 2) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    // the kernel treats d2 >= n as "no action": require f(n-1) small enough that sqrt(f) < tol*merge_factor for both passes
+    if (sqrt(f[n - 1]) >= c->cfg.coord_tol * c->cfg.merge_factor) return fail(TSD_E_INVALID, "similarity table too short: f(%d)=%g", n - 1, f[n - 1]);
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_simtab) CU(cudaFree(c->d_simtab));
+    c->d_simtab = nullptr;
+    CU(cudaMalloc(&c->d_simtab, sizeof(double) * n));
+    CU(cudaMemcpy(c->d_simtab, f, sizeof(double) * n, cudaMemcpyHostToDevice));
+    c->simtab_n = n;
+    return TSD_OK;
+}
+
+int tsd_set_lda(tsd_ctx* c, const double* W, const double* b, int nfeat) {
+    if (!c || !W || !b || nfeat < 1 || nfeat > 4096) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_ldaW) cudaFree(c->d_ldaW);
+    if (c->d_ldab) cudaFree(c->d_ldab);
+    CU(cudaMalloc(&c->d_ldaW, sizeof(double) * nfeat * 6));
+    CU(cudaMalloc(&c->d_ldab, sizeof(double) * 6));
+    CU(cudaMemcpy(c->d_ldaW, W, sizeof(double) * nfeat * 6, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_ldab, b, sizeof(double) * 6, cudaMemcpyHostToDevice));
+    c->lda_nfeat = nfeat;
+    return TSD_OK;
+}
+
+int tsd_set_knn(tsd_ctx* c, const double* xbar, const double* scalings, int nfeat, const double* Ztrain, const int32_t* ytrain,
+                int ntrain, int k) {
+    if (!c || !xbar || !scalings || !Ztrain || !ytrain || nfeat < 1 || ntrain < 1 || k < 1 || k > kKnnMaxK)
+        return fail(TSD_E_INVALID, "bad argument (k must be 1..%d)", kKnnMaxK);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    void* old[] = {c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    for (void* p : old) if (p) cudaFree(p);
+    CU(cudaMalloc(&c->d_xbar, sizeof(double) * nfeat));
+    CU(cudaMalloc(&c->d_scal, sizeof(double) * nfeat * 6));
+    CU(cudaMalloc(&c->d_Zt, sizeof(double) * (size_t)ntrain * 6));
+    CU(cudaMalloc(&c->d_yt, sizeof(int32_t) * ntrain));
+    CU(cudaMemcpy(c->d_xbar, xbar, sizeof(double) * nfeat, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_scal, scalings, sizeof(double) * nfeat * 6, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_Zt, Ztrain, sizeof(double) * (size_t)ntrain * 6, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_yt, ytrain, sizeof(int32_t) * ntrain, cudaMemcpyHostToDevice));
+    c->knn_nfeat = nfeat; c->knn_ntrain = ntrain; c->knn_k = k;
+    return TSD_OK;
+}
+
+}  // extern "C"
+
+// ---- staging helpers for host-pointer calls ----------------------------------------------------------------------
+struct Stage {                                               // stream-ordered temporaries, freed on destruction
+    tsd_ctx* c;
+    std::vector<void*> ptrs;
+    explicit Stage(tsd_ctx* ctx) : c(ctx) {}
+    ~Stage() { for (void* p : ptrs) cudaFreeAsync(p, c->stream); }
+    int alloc(void** p, size_t bytes) {
+        CU(cudaMallocAsync(p, bytes ? bytes : 1, c->stream));
+        ptrs.push_back(*p);
+        return TSD_OK;
+    }
+    int in(const void* host, size_t bytes, void** dev) {
+        TRY(alloc(dev, bytes));
+        if (bytes) CU(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return TSD_OK;
+    }
+    int out(void* host, const void* dev, size_t bytes) {
+        if (bytes) CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return TSD_OK;
+    }
+};
+
+static HsvBounds bounds_of(const tsd_config& cfg) {
+    HsvBounds hb;
+    memcpy(hb.red_lo, cfg.red_lo, 6); memcpy(hb.red_hi, cfg.red_hi, 6);
+    memcpy(hb.blue_lo, cfg.blue_lo, 3); memcpy(hb.blue_hi, cfg.blue_hi, 3);
+    return hb;
+}
+
+// ---- device-pointer implementations --------------------------------------------------------------------------------
+static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, int32_t* coords, uint8_t* valid) {
+    if (n == 0) return TSD_OK;
+    k1_expand_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>((const int4*)boxes, n, enlarge - 1.0, c->cfg.aspect_lo, c->cfg.aspect_hi, (int4*)coords, valid);
+    return check_launch(c, "k1_expand");
+}
+
+static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
+                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows) {
+    if (n_max == 0) return TSD_OK;
+    if (ch == 3)
+        k2_crop_resize_kernel<3><<<cdiv(n_max, 4), 128, 0, c->stream>>>(frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max, D, windows);
+    else
+        k2_crop_resize_kernel<1><<<cdiv(n_max, 4), 128, 0, c->stream>>>(frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max, D, windows);
+    return check_launch(c, "k2_crop_resize");
+}
+
+static int dev_scan(tsd_ctx* c, const int32_t* counts, int n, int32_t* offsets) {
+    scan_offsets_kernel<<<1, 1024, 0, c->stream>>>(counts, n, offsets);
+    return check_launch(c, "scan_offsets");
+}
+
+// K1 count + scan + compact -> coords/win_frame/win_offsets in context scratch or caller buffers
+static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* box_offsets, int nframes, int H, int W, double enlarge,
+                             int32_t* counts, int32_t* win_offsets, int32_t* coords, int32_t* win_frame) {
+    const double pm1 = enlarge - 1.0;
+    k1_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, counts);
+    TRY(check_launch(c, "k1_count"));
+    TRY(dev_scan(c, counts, nframes, win_offsets));
+    k1_compact_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, win_offsets, (int4*)coords, win_frame);
+    return check_launch(c, "k1_compact");
+}
+
+static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, uint32_t* entries, WinMeta* meta) {
+    if (n_max == 0) return TSD_OK;
+    int grid = n_max < c->sm_count * 16 ? n_max : c->sm_count * 16;
+    k5_hist_kernel<<<grid, 128, 0, c->stream>>>(windows, n_ptr, n_max, npx, c->d_tab, entries, meta);
+    return check_launch(c, "k5_hist");
+}
+
+static int dev_fold(tsd_ctx* c, uint8_t* windows, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
+                    int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count) {
+    FoldParams P;
+    P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
+    P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
+    P.npx = npx; P.do_hist = do_hist; P.do_coords = do_coords;
+    P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
+    P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
+    if (nframes == 0) return TSD_OK;
+    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->stream>>>(P, nframes);
+    return check_launch(c, "k5_fold");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int tsd_expand_boxes(tsd_ctx* c, const int32_t* boxes, int nboxes, double enlarge, int32_t* coords, uint8_t* valid, int mem) {
+    if (!c || nboxes < 0 || (nboxes && (!boxes || !coords || !valid))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (mem == TSD_MEM_DEVICE) return dev_expand(c, boxes, nboxes, enlarge, coords, valid);
+    Stage s(c);
+    void *db, *dc, *dv;
+    TRY(s.in(boxes, (size_t)nboxes * 16, &db));
+    TRY(s.alloc(&dc, (size_t)nboxes * 16));
+    TRY(s.alloc(&dv, (size_t)nboxes));
+    TRY(dev_expand(c, (int32_t*)db, nboxes, enlarge, (int32_t*)dc, (uint8_t*)dv));
+    TRY(s.out(coords, dc, (size_t)nboxes * 16));
+    TRY(s.out(valid, dv, (size_t)nboxes));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride, int channels,
+                    const int32_t* coords, const int32_t* win_frame, int n, int D, uint8_t* windows, int mem) {
+    if (!c || !frames || nframes < 1 || H < 1 || W < 1 || n < 0 || (channels != 1 && channels != 3) || D < 2 || D > kMaxD)
+        return fail(TSD_E_INVALID, "bad argument");
+    if (row_stride < (int64_t)W * channels || frame_stride < row_stride * (H - 1) + (int64_t)W * channels) return fail(TSD_E_INVALID, "bad strides");
+    if (n && (!coords || !win_frame || !windows)) return fail(TSD_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows);
+    Stage s(c);
+    void *df, *dc, *dwf, *dw;
+    TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * channels, &df));
+    TRY(s.in(coords, (size_t)n * 16, &dc));
+    TRY(s.in(win_frame, (size_t)n * 4, &dwf));
+    TRY(s.alloc(&dw, (size_t)n * D * D * channels));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, channels, (int32_t*)dc, (int32_t*)dwf, nullptr, n, D, (uint8_t*)dw));
+    TRY(s.out(windows, dw, (size_t)n * D * D * channels));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int tsd_windows(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                const int32_t* boxes, const int32_t* box_offsets, double enlarge, int D, uint8_t* windows, int32_t* coords,
+                int32_t* win_offsets, int32_t* total, int mem) {
+    if (!c || !frames || !box_offsets || !win_offsets || nframes < 1 || D < 2 || D > kMaxD) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_windows takes host pointers; use tsd_enqueue_frames for device-resident batches");
+    CU(cudaSetDevice(c->device));
+    const int nb = box_offsets[nframes];
+    Stage s(c);
+    void *df, *db, *dbo, *dcnt, *dwo, *dc, *dwf, *dw;
+    TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3, &df));
+    TRY(s.in(boxes, (size_t)nb * 16, &db));
+    TRY(s.in(box_offsets, (size_t)(nframes + 1) * 4, &dbo));
+    TRY(s.alloc(&dcnt, (size_t)nframes * 4));
+    TRY(s.alloc(&dwo, (size_t)(nframes + 1) * 4));
+    TRY(s.alloc(&dc, (size_t)nb * 16));
+    TRY(s.alloc(&dwf, (size_t)nb * 4));
+    TRY(s.alloc(&dw, (size_t)nb * D * D * 3));
+    TRY(dev_windows_index(c, (int32_t*)db, (int32_t*)dbo, nframes, H, W, enlarge, (int32_t*)dcnt, (int32_t*)dwo, (int32_t*)dc, (int32_t*)dwf));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, 3, (int32_t*)dc, (int32_t*)dwf, (int32_t*)dwo + nframes, nb, D, (uint8_t*)dw));
+    TRY(s.out(win_offsets, dwo, (size_t)(nframes + 1) * 4));
+    CU(cudaStreamSynchronize(c->stream));
+    const int tot = win_offsets[nframes];
+    if (total) *total = tot;
+    if (tot) {
+        if (!windows || !coords) return fail(TSD_E_INVALID, "NULL output");
+        TRY(s.out(windows, dw, (size_t)tot * D * D * 3));
+        TRY(s.out(coords, dc, (size_t)tot * 16));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const int32_t* offsets, int nframes, int D, int by_coords,
+              double tol, uint8_t* out_windows, int32_t* out_coords, int32_t* out_offsets, int32_t* total_out, int mem) {
+    if (!c || !offsets || !out_offsets || nframes < 0 || D < 2 || D > kMaxD) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_dedup takes host pointers; use tsd_enqueue_frames for device-resident batches");
+    CU(cudaSetDevice(c->device));
+    const int n = offsets[nframes], npx = D * D, nbytes = npx * 3;
+    if (n && (!windows || !coords)) return fail(TSD_E_INVALID, "NULL argument");
+    Stage s(c);
+    void *dw, *dc, *doff, *dent, *dmeta, *dlist, *dflags, *dcnt, *dooff, *dow, *doc;
+    TRY(s.in(windows, (size_t)n * nbytes, &dw));
+    TRY(s.in(coords, (size_t)n * 16, &dc));
+    TRY(s.in(offsets, (size_t)(nframes + 1) * 4, &doff));
+    TRY(s.alloc(&dent, (size_t)n * npx * 4));
+    TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
+    TRY(s.alloc(&dlist, (size_t)n * 4));
+    TRY(s.alloc(&dflags, (size_t)n));
+    TRY(s.alloc(&dcnt, (size_t)(nframes + 1) * 4));
+    TRY(s.alloc(&dooff, (size_t)(nframes + 1) * 4));
+    TRY(s.alloc(&dow, (size_t)n * nbytes));
+    TRY(s.alloc(&doc, (size_t)n * 16));
+    if (n) {
+        if (by_coords) {
+            k5_hash_kernel<<<n, 128, 0, c->stream>>>((uint8_t*)dw, n, npx, (WinMeta*)dmeta);
+            TRY(check_launch(c, "k5_hash"));
+        } else {
+            TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta));
+        }
+    }
+    TRY(dev_fold(c, (uint8_t*)dw, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt));
+    TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
+    if (nframes) {
+        k5_gather_kernel<<<nframes, 128, 0, c->stream>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes,
+                                                         (uint8_t*)dow, (int4*)doc, nullptr);
+        TRY(check_launch(c, "k5_gather"));
+    }
+    TRY(s.out(out_offsets, dooff, (size_t)(nframes + 1) * 4));
+    CU(cudaStreamSynchronize(c->stream));
+    const int tot = out_offsets[nframes];
+    if (total_out) *total_out = tot;
+    if (tot) {
+        if (!out_windows || !out_coords) return fail(TSD_E_INVALID, "NULL output");
+        TRY(s.out(out_windows, dow, (size_t)tot * nbytes));
+        TRY(s.out(out_coords, doc, (size_t)tot * 16));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+int tsd_hist(tsd_ctx* c, const uint8_t* windows, int n, int D, float* hist, int mem) {
+    if (!c || n < 0 || D < 2 || D > kMaxD || (n && (!windows || !hist))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    const int npx = D * D;
+    Stage s(c);
+    void *dw = (void*)windows, *dh = (void*)hist, *dent, *dmeta;
+    if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dh, (size_t)n * kHistBins * 4)); }
+    TRY(s.alloc(&dent, (size_t)n * npx * 4));
+    TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
+    TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta));
+    hist_dense_kernel<<<n, 256, 0, c->stream>>>((uint32_t*)dent, (WinMeta*)dmeta, n, npx, (float*)dh);
+    TRY(check_launch(c, "hist_dense"));
+    if (mem == TSD_MEM_HOST) { TRY(s.out(hist, dh, (size_t)n * kHistBins * 4)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* red, uint8_t* blue, int mem) {
+    if (!c || n < 0 || D < 1 || (n && (!windows || !red || !blue))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    const int npx = D * D;
+    Stage s(c);
+    void *dw = (void*)windows, *dr = red, *db = blue;
+    if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx)); }
+    int grid = cdiv((int64_t)n * npx, 256);
+    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
+    k3_masks_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db);
+    TRY(check_launch(c, "k3_masks"));
+    if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+int tsd_bgr2hsv(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* hsv, int mem) {
+    if (!c || npx < 0 || (npx && (!bgr || !hsv))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (npx == 0) return TSD_OK;
+    Stage s(c);
+    void *di = (void*)bgr, *dout = hsv;
+    if (mem == TSD_MEM_HOST) { TRY(s.in(bgr, (size_t)npx * 3, &di)); TRY(s.alloc(&dout, (size_t)npx * 3)); }
+    int grid = cdiv(npx, 256);
+    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
+    bgr2hsv_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, npx, c->d_tab, (uint8_t*)dout);
+    TRY(check_launch(c, "bgr2hsv"));
+    if (mem == TSD_MEM_HOST) { TRY(s.out(hsv, dout, (size_t)npx * 3)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+int tsd_score_masks(tsd_ctx* c, const uint8_t* red, const uint8_t* blue, int n, int D, int32_t* scores, int32_t* id,
+                    int32_t* hundredths, uint8_t* emit, int mem) {
+    if (!c || n < 0 || (n && (!red || !blue || !id || !hundredths || !emit))) return fail(TSD_E_INVALID, "bad argument");
+    if (!c->have_templates) return fail(TSD_E_STATE, "templates not set (tsd_set_templates)");
+    if (D != c->tmpl_D) return fail(TSD_E_INVALID, "D=%d but templates are %dx%d", D, c->tmpl_D, c->tmpl_D);
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    const int npx = D * D;
+    Stage s(c);
+    void *dr = (void*)red, *db = (void*)blue, *ds = scores, *di = id, *dh = hundredths, *de = emit;
+    if (mem == TSD_MEM_HOST) {
+        TRY(s.in(red, (size_t)n * npx, &dr)); TRY(s.in(blue, (size_t)n * npx, &db));
+        if (scores) TRY(s.alloc(&ds, (size_t)n * 12 * 4));
+        TRY(s.alloc(&di, (size_t)n * 4)); TRY(s.alloc(&dh, (size_t)n * 4)); TRY(s.alloc(&de, (size_t)n));
+    }
+    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, c->d_tmpl,
+                                                                        c->cfg.score_tol_hundredths, (int32_t*)ds, (int32_t*)di, (int32_t*)dh, (uint8_t*)de);
+    TRY(check_launch(c, "k4_score"));
+    if (mem == TSD_MEM_HOST) {
+        if (scores) TRY(s.out(scores, ds, (size_t)n * 12 * 4));
+        TRY(s.out(id, di, (size_t)n * 4)); TRY(s.out(hundredths, dh, (size_t)n * 4)); TRY(s.out(emit, de, (size_t)n));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+int tsd_bgr2gray(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* gray, int mem) {
+    if (!c || npx < 0 || npx > 0x7fffffffLL || (npx && (!bgr || !gray))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (npx == 0) return TSD_OK;
+    Stage s(c);
+    void *di = (void*)bgr, *dout = gray;
+    if (mem == TSD_MEM_HOST) { TRY(s.in(bgr, (size_t)npx * 3, &di)); TRY(s.alloc(&dout, (size_t)npx)); }
+    int grid = cdiv(npx, 256);
+    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
+    k6_gray_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, nullptr, nullptr, 1, (int)npx, (uint8_t*)dout);
+    TRY(check_launch(c, "k6_gray"));
+    if (mem == TSD_MEM_HOST) { TRY(s.out(gray, dout, (size_t)npx)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+int tsd_hog(tsd_ctx* c, const uint8_t* gray, int n, float* desc, int mem) {
+    if (!c || n < 0 || (n && (!gray || !desc))) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    Stage s(c);
+    void *dg = (void*)gray, *dd = desc;
+    if (mem == TSD_MEM_HOST) { TRY(s.in(gray, (size_t)n * 1024, &dg)); TRY(s.alloc(&dd, (size_t)n * TSD_HOG_LEN * 4)); }
+    k7_hog_kernel<<<cdiv(n, kHogWarps), kHogWarps * 32, 0, c->stream>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dd);
+    TRY(check_launch(c, "k7_hog"));
+    if (mem == TSD_MEM_HOST) { TRY(s.out(desc, dd, (size_t)n * TSD_HOG_LEN * 4)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+static int dev_lda(tsd_ctx* c, const float* X, const int32_t* n_ptr, int n_max, double tol, double* logits, int32_t* labels) {
+    int grid = cdiv((int64_t)n_max * 32, 256);
+    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    k8_lda_kernel<<<grid, 256, (size_t)c->lda_nfeat * 6 * sizeof(double), c->stream>>>(X, n_ptr, n_max, c->lda_nfeat, c->d_ldaW, c->d_ldab, tol, logits, labels);
+    return check_launch(c, "k8_lda");
+}
+
+int tsd_lda_predict(tsd_ctx* c, const float* X, int n, double tol, double* logits, int32_t* labels, int mem) {
+    if (!c || n < 0 || (n && (!X || !labels))) return fail(TSD_E_INVALID, "bad argument");
+    if (!c->d_ldaW) return fail(TSD_E_STATE, "LDA weights not set (tsd_set_lda)");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    Stage s(c);
+    void *dx = (void*)X, *dl = logits, *dy = labels;
+    if (mem == TSD_MEM_HOST) {
+        TRY(s.in(X, (size_t)n * c->lda_nfeat * 4, &dx));
+        if (logits) TRY(s.alloc(&dl, (size_t)n * 6 * 8));
+        TRY(s.alloc(&dy, (size_t)n * 4));
+    }
+    TRY(dev_lda(c, (float*)dx, nullptr, n, tol, (double*)dl, (int32_t*)dy));
+    if (mem == TSD_MEM_HOST) {
+        if (logits) TRY(s.out(logits, dl, (size_t)n * 6 * 8));
+        TRY(s.out(labels, dy, (size_t)n * 4));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* labels, int mem) {
+    if (!c || n < 0 || (n && (!X || !labels))) return fail(TSD_E_INVALID, "bad argument");
+    if (!c->d_Zt) return fail(TSD_E_STATE, "KNN model not set (tsd_set_knn)");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    Stage s(c);
+    void *dx = (void*)X, *dz = Z, *dy = labels;
+    if (mem == TSD_MEM_HOST) {
+        TRY(s.in(X, (size_t)n * c->knn_nfeat * 4, &dx));
+        if (Z) TRY(s.alloc(&dz, (size_t)n * 6 * 8));
+        TRY(s.alloc(&dy, (size_t)n * 4));
+    }
+    k8_knn_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((float*)dx, n, c->knn_nfeat, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt,
+                                                                      c->knn_ntrain, c->knn_k, (double*)dz, (int32_t*)dy);
+    TRY(check_launch(c, "k8_knn"));
+    if (mem == TSD_MEM_HOST) {
+        if (Z) TRY(s.out(Z, dz, (size_t)n * 6 * 8));
+        TRY(s.out(labels, dy, (size_t)n * 4));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+// ---- whole chain -------------------------------------------------------------------------------------------------
+int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                       const int32_t* d_boxes, const int32_t* d_box_offsets, int nb) {
+    if (!c || !d_frames || !d_box_offsets || nframes < 1 || nb < 0 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
+    if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
+    if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
+    const int D = c->cfg.window, npx = D * D, nbytes = npx * 3;
+    if (mode == TSD_RUN_DETECT && (!c->have_templates || c->tmpl_D != D)) return fail(TSD_E_STATE, "templates not set for D=%d", D);
+    if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
+    CU(cudaSetDevice(c->device));
+    const size_t cap = nb > 0 ? nb : 1;
+    TRY(ensure(c, c->b_cnt, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_winoff, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_survcnt, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_survoff, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_detcnt, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_detoff, (size_t)(nframes + 1) * 4));
+    TRY(ensure(c, c->b_coords, cap * 16));
+    TRY(ensure(c, c->b_winframe, cap * 4));
+    TRY(ensure(c, c->b_windows, cap * nbytes));
+    TRY(ensure(c, c->b_entries, cap * npx * 4));
+    TRY(ensure(c, c->b_meta, cap * sizeof(WinMeta)));
+    TRY(ensure(c, c->b_list, cap * 4));
+    TRY(ensure(c, c->b_flags, cap));
+    TRY(ensure(c, c->b_slots, cap * 4));
+    TRY(ensure(c, c->b_id, cap * 4));
+    TRY(ensure(c, c->b_hund, cap * 4));
+    TRY(ensure(c, c->b_emit, cap));
+    TRY(ensure(c, c->b_det, cap * sizeof(DetRec)));
+    if (mode == TSD_RUN_DETECT) {
+        TRY(ensure(c, c->b_red, cap * npx));
+        TRY(ensure(c, c->b_blue, cap * npx));
+    } else {
+        TRY(ensure(c, c->b_gray, cap * npx));
+        TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
+    }
+    int32_t *cnt = (int32_t*)c->b_cnt.p, *winoff = (int32_t*)c->b_winoff.p, *survcnt = (int32_t*)c->b_survcnt.p, *survoff = (int32_t*)c->b_survoff.p;
+    int32_t *detcnt = (int32_t*)c->b_detcnt.p, *detoff = (int32_t*)c->b_detoff.p;
+    int32_t* coords = (int32_t*)c->b_coords.p;
+    uint8_t* windows = (uint8_t*)c->b_windows.p;
+    c->ev_used = 0;
+    mark(c, "start");
+    // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
+    TRY(dev_windows_index(c, d_boxes, d_box_offsets, nframes, H, W, c->cfg.enlarge, cnt, winoff, coords, (int32_t*)c->b_winframe.p));
+    mark(c, "k1_expand_filter");
+    const int32_t* d_nwin = winoff + nframes;
+    // K2 (DET:123-124)
+    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, (int32_t*)c->b_winframe.p, d_nwin, nb, D, windows));
+    mark(c, "k2_crop_resize");
+    // K5 (DET:127-129)
+    TRY(dev_hist(c, windows, d_nwin, nb, npx, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p));
+    mark(c, "k5_hist");
+    TRY(dev_fold(c, windows, coords, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, winoff, nframes, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
+                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt));
+    TRY(dev_scan(c, survcnt, nframes, survoff));
+    k5_gather_kernel<<<nframes, 32, 0, c->stream>>>(windows, (int4*)coords, winoff, (int32_t*)c->b_list.p, survoff, nframes, nbytes, nullptr, nullptr, (int32_t*)c->b_slots.p);
+    TRY(check_launch(c, "k5_gather"));
+    mark(c, "k5_fold");
+    const int32_t* d_nsurv = survoff + nframes;
+    if (mode == TSD_RUN_DETECT) {
+        // K3 + K4 (DET:708-716)
+        int grid = cdiv((int64_t)cap * npx, 256);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        k3_masks_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p);
+        TRY(check_launch(c, "k3_masks"));
+        mark(c, "k3_masks");
+        k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p, d_nsurv, nb, npx, c->d_tmpl,
+                                                                             c->cfg.score_tol_hundredths, nullptr, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
+        TRY(check_launch(c, "k4_score"));
+        mark(c, "k4_score");
+    } else {
+        int grid = cdiv((int64_t)cap * npx, 256);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        k6_gray_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, (uint8_t*)c->b_gray.p);
+        TRY(check_launch(c, "k6_gray"));
+        mark(c, "k6_gray");
+        k7_hog_kernel<<<cdiv(cap, kHogWarps), kHogWarps * 32, 0, c->stream>>>((uint8_t*)c->b_gray.p, d_nsurv, nb, c->hog, (float*)c->b_hog.p);
+        TRY(check_launch(c, "k7_hog"));
+        mark(c, "k7_hog");
+        TRY(dev_lda(c, (float*)c->b_hog.p, d_nsurv, nb, c->cfg.proba_tol, nullptr, (int32_t*)c->b_id.p));
+        mark(c, "k8_lda");
+        // a survivor becomes a record when the classifier says "sign" (label != 0); no score in this flavour
+        CU(cudaMemsetAsync(c->b_hund.p, 0, cap * 4, c->stream));
+        label_emit_kernel<<<cdiv(cap, 256), 256, 0, c->stream>>>((int32_t*)c->b_id.p, d_nsurv, nb, (uint8_t*)c->b_emit.p);
+        TRY(check_launch(c, "label_emit"));
+    }
+    det_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_emit.p, survoff, nframes, detcnt);
+    TRY(check_launch(c, "det_count"));
+    TRY(dev_scan(c, detcnt, nframes, detoff));
+    det_write_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_emit.p, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (int4*)coords,
+                                                                               (int32_t*)c->b_slots.p, survoff, detoff, nframes, (int)cap, (DetRec*)c->b_det.p);
+    TRY(check_launch(c, "det_write"));
+    mark(c, "detections");
+    c->last_nframes = nframes; c->last_mode = mode; c->last_nboxes = nb; c->last_detcap = (int)cap;
+    return TSD_OK;
+}
+
+int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
+    if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
+    if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
+    CU(cudaSetDevice(c->device));
+    const int F = c->last_nframes;
+    int32_t h[3];
+    CU(cudaMemcpyAsync(&h[0], (int32_t*)c->b_winoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&h[1], (int32_t*)c->b_survoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&h[2], (int32_t*)c->b_detoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (counts) { counts[0] = c->last_nboxes; counts[1] = h[0]; counts[2] = h[1]; counts[3] = h[2]; }
+    *ndet = h[2];
+    if (h[2] > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, h[2]);
+    if (h[2]) {
+        if (!det) return fail(TSD_E_INVALID, "det is NULL");
+        static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
+        CU(cudaMemcpyAsync(det, c->b_det.p, (size_t)h[2] * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return TSD_OK;
+}
+
+int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                      const int32_t* boxes, const int32_t* box_offsets, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts, int mem) {
+    if (!c || !frames || !box_offsets || nframes < 1) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (mem == TSD_MEM_DEVICE) {
+        int32_t nb = 0;
+        CU(cudaMemcpyAsync(&nb, box_offsets + nframes, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        TRY(tsd_enqueue_frames(c, mode, frames, nframes, H, W, row_stride, frame_stride, boxes, box_offsets, nb));
+        return tsd_fetch_detections(c, det, det_cap, ndet, counts);
+    }
+    const int nb = box_offsets[nframes];
+    if (nb && !boxes) return fail(TSD_E_INVALID, "boxes is NULL");
+    Stage s(c);
+    void *df, *db, *dbo;
+    TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3, &df));
+    TRY(s.in(boxes, (size_t)nb * 16, &db));
+    TRY(s.in(box_offsets, (size_t)(nframes + 1) * 4, &dbo));
+    TRY(tsd_enqueue_frames(c, mode, (uint8_t*)df, nframes, H, W, row_stride, frame_stride, (int32_t*)db, (int32_t*)dbo, nb));
+    return tsd_fetch_detections(c, det, det_cap, ndet, counts);
+}
+
+}  // extern "C"
+

@@ -1,0 +1,1013 @@
+// tsd_kernels.cuh -- hand-written sm_100a kernels of the candidate-window scoring and recognition path.
+//
+// One kernel per stage (BASELINE.json north_star).  Citations: DET = "Deteción de Objetos/source.py",
+// REC = "Reconocimiento de Objetos/source.py" of the reference; the cv2 / sklearn internals each kernel reproduces
+// are specified in SURVEY.md Appendix A.  Compiled with -fmad=false: f64/f32 steps round like the reference's
+// scalar numpy / OpenCV code (no FMA contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace tsd {
+
+constexpr int kHistH = 50, kHistS = 60, kHistBins = kHistH * kHistS;   // DET:578
+constexpr int kMaxD = 32;
+constexpr int kMaxPx = kMaxD * kMaxD;
+
+// ---- small tables (global memory, L2-resident; staged to shared memory by the kernels that index them per lane)
+struct Tables {
+    int32_t sdiv[256];      // rne((255<<12)/i)         OpenCV RGB2HSV_b
+    int32_t hdiv[256];      // rne((180<<12)/(6 i))
+    uint8_t hbin[256];      // floor(H * 50/180)        calcHist LUT (only 0..179 used)
+    uint8_t sbin[256];      // floor(S * 60/256)
+};
+
+struct HsvBounds {          // DET:70-86
+    uint8_t red_lo[2][3], red_hi[2][3], blue_lo[3], blue_hi[3];
+};
+
+__device__ __forceinline__ void bgr2hsv(int b, int g, int r, const int32_t* __restrict__ sdiv,
+                                        const int32_t* __restrict__ hdiv, int& H, int& S, int& V) {
+    int v = max(b, max(g, r)), m = min(b, min(g, r));
+    int d = v - m;
+    int h = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * d) : (r - g + 4 * d);
+    S = (d * sdiv[v] + (1 << 11)) >> 12;
+    h = (h * hdiv[d] + (1 << 11)) >> 12;
+    H = h < 0 ? h + 180 : h;
+    V = v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =====================================================================================================
+// K1  makeWindowBiggerOrDiscardFakeDetections  (DET:155-174 = REC:88-107), SURVEY A.1.  f64, no FMA.
+// =====================================================================================================
+__device__ __forceinline__ bool expand_box(int4 b, double pm1, double alo, double ahi, int4& out) {
+    double w = (double)b.z, h = (double)b.w;
+    double ratio = __ddiv_rn(w, h);
+    if (!(alo < ratio && ratio < ahi)) return false;
+    double dw = __dmul_rn(__dmul_rn(w, pm1), 0.5), dh = __dmul_rn(__dmul_rn(h, pm1), 0.5);
+    double x1 = __dsub_rn((double)b.x, dw), y1 = __dsub_rn((double)b.y, dh);
+    double x2 = __dadd_rn((double)(b.x + b.z), dw), y2 = __dadd_rn((double)(b.y + b.w), dh);
+    x1 = x1 > 0 ? x1 : 0; y1 = y1 > 0 ? y1 : 0; x2 = x2 > 0 ? x2 : 0; y2 = y2 > 0 ? y2 : 0;
+    out = make_int4((int)x1, (int)y1, (int)x2, (int)y2);     // int(): truncation
+    return true;
+}
+
+// one result per box (per-stage parity entry point tsd_expand_boxes)
+__global__ void k1_expand_kernel(const int4* __restrict__ boxes, int n, double pm1, double alo, double ahi,
+                                 int4* __restrict__ coords, uint8_t* __restrict__ valid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 c = make_int4(0, 0, 0, 0);
+    bool ok = expand_box(boxes[i], pm1, alo, ahi, c);
+    coords[i] = c;
+    valid[i] = ok ? 1 : 0;
+}
+
+// per frame: count of aspect-passing boxes whose (frame-clipped) crop is not empty.  One warp per frame.
+__global__ void k1_count_kernel(const int4* __restrict__ boxes, const int32_t* __restrict__ box_offsets, int nframes,
+                                int H, int W, double pm1, double alo, double ahi, int32_t* __restrict__ counts) {
+    int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= nframes) return;
+    int b0 = box_offsets[f], b1 = box_offsets[f + 1], cnt = 0;
+    for (int i = b0 + lane; i < b1; i += 32) {
+        int4 c;
+        if (expand_box(boxes[i], pm1, alo, ahi, c) && min(c.z, W) > min(c.x, W) && min(c.w, H) > min(c.y, H)) cnt++;
+    }
+    cnt = warp_sum_i(cnt);
+    if (lane == 0) counts[f] = cnt;
+}
+
+// exclusive scan of counts[0..n) -> offsets[0..n]; single CTA (n = number of frames; small)
+__global__ void scan_offsets_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
+    __shared__ int32_t wsum[32];
+    __shared__ int32_t carry;
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + tid;
+        int v = i < n ? counts[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        int pre = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (i < n) offsets[i] = pre;
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry = pre + v;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry;
+}
+
+// order-preserving compaction: coords of passing boxes -> coords[win_offsets[f] + rank], win_frame[...] = f.
+__global__ void k1_compact_kernel(const int4* __restrict__ boxes, const int32_t* __restrict__ box_offsets, int nframes,
+                                  int H, int W, double pm1, double alo, double ahi,
+                                  const int32_t* __restrict__ win_offsets, int4* __restrict__ coords,
+                                  int32_t* __restrict__ win_frame) {
+    int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= nframes) return;
+    int b0 = box_offsets[f], b1 = box_offsets[f + 1], out = win_offsets[f];
+    for (int base = b0; base < b1; base += 32) {
+        int i = base + lane;
+        int4 c = make_int4(0, 0, 0, 0);
+        bool ok = false;
+        if (i < b1) ok = expand_box(boxes[i], pm1, alo, ahi, c) && min(c.z, W) > min(c.x, W) && min(c.w, H) > min(c.y, H);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            int r = out + __popc(m & ((1u << lane) - 1));
+            coords[r] = c;
+            win_frame[r] = f;
+        }
+        out += __popc(m);
+    }
+}
+
+// =====================================================================================================
+// K2  cv2.resize(cropImageByCoords(coords, frame), (D, D))  (DET:123-124,570-572; REC:57,253-254), SURVEY A.2.
+// One warp per window.  The crop is the numpy slice frame[y1:y2, x1:x2] clipped to the frame; three code paths:
+// same-size copy, exact 2x2 INTER_AREA, general two-pass 11-bit fixed point (x coefficient clamp, y row clip).
+// v1: taps are gathered straight from global memory through L1 (a window's ROI is ~5 KB and stays L1-resident).
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(128) k2_crop_resize_kernel(
+    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
+    int D, uint8_t* __restrict__ windows) {
+    __shared__ int16_t s_xo[4][kMaxD], s_xa0[4][kMaxD], s_xa1[4][kMaxD];
+    __shared__ int16_t s_y0[4][kMaxD], s_y1[4][kMaxD], s_yb0[4][kMaxD], s_yb1[4][kMaxD];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + wl;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const int4 c = coords[w];
+    const int cx = min(c.x, W), cy = min(c.y, H);
+    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
+    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
+    uint8_t* __restrict__ dst = windows + (int64_t)w * D * D * C;
+    const int rowlen = D * C, total = D * rowlen;
+    if (cw <= 0 || ch <= 0) return;                         // filtered out by K1 (cv2.resize would raise)
+    if (cw == D && ch == D) {                               // same size: copy
+        for (int i = lane; i < total; i += 32) { int y = i / rowlen, r = i - y * rowlen; dst[i] = src[(int64_t)y * row_stride + r]; }
+        return;
+    }
+    if (cw == 2 * D && ch == 2 * D) {                       // INTER_AREA 2x2 fast path
+        for (int i = lane; i < total; i += 32) {
+            int y = i / rowlen, r = i - y * rowlen, x = r / C, k = r - x * C;
+            const uint8_t* p = src + (int64_t)(2 * y) * row_stride + (2 * x) * C + k;
+            dst[i] = (uint8_t)((p[0] + p[C] + p[row_stride] + p[row_stride + C] + 2) >> 2);
+        }
+        return;
+    }
+    if (lane < D) {                                         // coefficient tables (float32 rounding as in OpenCV)
+        {
+            double scale = 1.0 / ((double)D / (double)cw);
+            float f = (float)(((double)lane + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= cw - 1) { f = 0.f; s = cw - 1; }
+            s_xo[wl][lane] = (int16_t)s;
+            s_xa0[wl][lane] = (int16_t)__float2int_rn((1.f - f) * 2048.f);
+            s_xa1[wl][lane] = (int16_t)__float2int_rn(f * 2048.f);
+        }
+        {
+            double scale = 1.0 / ((double)D / (double)ch);
+            float f = (float)(((double)lane + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            s_y0[wl][lane] = (int16_t)min(max(s, 0), ch - 1);
+            s_y1[wl][lane] = (int16_t)min(max(s + 1, 0), ch - 1);
+            s_yb0[wl][lane] = (int16_t)__float2int_rn((1.f - f) * 2048.f);
+            s_yb1[wl][lane] = (int16_t)__float2int_rn(f * 2048.f);
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        int y = i / rowlen, r = i - y * rowlen, x = r / C, k = r - x * C;
+        int s0 = s_xo[wl][x], s1 = min(s0 + 1, cw - 1);
+        int a0 = s_xa0[wl][x], a1 = s_xa1[wl][x];
+        const uint8_t* S0 = src + (int64_t)s_y0[wl][y] * row_stride;
+        const uint8_t* S1 = src + (int64_t)s_y1[wl][y] * row_stride;
+        int t0 = S0[s0 * C + k] * a0 + S0[s1 * C + k] * a1;
+        int t1 = S1[s0 * C + k] * a0 + S1[s1 * C + k] * a1;
+        int v = (((s_yb0[wl][y] * (t0 >> 4)) >> 16) + ((s_yb1[wl][y] * (t1 >> 4)) >> 16) + 2) >> 2;
+        dst[i] = (uint8_t)v;
+    }
+}
+
+// =====================================================================================================
+// K3  getColorMaskRedOrBlue(img,'r'/'b')  (DET:63-89), SURVEY A.3.  One thread per pixel; integer HSV tables.
+// `slots` (optional) = indirection to the surviving windows inside the work buffer.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k3_masks_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
+                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx,
+                                                       const Tables* __restrict__ tab, HsvBounds hb,
+                                                       uint8_t* __restrict__ red, uint8_t* __restrict__ blue) {
+    __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    s_sdiv[threadIdx.x & 255] = tab->sdiv[threadIdx.x & 255];
+    s_hdiv[threadIdx.x & 255] = tab->hdiv[threadIdx.x & 255];
+    __syncthreads();
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int64_t total = (int64_t)n * npx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = (int)(i / npx), p = (int)(i - (int64_t)w * npx);
+        int slot = slots ? slots[w] : w;
+        const uint8_t* px = windows + ((int64_t)slot * npx + p) * 3;
+        int H, S, V;
+        bgr2hsv(px[0], px[1], px[2], s_sdiv, s_hdiv, H, S, V);
+        bool r0 = H >= hb.red_lo[0][0] && H <= hb.red_hi[0][0] && S >= hb.red_lo[0][1] && S <= hb.red_hi[0][1] &&
+                  V >= hb.red_lo[0][2] && V <= hb.red_hi[0][2];
+        bool r1 = H >= hb.red_lo[1][0] && H <= hb.red_hi[1][0] && S >= hb.red_lo[1][1] && S <= hb.red_hi[1][1] &&
+                  V >= hb.red_lo[1][2] && V <= hb.red_hi[1][2];
+        bool bl = H >= hb.blue_lo[0] && H <= hb.blue_hi[0] && S >= hb.blue_lo[1] && S <= hb.blue_hi[1] &&
+                  V >= hb.blue_lo[2] && V <= hb.blue_hi[2];
+        red[i] = (r0 || r1) ? 255 : 0;                      // cv2.add saturates
+        blue[i] = bl ? 255 : 0;
+    }
+}
+
+__global__ void bgr2hsv_kernel(const uint8_t* __restrict__ bgr, int64_t npx, const Tables* __restrict__ tab,
+                               uint8_t* __restrict__ hsv) {
+    __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    s_sdiv[threadIdx.x & 255] = tab->sdiv[threadIdx.x & 255];
+    s_hdiv[threadIdx.x & 255] = tab->hdiv[threadIdx.x & 255];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (int64_t)gridDim.x * blockDim.x) {
+        int H, S, V;
+        bgr2hsv(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2], s_sdiv, s_hdiv, H, S, V);
+        hsv[3 * i] = (uint8_t)H; hsv[3 * i + 1] = (uint8_t)S; hsv[3 * i + 2] = (uint8_t)V;
+    }
+}
+
+// =====================================================================================================
+// K4  getSimilarSignalType x2 + detectionsMaskCorrelation decision  (DET:229-261,545-567), SURVEY A.4.
+// mask*template wraps to {0,1} so FP == 0, FN = T - TP, TN = npx - T: the score depends on (TP, template) only.
+// Templates are bit-packed (32 px / word); lut[k][TP] = hundredths of round(2TP/(TP+T_k), 2) or 0 when the
+// template is degenerate -- built on the host with the reference's own arithmetic.
+// One warp per window: 32 mask bytes -> one ballot word; lane k < 12 accumulates popc(word & template_k).
+// =====================================================================================================
+struct ScoreTemplates {
+    uint32_t bits[12][kMaxPx / 32];      // [0..5] red, [6..11] blue
+    uint8_t lut[12][kMaxPx + 1];
+};
+
+__global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict__ red, const uint8_t* __restrict__ blue,
+                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx,
+                                                       const ScoreTemplates* __restrict__ tmpl, int tol_hundredths,
+                                                       int32_t* __restrict__ scores, int32_t* __restrict__ id,
+                                                       int32_t* __restrict__ hundredths, uint8_t* __restrict__ emit) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const uint8_t* r = red + (int64_t)w * npx;
+    const uint8_t* b = blue + (int64_t)w * npx;
+    const int nwords = (npx + 31) >> 5;
+    int tp = 0;
+    for (int i = 0; i < nwords; i++) {
+        int p = i * 32 + lane;
+        unsigned wr = __ballot_sync(0xffffffffu, p < npx && r[p] != 0);
+        unsigned wb = __ballot_sync(0xffffffffu, p < npx && b[p] != 0);
+        if (lane < 12) tp += __popc((lane < 6 ? wr : wb) & tmpl->bits[lane][i]);
+    }
+    int sc = lane < 12 ? (int)tmpl->lut[lane][tp] : -1;
+    if (scores && lane < 12) scores[(int64_t)w * 12 + lane] = sc;
+    // first strict maximum within each group of 6 (DET:249-259)
+    int best_r = -1, id_r = 0, best_b = -1, id_b = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int sr = __shfl_sync(0xffffffffu, sc, k), sb = __shfl_sync(0xffffffffu, sc, 6 + k);
+        if (sr > best_r) { best_r = sr; id_r = k + 1; }
+        if (sb > best_b) { best_b = sb; id_b = k + 1; }
+    }
+    if (lane == 0) {
+        bool red_wins = best_r > best_b;                    // tie -> blue (DET:236)
+        int s = red_wins ? best_r : best_b;
+        id[w] = red_wins ? id_r : id_b;
+        hundredths[w] = s;
+        emit[w] = s > tol_hundredths ? 1 : 0;
+    }
+}
+
+// =====================================================================================================
+// K5  cleanDuplicatedDetections (DET:177-223) -- SURVEY A.5.
+// Per-window sparse H-S histogram record (calculateHistAndNormalize DET:575-586):
+//   entries (bin << 16 | count), sorted by bin; a = (float)(1/max) ; h[bin] = (float)count * a  (min is always 0
+//   because npx <= 1024 < 3000 bins, so the MINMAX shift is +0);  s1 = sum h, s11 = sum h^2 in f64;
+//   hash = 64-bit hash of the pixels (used only to pre-filter the pop-by-pixel-equality rule DET:471-477).
+// =====================================================================================================
+struct WinMeta {
+    double s1, s11;
+    unsigned long long hash;
+    float a;
+    int32_t nnz;
+};
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// Block-wide: histogram of one window.  dense[kHistBins] (shared, zero on entry, left holding the counts),
+// red[] = shared scratch of >= 64 doubles.  Writes entries + meta for `slot`.  All threads must call.
+__device__ void build_hist_block(const uint8_t* __restrict__ px, int npx, const int32_t* s_sdiv, const int32_t* s_hdiv,
+                                 const uint8_t* s_hbin, const uint8_t* s_sbin, uint32_t* dense, double* red,
+                                 uint32_t* __restrict__ entries, WinMeta* __restrict__ meta) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    unsigned long long hsh = 0;
+    for (int p = tid; p < npx; p += nt) {
+        int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
+        int H, S, V;
+        bgr2hsv(b, g, r, s_sdiv, s_hdiv, H, S, V);
+        atomicAdd(&dense[(int)s_hbin[H] * kHistS + (int)s_sbin[S]], 1u);
+        hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(b | (g << 8) | (r << 16)));
+    }
+    // hash: order-independent sum of per-pixel mixes
+    unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
+    // reduce hash with 64-bit adds through shuffles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
+        hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
+    }
+    unsigned long long* red_u = reinterpret_cast<unsigned long long*>(red);
+    __syncthreads();
+    if (lane == 0) red_u[wid] = hsh;
+    __syncthreads();
+    unsigned long long hash_all = 0;
+    for (int i = 0; i < nw; i++) hash_all += red_u[i];
+    __syncthreads();
+    // max count + per-warp nnz over contiguous bin ranges (deterministic, sorted-by-bin output)
+    const int per_warp = (kHistBins + nw - 1) / nw;
+    const int b0 = wid * per_warp, b1 = min(kHistBins, b0 + per_warp);
+    unsigned mx = 0; int cnt = 0;
+    for (int b = b0 + lane; b < b1; b += 32) { unsigned c = dense[b]; mx = max(mx, c); cnt += c != 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    int* red_i = reinterpret_cast<int*>(red);
+    if (lane == 0) { red_i[wid] = (int)mx; red_i[32 + wid] = cnt; }
+    __syncthreads();
+    unsigned mx_all = 0; int base = 0, nnz = 0;
+    for (int i = 0; i < nw; i++) { mx_all = max(mx_all, (unsigned)red_i[i]); if (i < wid) base += red_i[32 + i]; nnz += red_i[32 + i]; }
+    __syncthreads();
+    // normalize: scale = 1/(max-min) in f64, a = (float)scale (cv2.normalize NORM_MINMAX -> convertTo)
+    double scale = ((double)mx_all - 0.0) > DBL_EPSILON ? 1.0 / ((double)mx_all - 0.0) : 0.0;
+    float a = (float)scale;
+    double s1 = 0, s11 = 0;
+    int outp = base;
+    for (int bb = b0; bb < b1; bb += 32) {
+        int b = bb + lane;
+        unsigned c = b < b1 ? dense[b] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, c != 0);
+        if (c) {
+            entries[outp + __popc(m & ((1u << lane) - 1))] = ((uint32_t)b << 16) | c;
+            double h = (double)((float)c * a);
+            s1 += h; s11 += h * h;
+        }
+        outp += __popc(m);
+    }
+    s1 = warp_sum(s1); s11 = warp_sum(s11);
+    if (lane == 0) { red[wid] = s1; red[32 + wid] = s11; }
+    __syncthreads();
+    if (tid == 0) {
+        double t1 = 0, t11 = 0;
+        for (int i = 0; i < nw; i++) { t1 += red[i]; t11 += red[32 + i]; }
+        meta->s1 = t1; meta->s11 = t11; meta->hash = hash_all; meta->a = a; meta->nnz = nnz;
+    }
+    __syncthreads();
+}
+
+// zero the dense histogram entries listed in `entries` (cheaper than clearing all 3000 bins)
+__device__ __forceinline__ void clear_dense_block(uint32_t* dense, const uint32_t* __restrict__ entries, int nnz) {
+    for (int e = threadIdx.x; e < nnz; e += blockDim.x) dense[entries[e] >> 16] = 0;
+}
+
+struct HistSmem {
+    int32_t sdiv[256], hdiv[256];
+    uint8_t hbin[256], sbin[256];
+    uint32_t dense[kHistBins];
+    double red[64];
+};
+
+__device__ __forceinline__ void load_tables_block(HistSmem& sm, const Tables* __restrict__ tab) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sm.sdiv[i] = tab->sdiv[i]; sm.hdiv[i] = tab->hdiv[i]; sm.hbin[i] = tab->hbin[i]; sm.sbin[i] = tab->sbin[i];
+    }
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sm.dense[i] = 0;
+}
+
+// K5a: sparse histogram + meta of every window (one CTA of 128 threads per window, grid-stride).
+__global__ void __launch_bounds__(128) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
+                                                      int n_max, int npx, const Tables* __restrict__ tab,
+                                                      uint32_t* __restrict__ entries, WinMeta* __restrict__ meta) {
+    __shared__ HistSmem sm;
+    load_tables_block(sm, tab);
+    __syncthreads();
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        uint32_t* e = entries + (int64_t)w * npx;
+        build_hist_block(windows + (int64_t)w * npx * 3, npx, sm.sdiv, sm.hdiv, sm.hbin, sm.sbin, sm.dense, sm.red, e, meta + w);
+        clear_dense_block(sm.dense, e, meta[w].nnz);
+        __syncthreads();
+    }
+}
+
+// dense float32 [n][50][60] normalised histograms (tsd_hist, parity artefact of calculateHistAndNormalize)
+__global__ void hist_dense_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta, int n, int npx,
+                                  float* __restrict__ out) {
+    int w = blockIdx.x;
+    if (w >= n) return;
+    float* o = out + (int64_t)w * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) o[i] = 0.f;
+    __syncthreads();
+    const uint32_t* e = entries + (int64_t)w * npx;
+    float a = meta[w].a;
+    for (int i = threadIdx.x; i < meta[w].nnz; i += blockDim.x) o[e[i] >> 16] = (float)(e[i] & 0xffffu) * a;
+}
+
+// pixel hash only (pass-2-only entry point)
+__global__ void __launch_bounds__(128) k5_hash_kernel(const uint8_t* __restrict__ windows, int n, int npx, WinMeta* __restrict__ meta) {
+    __shared__ unsigned long long red_u[4];
+    int w = blockIdx.x;
+    if (w >= n) return;
+    const uint8_t* px = windows + (int64_t)w * npx * 3;
+    unsigned long long hsh = 0;
+    for (int p = threadIdx.x; p < npx; p += blockDim.x)
+        hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(px[3 * p] | (px[3 * p + 1] << 8) | (px[3 * p + 2] << 16)));
+    unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
+        hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
+    }
+    if ((threadIdx.x & 31) == 0) red_u[threadIdx.x >> 5] = hsh;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red_u[i]; meta[w].hash = t; }
+}
+
+// ---- the fold ----------------------------------------------------------------------------------------
+struct FoldParams {
+    uint8_t* windows;            // work buffer [n][npx*3]; merged items are averaged IN PLACE in the item's slot
+    int4* coords;                // [n]; merged coords are written in place
+    uint32_t* entries;           // [n][npx] sparse histograms
+    WinMeta* meta;               // [n]
+    const int32_t* offsets;      // [nframes+1] CSR of the input windows
+    int32_t* list;               // [n] scratch: per frame, list positions -> slot (frame's region = its CSR range)
+    uint8_t* flags;              // [n] scratch: deletion marks per list position
+    int32_t* out_count;          // [nframes] survivors per frame
+    const double* simtab;        // f(d2), d2 < simtab_n (DET:459-462)
+    int simtab_n;
+    const Tables* tab;
+    int npx;
+    int do_hist, do_coords;      // which passes to run (DET:127 then DET:129)
+    double hist_tol, hist_lo, coord_tol, coord_lo;   // lo = tol * 0.8823 (DET:217), computed on the host in f64
+};
+
+constexpr int kFoldThreads = 256;
+constexpr int kFoldChunk = 1024;
+
+struct FoldSmem {
+    HistSmem h;
+    uint8_t cls[kFoldChunk];
+    int first_merge;
+    int any_del;
+    int S;
+    int4 icoords;
+    int victim;
+};
+
+__device__ __forceinline__ double coord_sim(int4 a, int4 b, const double* __restrict__ simtab, int simtab_n) {
+    long long dx = (long long)a.x - b.x, dy = (long long)a.y - b.y, ex = (long long)a.z - b.z, ey = (long long)a.w - b.w;
+    long long d1 = dx * dx + dy * dy, d2 = ex * ex + ey * ey;
+    if (d1 >= simtab_n || d2 >= simtab_n) return 0.0;      // f < 0.16 beyond the table: sqrt(f1 f2) < 0.4 < tol*0.8823
+    return __dsqrt_rn(__dmul_rn(simtab[d1], simtab[d2]));
+}
+
+// pop-by-pixel-equality (DET:183-185,471-477): for each marked position, in list order, remove the FIRST live entry
+// whose pixels equal the marked one's.  Then compact the list.  Block-wide; returns the new length in sm.S.
+__device__ void apply_deletions_block(FoldSmem& sm, const FoldParams& P, int32_t* list, uint8_t* flags, int nbytes) {
+    const int tid = threadIdx.x;
+    const int S = sm.S;
+    // flags: 1 = marked for deletion (by scan), 2 = dead (already removed).  Process marks in increasing position.
+    for (int p = 0; p < S; p++) {
+        if (flags[p] != 1) continue;                        // uniform across the block (global memory, synced)
+        const int slot_d = list[p];
+        const unsigned long long hd = P.meta[slot_d].hash;
+        if (tid == 0) sm.victim = p;
+        __syncthreads();
+        // earlier live entries (flag 0 or 1) with equal hash -> verify bytes; smallest position wins
+        for (int q = tid; q < p; q += blockDim.x) {
+            if (flags[q] != 2 && P.meta[list[q]].hash == hd) {
+                const uint8_t* A = P.windows + (int64_t)list[q] * nbytes;
+                const uint8_t* B = P.windows + (int64_t)slot_d * nbytes;
+                bool eq = true;
+                for (int i = 0; i < nbytes; i++) if (A[i] != B[i]) { eq = false; break; }
+                if (eq) atomicMin(&sm.victim, q);
+            }
+        }
+        __syncthreads();
+        const int v = sm.victim;
+        __syncthreads();
+        if (tid == 0) {
+            // the victim leaves the list; if it was itself marked, that mark is consumed with it and the entry at p
+            // stays pending only if v != p -- in the reference the second pop then removes the next equal entry,
+            // which is p itself once v is gone (v's own mark, processed earlier, cannot exist since v < p was live+unprocessed
+            // only if unmarked or marked-later; marks are processed in order, so a marked v < p was already handled).
+            flags[v] = 2;
+            if (v != p) flags[p] = 0;                       // p survives (its twin was popped instead)
+        }
+        __syncthreads();
+    }
+    // compaction by warp 0, order preserving
+    if (tid < 32) {
+        int outp = 0;
+        for (int base = 0; base < S; base += 32) {
+            int p = base + tid;
+            bool live = p < S && flags[p] != 2;
+            int slot = p < S ? list[p] : 0;
+            unsigned m = __ballot_sync(0xffffffffu, live);
+            __syncwarp();
+            if (live) list[outp + __popc(m & ((1u << tid) - 1))] = slot;
+            outp += __popc(m);
+            __syncwarp();
+        }
+        if (tid == 0) sm.S = outp;
+    }
+    __syncthreads();
+    for (int p = tid; p < S; p += blockDim.x) flags[p] = 0;
+    __syncthreads();
+}
+
+// One CTA per frame.  Sequential over the frame's items (the fold order is the semantics); each item is compared
+// with ALL current survivors in parallel, the classes are scanned in list order up to the first merge, the merge is
+// applied and only the survivors after it are re-evaluated with the updated item (speculate-then-scan).
+__global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int nframes) {
+    __shared__ FoldSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = kFoldThreads >> 5;
+    const int nbytes = P.npx * 3;
+    if (P.do_hist) load_tables_block(sm.h, P.tab);
+    if (tid == 0) sm.any_del = 0;
+    __syncthreads();
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const int base = P.offsets[f], n = P.offsets[f + 1] - base;
+        int32_t* list = P.list + base;
+        uint8_t* flags = P.flags + base;
+        for (int p = tid; p < n; p += blockDim.x) flags[p] = 0;
+        if (tid == 0) sm.S = 0;
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+            const bool by_coords = pass == 1;
+            if (by_coords ? !P.do_coords : !P.do_hist) continue;
+            const double tol = by_coords ? P.coord_tol : P.hist_tol, lo = by_coords ? P.coord_lo : P.hist_lo;
+            // items of this pass: pass 0 (or coords-only) -> slots base..base+n-1 in order; pass 1 after pass 0 -> the
+            // survivors of pass 0, which we first move aside to the tail of the scratch region as the "input" order.
+            // To avoid a second array the input order is read from `list` itself: survivors of pass 0 occupy
+            // list[0..S0) and pass 1 rebuilds the list in place (the write index never passes the read index).
+            const bool from_list = by_coords && P.do_hist;
+            const int nin = from_list ? sm.S : n;
+            __syncthreads();
+            if (tid == 0) sm.S = 0;
+            __syncthreads();
+            for (int it = 0; it < nin; it++) {
+                const int slot = from_list ? list[it] : base + it;
+                __syncthreads();                            // list[it] read before anyone overwrites it below
+                uint8_t* ipx = P.windows + (int64_t)slot * nbytes;
+                uint32_t* ient = P.entries + (int64_t)slot * P.npx;
+                if (tid == 0) sm.icoords = P.coords[slot];
+                if (!by_coords) {
+                    const int nnz = P.meta[slot].nnz;
+                    for (int e = tid; e < nnz; e += blockDim.x) { uint32_t v = ient[e]; sm.h.dense[v >> 16] = v & 0xffffu; }
+                }
+                __syncthreads();
+                int start = 0;
+                while (start < sm.S) {
+                    const int S = sm.S;
+                    const int end = min(S, start + kFoldChunk);
+                    if (tid == 0) sm.first_merge = 0x7fffffff;
+                    __syncthreads();
+                    if (by_coords) {
+                        const int4 ic = sm.icoords;
+                        for (int p = start + tid; p < end; p += blockDim.x) {
+                            double sim = coord_sim(ic, P.coords[list[p]], P.simtab, P.simtab_n);
+                            int c = sim > tol ? 1 : (lo <= sim && sim <= tol) ? 2 : 0;
+                            sm.cls[p - start] = (uint8_t)c;
+                            if (c == 2) atomicMin(&sm.first_merge, p);
+                        }
+                    } else {
+                        const WinMeta mi = P.meta[slot];
+                        for (int p = start + wid; p < end; p += nw) {
+                            const int sj = list[p];
+                            const WinMeta mj = P.meta[sj];
+                            const uint32_t* ej = P.entries + (int64_t)sj * P.npx;
+                            double s12 = 0;
+                            for (int e = lane; e < mj.nnz; e += 32) {
+                                uint32_t v = ej[e];
+                                float hi = (float)sm.h.dense[v >> 16] * mi.a;
+                                float hj = (float)(v & 0xffffu) * mj.a;
+                                s12 += (double)hi * (double)hj;
+                            }
+                            s12 = warp_sum(s12);
+                            if (lane == 0) {
+                                // cv2.compareHist CORREL (DET:200-202): h1 = item, h2 = survivor
+                                const double scale = 1.0 / (double)kHistBins;
+                                double num = s12 - mi.s1 * mj.s1 * scale;
+                                double den2 = (mi.s11 - mi.s1 * mi.s1 * scale) * (mj.s11 - mj.s1 * mj.s1 * scale);
+                                double sim = fabs(den2) > DBL_EPSILON ? num / sqrt(den2) : 1.0;
+                                int c = sim > tol ? 1 : (lo <= sim && sim <= tol) ? 2 : 0;
+                                sm.cls[p - start] = (uint8_t)c;
+                                if (c == 2) atomicMin(&sm.first_merge, p);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int fm = sm.first_merge;
+                    const int lim = min(fm, end);
+                    for (int p = start + tid; p < lim; p += blockDim.x)
+                        if (sm.cls[p - start] == 1) { flags[p] = 1; sm.any_del = 1; }
+                    if (fm < end) {
+                        // merge (DET:217-221): pixels = addWeighted(.5,.5) round-half-even, coords = floor mean
+                        const int sk = list[fm];
+                        const uint8_t* kpx = P.windows + (int64_t)sk * nbytes;
+                        if (!by_coords) clear_dense_block(sm.h.dense, ient, P.meta[slot].nnz);
+                        for (int i = tid; i < nbytes; i += blockDim.x) {
+                            int s = ipx[i] + kpx[i];
+                            ipx[i] = (uint8_t)((s >> 1) + ((s & 1) & ((s >> 1) & 1)));
+                        }
+                        if (tid == 0) {
+                            int4 a = sm.icoords, b = P.coords[sk];
+                            // Python // on ints (coords are >= 0)
+                            sm.icoords = make_int4((a.x + b.x) >> 1, (a.y + b.y) >> 1, (a.z + b.z) >> 1, (a.w + b.w) >> 1);
+                            flags[fm] = 1; sm.any_del = 1;
+                        }
+                        __syncthreads();
+                        if (!by_coords) {
+                            build_hist_block(ipx, P.npx, sm.h.sdiv, sm.h.hdiv, sm.h.hbin, sm.h.sbin, sm.h.dense, sm.h.red, ient, P.meta + slot);
+                        } else {
+                            // keep the pixel hash current for the pop-by-equality rule
+                            unsigned long long hsh = 0;
+                            for (int p = tid; p < P.npx; p += blockDim.x)
+                                hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(ipx[3 * p] | (ipx[3 * p + 1] << 8) | (ipx[3 * p + 2] << 16)));
+                            unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
+                                hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
+                            }
+                            unsigned long long* ru = reinterpret_cast<unsigned long long*>(sm.h.red);
+                            if (lane == 0) ru[wid] = hsh;
+                            __syncthreads();
+                            if (tid == 0) { unsigned long long t = 0; for (int i = 0; i < nw; i++) t += ru[i]; P.meta[slot].hash = t; }
+                            __syncthreads();
+                        }
+                        start = fm + 1;
+                    } else {
+                        start = end;
+                    }
+                    __syncthreads();
+                }
+                __syncthreads();
+                if (!by_coords) clear_dense_block(sm.h.dense, ient, P.meta[slot].nnz);
+                if (tid == 0) P.coords[slot] = sm.icoords;
+                __syncthreads();
+                if (sm.any_del) {
+                    apply_deletions_block(sm, P, list, flags, nbytes);
+                    if (tid == 0) sm.any_del = 0;
+                }
+                __syncthreads();
+                if (tid == 0) { list[sm.S] = slot; sm.S = sm.S + 1; }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        if (!(P.do_hist || P.do_coords)) {                  // no pass requested: identity
+            for (int p = tid; p < n; p += blockDim.x) list[p] = base + p;
+            if (tid == 0) sm.S = n;
+            __syncthreads();
+        }
+        if (tid == 0) P.out_count[f] = sm.S;
+        __syncthreads();
+    }
+}
+
+// gather survivors (list -> compact CSR output).  One CTA per frame.
+__global__ void k5_gather_kernel(const uint8_t* __restrict__ windows, const int4* __restrict__ coords,
+                                 const int32_t* __restrict__ in_offsets, const int32_t* __restrict__ list,
+                                 const int32_t* __restrict__ out_offsets, int nframes, int nbytes,
+                                 uint8_t* __restrict__ out_windows, int4* __restrict__ out_coords, int32_t* __restrict__ out_slots) {
+    int f = blockIdx.x;
+    if (f >= nframes) return;
+    const int o0 = out_offsets[f], cnt = out_offsets[f + 1] - o0;
+    const int32_t* l = list + in_offsets[f];
+    for (int r = 0; r < cnt; r++) {
+        const int slot = l[r];
+        if (out_windows) {
+            const uint8_t* s = windows + (int64_t)slot * nbytes;
+            uint8_t* d = out_windows + (int64_t)(o0 + r) * nbytes;
+            for (int i = threadIdx.x; i < nbytes; i += blockDim.x) d[i] = s[i];
+        }
+        if (threadIdx.x == 0) {
+            if (out_coords) out_coords[o0 + r] = coords[slot];
+            if (out_slots) out_slots[o0 + r] = slot;
+        }
+    }
+}
+
+// =====================================================================================================
+// K6  cv2.cvtColor(BGR2GRAY)  (REC:388), SURVEY A.6
+// =====================================================================================================
+__global__ void k6_gray_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
+                               const int32_t* __restrict__ n_ptr, int n_max, int npx, uint8_t* __restrict__ gray) {
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int64_t total = (int64_t)n * npx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t src = i;
+        if (slots) { int w = (int)(i / npx); src = (int64_t)slots[w] * npx + (i - (int64_t)w * npx); }
+        const uint8_t* p = windows + src * 3;
+        gray[i] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+    }
+}
+
+// =====================================================================================================
+// K7  cv2.HOGDescriptor((32,32),(16,16),(8,8),(8,8),9,signed).compute  (REC:487-494,519), SURVEY A.7.
+// One warp per window.  Gradient votes are staged in shared memory; each (block, cell, bin) accumulator has a
+// FIXED owner lane that walks the block's pixels in raster order -> no float atomics, bit-reproducible runs.
+// =====================================================================================================
+__device__ __forceinline__ float fast_atan_deg(float y, float x) {
+    const float sc = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * sc, p3 = -0.3258083974640975f * sc;
+    const float p5 = 0.1555786518463281f * sc, p7 = -0.04432655554792128f * sc;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, ax + (float)DBL_EPSILON); c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = __fdiv_rn(ax, ay + (float)DBL_EPSILON); c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+struct HogConst {
+    float gauss[16];           // exp(-(i-8)^2 / 32)
+};
+
+constexpr int kHogWarps = 2;
+__global__ void __launch_bounds__(kHogWarps * 32) k7_hog_kernel(const uint8_t* __restrict__ gray, const int32_t* __restrict__ n_ptr,
+                                                               int n_max, HogConst hc, float* __restrict__ desc) {
+    __shared__ uint8_t s_img[kHogWarps][32 * 32];
+    __shared__ float s_g0[kHogWarps][32 * 32], s_g1[kHogWarps][32 * 32];
+    __shared__ uint8_t s_q0[kHogWarps][32 * 32], s_q1[kHogWarps][32 * 32];
+    __shared__ float s_hist[kHogWarps][9 * 36];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kHogWarps + wl;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const uint8_t* img = gray + (int64_t)w * 1024;
+    // 1024 B = 64 x 16 B: two 128-bit loads per lane
+    const uint4* img4 = reinterpret_cast<const uint4*>(img);
+    uint4* s4 = reinterpret_cast<uint4*>(s_img[wl]);
+    s4[lane] = img4[lane];
+    s4[lane + 32] = img4[lane + 32];
+    __syncwarp();
+    const float angleScale = (float)(9.0 / (2.0 * 3.14159265358979323846));
+    const float deg2rad = (float)(3.14159265358979323846 / 180.0);
+    for (int y = 0; y < 32; y++) {                          // lane = x
+        const int x = lane;
+        int yp = y == 0 ? 1 : y - 1, yn = y == 31 ? 30 : y + 1;     // BORDER_REFLECT_101
+        int xp = x == 0 ? 1 : x - 1, xn = x == 31 ? 30 : x + 1;
+        float dx = (float)s_img[wl][y * 32 + xn] - (float)s_img[wl][y * 32 + xp];
+        float dy = (float)s_img[wl][yn * 32 + x] - (float)s_img[wl][yp * 32 + x];
+        float mag = __fsqrt_rn(dx * dx + dy * dy);
+        float ang = fast_atan_deg(dy, dx) * deg2rad;
+        float t = ang * angleScale - 0.5f;
+        int hidx = (int)floorf(t);
+        t -= (float)hidx;
+        if (hidx < 0) hidx += 9; else if (hidx >= 9) hidx -= 9;
+        int h1 = hidx + 1; if (h1 >= 9) h1 = 0;
+        s_g0[wl][y * 32 + x] = mag * (1.f - t);
+        s_g1[wl][y * 32 + x] = mag * t;
+        s_q0[wl][y * 32 + x] = (uint8_t)hidx;
+        s_q1[wl][y * 32 + x] = (uint8_t)h1;
+    }
+    __syncwarp();
+    // accumulators: 9 blocks x 36 = 324 (block, cell, bin) triples; owner lane o handles triples o, o+32, ...
+    for (int a = lane; a < 324; a += 32) {
+        const int blk = a / 36, r = a - blk * 36, cell = r / 9, bin = r - cell * 9;
+        const int bx = blk / 3, by = blk - bx * 3;          // blocks column-major: offset (bx*3+by)*36
+        const int cxi = cell >> 1, cyi = cell & 1;          // cells column-major: (ix*2+iy)*9
+        float acc = 0.f;
+        // OpenCV walks the block's pixels in raster order (j rows, i cols); only pixels whose bilinear footprint
+        // includes this cell contribute.
+        for (int j = 0; j < 16; j++) {
+            float cellY = (j + 0.5f) / 8 - 0.5f;
+            int iy0 = (int)floorf(cellY);
+            float fy = cellY - iy0;
+            float wy = (cyi == iy0) ? 1.f - fy : (cyi == iy0 + 1) ? fy : -1.f;
+            if (wy < 0.f) continue;
+            for (int i = 0; i < 16; i++) {
+                float cellX = (i + 0.5f) / 8 - 0.5f;
+                int ix0 = (int)floorf(cellX);
+                float fx = cellX - ix0;
+                float wx = (cxi == ix0) ? 1.f - fx : (cxi == ix0 + 1) ? fx : -1.f;
+                if (wx < 0.f) continue;
+                const int p = (by * 8 + j) * 32 + bx * 8 + i;
+                const float ww = (hc.gauss[i] * hc.gauss[j]) * (wx * wy);
+                if (s_q0[wl][p] == bin) acc += s_g0[wl][p] * ww;
+                if (s_q1[wl][p] == bin) acc += s_g1[wl][p] * ww;
+            }
+        }
+        s_hist[wl][a] = acc;
+    }
+    __syncwarp();
+    // L2-Hys per block (36 values): lanes 0..8 each normalise one block sequentially (matches the scalar order)
+    if (lane < 9) {
+        float* h = s_hist[wl] + lane * 36;
+        float sum = 0.f;
+        for (int k = 0; k < 36; k++) sum += h[k] * h[k];
+        float sc = 1.f / (__fsqrt_rn(sum) + 36 * 0.1f);
+        sum = 0.f;
+        for (int k = 0; k < 36; k++) { float v = fminf(h[k] * sc, 0.2f); h[k] = v; sum += v * v; }
+        sc = 1.f / (__fsqrt_rn(sum) + 1e-3f);
+        for (int k = 0; k < 36; k++) h[k] *= sc;
+    }
+    __syncwarp();
+    float* o = desc + (int64_t)w * 324;
+    for (int a = lane; a < 324; a += 32) o[a] = s_hist[wl][a];
+}
+
+// =====================================================================================================
+// K8  predictProbabilityLDAClassifiers + extractBestPredictions  (REC:565-577,627-641,342-347), SURVEY A.8.
+// z = x . w_c + b_c in f64 (sklearn up-casts the f32 descriptors); one warp per window, W staged in shared memory.
+// Decision on p = expit(z) (keeps the saturation tie rule).
+// =====================================================================================================
+__device__ __forceinline__ int lda_decide(const double z[6], double tol) {
+    double best[6]; int tag[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double p1 = 1.0 / (1.0 + exp(-z[c])), p0 = 1.0 - p1;
+        best[c] = p0 > p1 ? p0 : p1;
+        tag[c] = p0 > p1 ? 0 : c + 1;
+    }
+    bool nosign = true;
+#pragma unroll
+    for (int c = 0; c < 6; c++) if (tag[c] != 0 && best[c] > tol) nosign = false;
+    if (nosign) return 0;
+    int lab = 0; double bv = 0; bool first = true;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double key = tag[c] != 0 ? best[c] : -INFINITY;
+        if (first || key > bv) { bv = key; lab = tag[c]; first = false; }
+    }
+    return lab;
+}
+
+__global__ void __launch_bounds__(256) k8_lda_kernel(const float* __restrict__ X, const int32_t* __restrict__ n_ptr, int n_max,
+                                                     int nfeat, const double* __restrict__ W, const double* __restrict__ b,
+                                                     double tol, double* __restrict__ logits, int32_t* __restrict__ labels) {
+    extern __shared__ double s_W[];                         // [nfeat][6]
+    for (int i = threadIdx.x; i < nfeat * 6; i += blockDim.x) s_W[i] = W[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+        const float* x = X + (int64_t)w * nfeat;
+        double z[6] = {0, 0, 0, 0, 0, 0};
+        for (int f = lane; f < nfeat; f += 32) {
+            double xv = (double)x[f];
+#pragma unroll
+            for (int c = 0; c < 6; c++) z[c] += xv * s_W[f * 6 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) z[c] = warp_sum(z[c]) + b[c];
+        if (lane == 0) {
+            if (logits) for (int c = 0; c < 6; c++) logits[(int64_t)w * 6 + c] = z[c];
+            labels[w] = lda_decide(z, tol);
+        }
+    }
+}
+
+// K8b  reducer.transform + KNeighborsClassifier(k).predict  (REC:592-596).  One warp per query: Z = (x - xbar) S in
+// f64, then every lane keeps its k best of the training rows it visits; the warp merges by (distance, index).
+constexpr int kKnnMaxK = 8;
+__global__ void __launch_bounds__(128) k8_knn_kernel(const float* __restrict__ X, int n, int nfeat, const double* __restrict__ xbar,
+                                                     const double* __restrict__ S, const double* __restrict__ Zt,
+                                                     const int32_t* __restrict__ yt, int ntrain, int k,
+                                                     double* __restrict__ Zout, int32_t* __restrict__ labels) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    const float* x = X + (int64_t)w * nfeat;
+    double z[6] = {0, 0, 0, 0, 0, 0};
+    for (int f = lane; f < nfeat; f += 32) {
+        double xc = (double)x[f] - xbar[f];
+#pragma unroll
+        for (int c = 0; c < 6; c++) z[c] += xc * S[f * 6 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) z[c] = warp_sum(z[c]);
+    if (lane == 0 && Zout) for (int c = 0; c < 6; c++) Zout[(int64_t)w * 6 + c] = z[c];
+    double bd[kKnnMaxK]; int bi[kKnnMaxK];
+#pragma unroll
+    for (int j = 0; j < kKnnMaxK; j++) { bd[j] = INFINITY; bi[j] = 0x7fffffff; }
+    for (int t = lane; t < ntrain; t += 32) {
+        double d = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) { double e = z[c] - Zt[(int64_t)t * 6 + c]; d += e * e; }
+        if (d < bd[k - 1]) {                                // per-lane indices increase, so ties keep the smaller index
+            int pos = k - 1;
+            while (pos > 0 && bd[pos - 1] > d) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; pos--; }
+            bd[pos] = d; bi[pos] = t;
+        }
+    }
+    // k rounds of warp arg-min over the lanes' current heads
+    int votes[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) votes[j] = 0;
+    int head = 0;
+    for (int r = 0; r < k; r++) {
+        double d = head < k ? bd[head] : INFINITY; int idx = head < k ? bi[head] : 0x7fffffff;
+        double bdv = d; int bidx = idx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, bdv, o); int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (od < bdv || (od == bdv && oi < bidx)) { bdv = od; bidx = oi; }
+        }
+        if (idx == bidx && d == bdv) head++;
+        if (bidx != 0x7fffffff) { int y = yt[bidx]; if (y >= 0 && y < 16) votes[y]++; }
+    }
+    if (lane == 0) {
+        int lab = 0, bv = -1;
+        for (int y = 0; y < 16; y++) if (votes[y] > bv) { bv = votes[y]; lab = y; }   // ties -> smallest label
+        labels[w] = lab;
+    }
+}
+
+// =====================================================================================================
+// detection records (one line of resultado.txt, DET:501-508)
+// =====================================================================================================
+struct DetRec { int32_t frame, x1, y1, x2, y2, id, hundredths, reserved; };
+
+// per-frame count of emitted survivors (survivors are CSR by surv_offsets); one warp per frame
+__global__ void det_count_kernel(const uint8_t* __restrict__ emit, const int32_t* __restrict__ surv_offsets, int nframes,
+                                 int32_t* __restrict__ counts) {
+    int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= nframes) return;
+    int c = 0;
+    for (int i = surv_offsets[f] + lane; i < surv_offsets[f + 1]; i += 32) c += emit[i] != 0;
+    c = warp_sum_i(c);
+    if (lane == 0) counts[f] = c;
+}
+
+__global__ void det_write_kernel(const uint8_t* __restrict__ emit, const int32_t* __restrict__ id, const int32_t* __restrict__ hundredths,
+                                 const int4* __restrict__ coords, const int32_t* __restrict__ slots,
+                                 const int32_t* __restrict__ surv_offsets, const int32_t* __restrict__ det_offsets, int nframes,
+                                 int det_cap, DetRec* __restrict__ out) {
+    int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= nframes) return;
+    int o = det_offsets[f];
+    for (int base = surv_offsets[f]; base < surv_offsets[f + 1]; base += 32) {
+        int i = base + lane;
+        bool e = i < surv_offsets[f + 1] && emit[i] != 0;
+        unsigned m = __ballot_sync(0xffffffffu, e);
+        if (e) {
+            int r = o + __popc(m & ((1u << lane) - 1));
+            if (r < det_cap) {
+                int4 c = coords[slots ? slots[i] : i];
+                out[r] = DetRec{f, c.x, c.y, c.z, c.w, id[i], hundredths[i], 0};
+            }
+        }
+        o += __popc(m);
+    }
+}
+
+__global__ void label_emit_kernel(const int32_t* __restrict__ lab, const int32_t* __restrict__ n_ptr, int n_max, uint8_t* __restrict__ emit) {
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) emit[i] = lab[i] != 0 ? 1 : 0;
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, int64_t n, uint8_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace tsd

@@ -71,10 +71,21 @@ def make_boxes(nframes, nboxes, H=800, W=1360, seed=BOX_SEED, enlarge=1.30, D=25
                         y = H - h
                 elif u > 0.96:                                 # exact 2D x 2D or D x D crop (AREA / copy paths)
                     target = 2 * D if rng.random() < 0.5 else D
+                    # interior boxes give odd/even crop sides only for some sizes; the low-side clamp at 0
+                    # (DET:167-168) reaches the others, so small offsets are tried as well
+                    found = False
                     for cand in range(max(3, int(target / enlarge) - 2), int(target / enlarge) + 3):
-                        xx = int(rng.integers(8, W - cand - 8)); yy = int(rng.integers(8, H - cand - 8))
-                        if _crop_side(xx, cand, enlarge, W) == target and _crop_side(yy, cand, enlarge, H) == target:
-                            x, y, w, h = xx, yy, cand, cand
+                        for xx in [int(rng.integers(8, W - cand - 8))] + list(range(0, 8)):
+                            if _crop_side(xx, cand, enlarge, W) != target:
+                                continue
+                            for yy in [int(rng.integers(8, H - cand - 8))] + list(range(0, 8)):
+                                if _crop_side(yy, cand, enlarge, H) == target:
+                                    x, y, w, h = xx, yy, cand, cand
+                                    found = True
+                                    break
+                            if found:
+                                break
+                        if found:
                             break
             boxes[f, i] = (x, y, w, h)
     offsets = (np.arange(nframes + 1) * nboxes).astype(np.int32)

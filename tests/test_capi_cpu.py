@@ -1,0 +1,78 @@
+"""CPU (-m "not gpu"): the C-ABI library loads, exports every symbol include/tsd_b200.h declares, and the host
+logic around it behaves (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "tsd_b200.h")).read()
+    return sorted(set(re.findall(r"TSD_API\s+[\w\s\*]+?\b(tsd_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(tsd):
+    lib = tsd._capi.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 28
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) == set(tsd._capi.EXPORTS)
+
+
+def test_struct_layouts_match_header(tsd):
+    assert C.sizeof(tsd._capi.Detection) == 32 and tsd.DET_DTYPE.itemsize == 32
+    cfg = tsd.default_config("det")
+    assert (cfg.enlarge, cfg.window, cfg.score_tol_hundredths) == (1.30, 25, 55)
+    assert (cfg.hist_tol, cfg.coord_tol, cfg.merge_factor, cfg.proba_tol, cfg.knn_k) == (0.85, 0.95, 0.8823, 0.5, 4)
+    assert [list(r) for r in cfg.red_lo] == [[0, 50, 10], [160, 50, 10]] and list(cfg.blue_hi) == [128, 255, 255]
+    rec = tsd.default_config("rec")
+    assert (rec.enlarge, rec.window) == (1.15, 32)
+    assert cfg.enlarge - 1 == 0.30000000000000004 and rec.enlarge - 1 == 0.1499999999999999   # SURVEY A.1 literals
+
+
+def test_no_cpu_fallback(tsd):
+    """Without a CUDA device the product path must fail loudly."""
+    if tsd._capi.lib().tsd_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(tsd.TsdError, match="no CUDA device"):
+        tsd.Context()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "opencv-traffic-sign-detector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "tsd_oracle" not in text and "orc_" not in text, f
+
+
+def test_similarity_table_matches_reference_expression(tsd, oracle):
+    t = tsd.similarity_table(4096)
+    assert t[0] == 1.0 and np.all(np.diff(t) <= 0) and t[-1] < t[1]       # monotone non-increasing
+    for d2 in (1, 2, 25, 1000, 3721, 4095):
+        assert abs(t[d2] - oracle.eucl_similarity_d2(d2)) < 1e-15
+    full = tsd.similarity_table()
+    assert np.sqrt(full[-1]) < 0.95 * 0.8823                              # beyond the table nothing can act
+
+
+def test_synth_is_deterministic_and_exercises_paths(tsd, oracle):
+    fr = tsd.synth.make_frames(2, H=200, W=300)
+    assert fr.shape == (2, 200, 300, 3) and fr.dtype == np.uint8
+    assert np.array_equal(fr, tsd.synth.make_frames(2, H=200, W=300))
+    bx, off = tsd.synth.make_boxes(16, 200)
+    assert np.array_equal(bx, tsd.synth.make_boxes(16, 200)[0]) and off[-1] == 3200
+    assert np.all(bx[:, 0] >= 0) and np.all(bx[:, 0] + bx[:, 2] <= 1360) and np.all(bx[:, 1] + bx[:, 3] <= 800)
+    coords, valid = oracle.expand_boxes(bx, 1.30)
+    frac = valid.mean()
+    assert 0.25 < frac < 0.6
+    cw = np.minimum(coords[valid][:, 2], 1360) - coords[valid][:, 0]
+    ch = np.minimum(coords[valid][:, 3], 800) - coords[valid][:, 1]
+    assert np.any((cw == 50) & (ch == 50)) and np.any((cw == 25) & (ch == 25))      # AREA and copy paths
+    assert np.any(coords[valid][:, 2] > 1360) or np.any(coords[valid][:, 3] > 800)    # clipped crops

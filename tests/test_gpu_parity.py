@@ -1,0 +1,319 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the reference-generated goldens.
+Bit-exact for every integer / byte / index artefact; HOG within 1e-4 relative; LDA logits within 1e-9."""
+import numpy as np
+import pytest
+
+from conftest import STORED
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- K1 -------------------------------------------------------------------------------------------------------------
+def test_k1_expand(ctx_det, ctx_rec, oracle, det_frames):
+    rng = np.random.default_rng(11)
+    n = 20000
+    w = rng.integers(1, 400, n); h = np.maximum(1, np.rint(w / rng.uniform(0.6, 1.6, n))).astype(np.int64)
+    boxes = np.stack([rng.integers(0, 3840, n), rng.integers(0, 2160, n), w, h], 1).astype(np.int32)
+    boxes[:50, 3] = 0                                                    # h == 0 -> inf/nan ratio -> rejected
+    for ctx, p in ((ctx_det, 1.30), (ctx_rec, 1.15)):
+        c, v = ctx.expand_boxes(boxes)
+        oc, ov = oracle.expand_boxes(boxes, p)
+        assert np.array_equal(v, ov) and np.array_equal(c[v], oc[ov])
+    for k in STORED:
+        c, v = ctx_det.expand_boxes(det_frames[k + "_boxes"])
+        assert np.array_equal(v, det_frames[k + "_valid"]) and np.array_equal(c[v], det_frames[k + "_coords"][v])
+    c, v = ctx_det.expand_boxes(np.zeros((0, 4), np.int32))
+    assert c.shape == (0, 4) and v.shape == (0,)
+
+
+# ---- K2 -------------------------------------------------------------------------------------------------------------
+def test_k2_resize_sweep(ctx_det, ctx_rec, oracle):
+    """Size sweep incl. the same-size copy, the 2x AREA path, upscales, 1-px crops and frame-edge clipping."""
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, (2, 420, 640, 3), dtype=np.uint8)
+    for ctx, D in ((ctx_det, 25), (ctx_rec, 32)):
+        coords, wf = [], []
+        for h in list(range(1, 90)) + [2 * D, 2 * D + 1, 128, 257, 400]:
+            for w in (1, 2, 3, D - 1, D, D + 1, 2 * D - 1, 2 * D, 2 * D + 1, 37, 100, 300, h):
+                x0 = int(rng.integers(0, 640 - min(w, 600))); y0 = int(rng.integers(0, 420 - min(h, 400)))
+                coords.append((x0, y0, x0 + w, y0 + h)); wf.append(int(rng.integers(0, 2)))
+        coords += [(600, 400, 700, 480), (630, 0, 660, 30), (0, 410, 40, 450), (639, 419, 700, 500)]   # clipped by the frame
+        wf += [0, 1, 0, 1]
+        coords = np.array(coords, np.int32); wf = np.array(wf, np.int32)
+        got = ctx.crop_resize(frame, coords, wf, D)
+        for i, (c, f) in enumerate(zip(coords, wf)):
+            assert np.array_equal(got[i], oracle.crop_resize(frame[f], c, D)), (D, c)
+        gray = np.ascontiguousarray(frame[..., 1])
+        got1 = ctx.crop_resize(gray, coords[::3], wf[::3], D)
+        for i, (c, f) in enumerate(zip(coords[::3], wf[::3])):
+            assert np.array_equal(got1[i], oracle.crop_resize(gray[f], c, D)), (D, c, "grey")
+
+
+def test_k2_golden_frames(ctx_det, det_frames, frames3):
+    for k in STORED:
+        v = det_frames[k + "_valid"]
+        got = ctx_det.crop_resize(frames3[k], det_frames[k + "_coords"][v])
+        assert np.array_equal(got, det_frames[k + "_windows"])
+
+
+def test_k1k2_windows_batch(ctx_det, det_frames, frames3, oracle, tsd):
+    frames = np.stack([frames3[k] for k in STORED])
+    boxes = [det_frames[k + "_boxes"] for k in STORED]
+    off = np.concatenate([[0], np.cumsum([len(b) for b in boxes])]).astype(np.int32)
+    wins, coords, woff = ctx_det.windows(frames, np.concatenate(boxes), off)
+    exp_w = np.concatenate([det_frames[k + "_windows"] for k in STORED])
+    exp_c = np.concatenate([det_frames[k + "_coords"][det_frames[k + "_valid"]] for k in STORED])
+    assert np.array_equal(woff, np.concatenate([[0], np.cumsum([det_frames[k + "_valid"].sum() for k in STORED])]))
+    assert np.array_equal(coords, exp_c) and np.array_equal(wins, exp_w)
+    # a frame without boxes in the middle, and an empty batch of boxes
+    off2 = np.array([0, len(boxes[0]), len(boxes[0]), len(boxes[0]) + len(boxes[2])], np.int32)
+    w2, c2, wo2 = ctx_det.windows(frames, np.concatenate([boxes[0], boxes[2]]), off2)
+    assert wo2[1] == wo2[2] and np.array_equal(w2[wo2[2]:], det_frames[STORED[2] + "_windows"])
+    w3, c3, wo3 = ctx_det.windows(frames[:1], np.zeros((0, 4), np.int32), np.array([0, 0], np.int32))
+    assert len(w3) == 0 and wo3.tolist() == [0, 0]
+
+
+# ---- K3 -------------------------------------------------------------------------------------------------------------
+def test_k3_exhaustive_colours(ctx_det, oracle):
+    """All 2^24 BGR colours: HSV bytes and both masks bit-exact."""
+    g, r = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for b0 in range(0, 256, 32):
+        img = np.stack([np.stack([np.full_like(g, b), g, r], -1) for b in range(b0, b0 + 32)])      # [32,256,256,3]
+        assert np.array_equal(ctx_det.bgr2hsv(img), oracle.bgr2hsv(img))
+        # masks kernel works on DxD windows: view the colours as 25x25 windows (pad the tail)
+        flat = img.reshape(-1, 3)
+        n = (len(flat) // 625) * 625
+        wins = flat[:n].reshape(-1, 25, 25, 3)
+        red, blue = ctx_det.color_masks(wins)
+        ored, oblue = oracle.color_masks(wins)
+        assert np.array_equal(red, ored) and np.array_equal(blue, oblue)
+        tail = np.zeros((1, 25, 25, 3), np.uint8); tail.reshape(-1, 3)[:len(flat) - n] = flat[n:]
+        red, blue = ctx_det.color_masks(tail)
+        ored, oblue = oracle.color_masks(tail)
+        assert np.array_equal(red, ored) and np.array_equal(blue, oblue)
+        assert np.array_equal(ctx_det.bgr2gray(img), oracle.bgr2gray(img))
+
+
+def test_k3_golden(ctx_det, det_frames):
+    for k in STORED:
+        wins = det_frames[k + "_p2_windows"]
+        assert np.array_equal(ctx_det.bgr2hsv(wins), det_frames[k + "_hsv"])
+        red, blue = ctx_det.color_masks(wins)
+        assert np.array_equal(red, det_frames[k + "_red"]) and np.array_equal(blue, det_frames[k + "_blue"])
+
+
+# ---- K4 -------------------------------------------------------------------------------------------------------------
+def test_k4_scores_golden_and_random(ctx_det, oracle, det_frames, templates, tsd):
+    red6, blue6 = templates
+    for k in STORED:
+        r = ctx_det.score_masks(det_frames[k + "_red"], det_frames[k + "_blue"])
+        assert np.array_equal(r["scores"], np.rint(det_frames[k + "_scores"] * 100).astype(np.int32))
+    rng = np.random.default_rng(2)
+    n = 3000
+    red = (rng.random((n, 25, 25)) < rng.random((n, 1, 1))).astype(np.uint8) * 255
+    blue = (rng.random((n, 25, 25)) < rng.random((n, 1, 1))).astype(np.uint8) * 255
+    red[0] = 0; blue[0] = 0; red[1] = 255; blue[1] = 255; red[2] = red6[2]; blue[2] = blue6[5]
+    r = ctx_det.score_masks(red, blue)
+    for i in range(n):
+        for ci, (m, t6) in enumerate(((red[i], red6), (blue[i], blue6))):
+            for ti in range(6):
+                assert r["scores"][i, ci, ti] == oracle.score_hundredths(m, t6[ti])[0]
+    # random templates (incl. degenerate ones with <= 6 pixels set), decision rule vs the oracle's window scorer
+    with tsd.Context(device=0, flavour="det") as c2:
+        t_r = (rng.random((6, 25, 25)) < np.array([0.0, 0.005, 0.01, 0.2, 0.5, 1.0])[:, None, None]).astype(np.uint8) * 255
+        t_b = (rng.random((6, 25, 25)) < np.array([0.3, 0.3, 0.009, 0.0, 0.7, 0.1])[:, None, None]).astype(np.uint8) * 255
+        c2.set_templates(t_r, t_b)
+        wins = rng.integers(0, 256, (500, 25, 25, 3), dtype=np.uint8)
+        wins[:250, :, :, 2] = 255; wins[:250, :, :, :2] //= 3                     # reddish
+        wins[250:400, :, :, 0] = 250; wins[250:400, :, :, 1:] //= 3               # bluish
+        mr, mb = c2.color_masks(wins)
+        r = c2.score_masks(mr, mb)
+        for i in range(len(wins)):
+            ok, oid, oh = oracle.score_window(wins[i], t_r, t_b, 55)
+            assert (bool(r["emit"][i]), int(r["id"][i]), int(r["hundredths"][i])) == (ok, oid, oh)
+
+
+# ---- K5 -------------------------------------------------------------------------------------------------------------
+def test_k5_hist(ctx_det, ctx_rec, oracle, det_frames):
+    for k in STORED:
+        got = ctx_det.hist(det_frames[k + "_windows"])
+        assert np.array_equal(got, det_frames[k + "_hists"])
+    rng = np.random.default_rng(9)
+    w32 = rng.integers(0, 256, (40, 32, 32, 3), dtype=np.uint8)
+    w32[0] = 200; w32[1, :16] = (10, 200, 30)
+    got = ctx_rec.hist(w32)
+    for i in range(len(w32)):
+        assert np.array_equal(got[i], oracle.hist_normalized(w32[i]))
+
+
+def test_k5_dedup_golden_50_frames(ctx_det, det_windows50):
+    g = det_windows50
+    w1, c1, o1 = ctx_det.dedup(g["windows"], g["coords"], g["offsets"], False, 0.85)
+    assert np.array_equal(o1, g["p1_offsets"]) and np.array_equal(c1, g["p1_coords"])
+    w2, c2, o2 = ctx_det.dedup(w1, c1, o1, True, 0.95)
+    assert np.array_equal(o2, g["surv_offsets"])
+    assert np.array_equal(c2, g["surv_coords"]) and np.array_equal(w2, g["surv_windows"])
+
+
+def test_k5_dedup_per_frame_golden(ctx_det, det_frames):
+    for k in STORED:
+        wins = det_frames[k + "_windows"]; coords = det_frames[k + "_coords"][det_frames[k + "_valid"]]
+        off = np.array([0, len(wins)], np.int32)
+        w1, c1, o1 = ctx_det.dedup(wins, coords, off, False, 0.85)
+        assert np.array_equal(w1, det_frames[k + "_p1_windows"]) and np.array_equal(c1, det_frames[k + "_p1_coords"])
+        w2, c2, o2 = ctx_det.dedup(w1, c1, o1, True, 0.95)
+        assert np.array_equal(w2, det_frames[k + "_p2_windows"]) and np.array_equal(c2, det_frames[k + "_p2_coords"])
+
+
+def test_k5_dedup_adversarial(ctx_det, oracle):
+    """Duplicates, identical pixels at different places, merge chains, empty and single-item frames."""
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, (12, 25, 25, 3), dtype=np.uint8)
+    wins, coords, off = [], [], [0]
+    for f in range(40):
+        n = int(rng.integers(0, 60)) if f not in (3, 4) else (0 if f == 3 else 1)
+        for i in range(n):
+            b = base[int(rng.integers(0, 12))].astype(np.int16)
+            mode = rng.random()
+            if mode < 0.3:
+                w = b                                                    # exact duplicate pixels
+            elif mode < 0.7:
+                w = b + rng.integers(-12, 13, b.shape)                   # near duplicate -> delete / merge bands
+            else:
+                w = rng.integers(0, 256, b.shape)
+            wins.append(np.clip(w, 0, 255).astype(np.uint8))
+            x, y = int(rng.integers(0, 1300)), int(rng.integers(0, 760))
+            if coords and rng.random() < 0.5 and len(coords) > off[-1]:
+                px = coords[int(rng.integers(off[-1], len(coords)))]
+                x, y = max(0, px[0] + int(rng.integers(-30, 31))), max(0, px[1] + int(rng.integers(-30, 31)))
+            s = int(rng.integers(20, 80))
+            coords.append((x, y, x + s + int(rng.integers(-5, 6)), y + s + int(rng.integers(-5, 6))))
+        off.append(len(coords))
+    wins = np.stack(wins); coords = np.array(coords, np.int32); off = np.array(off, np.int32)
+    for by_coords, tol in ((False, 0.85), (True, 0.95), (False, 0.5), (True, 0.6)):
+        gw, gc, go = ctx_det.dedup(wins, coords, off, by_coords, tol)
+        for f in range(len(off) - 1):
+            ow, oc = oracle.dedup(wins[off[f]:off[f + 1]], coords[off[f]:off[f + 1]], by_coords, tol)
+            assert go[f + 1] - go[f] == len(oc), (by_coords, tol, f)
+            assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (by_coords, tol, f)
+
+
+# ---- whole chain ------------------------------------------------------------------------------------------------------
+def _records(det):
+    return [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
+
+
+def test_chain_golden_frames(ctx_det, det_frames, frames3):
+    frames = np.stack([frames3[k] for k in STORED])
+    boxes = [det_frames[k + "_boxes"] for k in STORED]
+    off = np.concatenate([[0], np.cumsum([len(b) for b in boxes])]).astype(np.int32)
+    det, counts = ctx_det.detect_frames(frames, np.concatenate(boxes), off)
+    exp = []
+    for f, k in enumerate(STORED):
+        for c, i, s in zip(det_frames[k + "_det_coords"], det_frames[k + "_det_ids"], det_frames[k + "_det_scores"]):
+            exp.append((f,) + tuple(int(v) for v in c) + (int(i), int(round(s * 100))))
+    assert _records(det) == exp
+    assert counts.tolist() == [int(off[-1]), int(sum(det_frames[k + "_valid"].sum() for k in STORED)),
+                               int(sum(len(det_frames[k + "_p2_coords"]) for k in STORED)), len(exp)]
+
+
+def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
+    """BASELINE config 3 shape (1360x800, 200 candidates/frame) on 12 frames, plus a 4K frame with 500 candidates."""
+    red6, blue6 = templates
+    for (H, W, F, N) in ((800, 1360, 12, 200), (2160, 3840, 1, 500)):
+        frames = tsd.synth.make_frames(F, H, W)
+        boxes, off = tsd.synth.make_boxes(F, N, H, W)
+        det, counts = ctx_det.detect_frames(frames, boxes, off)
+        exp, tot = [], np.zeros(4, np.int64)
+        for f in range(F):
+            o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+            tot += o["stage_counts"]
+            exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+        assert counts.tolist() == tot.tolist()
+        assert _records(det) == exp
+
+
+def test_chain_properties_full_size(ctx_det, tsd):
+    """Size-independent properties at a larger batch: idempotence of the fold, determinism, frame independence."""
+    F = 48
+    frames = tsd.synth.make_frames(8)
+    frames = np.concatenate([frames] * (F // 8))
+    boxes, off = tsd.synth.make_boxes(F, 200)
+    det, counts = ctx_det.detect_frames(frames, boxes, off)
+    det2, counts2 = ctx_det.detect_frames(frames, boxes, off)
+    assert np.array_equal(det, det2) and np.array_equal(counts, counts2)            # deterministic
+    # frame independence: a frame processed alone gives the same records as inside the batch
+    for f in (0, 17, 47):
+        d1, _ = ctx_det.detect_frames(frames[f], boxes[off[f]:off[f + 1]], np.array([0, off[f + 1] - off[f]], np.int32))
+        sel = det[det["frame"] == f]
+        assert [r[1:] for r in _records(d1)] == [r[1:] for r in _records(sel)]
+    # the coordinate pass is idempotent on its own output
+    wins, coords, woff = ctx_det.windows(frames[:4], boxes[:off[4]], off[:5])
+    w1, c1, o1 = ctx_det.dedup(wins, coords, woff, False, 0.85)
+    w2, c2, o2 = ctx_det.dedup(w1, c1, o1, True, 0.95)
+    w3, c3, o3 = ctx_det.dedup(w2, c2, o2, True, 0.95)
+    assert np.array_equal(o2, o3) and np.array_equal(c2, c3) and np.array_equal(w2, w3)
+    assert counts[0] == F * 200 and counts[0] >= counts[1] >= counts[2] >= counts[3]
+
+
+# ---- recognition --------------------------------------------------------------------------------------------------------
+def test_k6_k7_k8_recognition_golden(ctx_rec, rec_golden, rec_frames, oracle):
+    g = rec_golden
+    hog = ctx_rec.hog(g["gray"])
+    ref = g["hog"]
+    rel = np.abs(hog - ref) / np.maximum(np.abs(ref), 1e-2)
+    assert rel.max() < 1e-4, rel.max()                                   # north_star: HOG within 1e-4 relative
+    assert np.abs(ctx_rec.hog(np.full((1, 32, 32), 9, np.uint8))).max() == 0.0    # constant image -> all zeros, no NaN
+    lg, lab = ctx_rec.lda_predict(g["hog"])
+    assert np.max(np.abs(lg - g["logits"])) < 1e-9
+    assert np.array_equal(lab, g["pred_lda"])
+    lg2, lab2 = ctx_rec.lda_predict(hog)                                  # our own descriptors: labels still exact
+    assert np.array_equal(lab2, g["pred_lda"])
+    Z, lk = ctx_rec.knn_predict(g["hog"])
+    assert np.max(np.abs(Z - g["knn_Zq"])) < 1e-9
+    assert np.array_equal(lk, g["pred_knn"])
+    # saturation tie rule: logits this large make p == 1.0 for several classifiers -> lowest class wins
+    X = np.zeros((3, 324), np.float32)
+    with_big = type(ctx_rec)(device=0, flavour="rec")
+    W = np.zeros((324, 6)); b = np.array([-50.0, 40.0, 45.0, -1.0, 60.0, 0.0])
+    with_big.set_lda(W, b)
+    _, lab = with_big.lda_predict(X)
+    _, olab = oracle.lda_predict(X, W, b)
+    assert np.array_equal(lab, olab) and lab[0] == 2
+    with_big.close()
+    for k in STORED:
+        assert np.array_equal(ctx_rec.bgr2gray(rec_frames[k + "_windows"]), rec_frames[k + "_gray"])
+
+
+def test_recognition_window_extraction_golden(ctx_rec, rec_frames, frames3):
+    """x1.15 / 32x32 flavour of K1+K2+K5 (REC:47-64) reproduces the reference's survivors."""
+    for k in STORED:
+        boxes = rec_frames[k + "_boxes"]
+        wins, coords, woff = ctx_rec.windows(frames3[k], boxes, np.array([0, len(boxes)], np.int32))
+        w1, c1, o1 = ctx_rec.dedup(wins, coords, woff, False, 0.85)
+        w2, c2, o2 = ctx_rec.dedup(w1, c1, o1, True, 0.95)
+        assert np.array_equal(c2, rec_frames[k + "_coords"]) and np.array_equal(w2, rec_frames[k + "_windows"])
+
+
+def test_recognition_chain(ctx_rec, rec_frames, frames3, tsd):
+    """detect -> recognise composition: labels of the surviving windows equal the reference's."""
+    for k in STORED:
+        boxes = rec_frames[k + "_boxes"]
+        det, counts = ctx_rec.detect_frames(frames3[k], boxes, np.array([0, len(boxes)], np.int32), mode=tsd.RUN_RECOGNIZE)
+        lab = rec_frames[k + "_pred_lda"]
+        exp = [tuple(int(v) for v in c) + (int(l),) for c, l in zip(rec_frames[k + "_coords"], lab) if l != 0]
+        got = [(int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"])) for d in det]
+        assert got == exp and counts[2] == len(lab)
+
+
+# ---- error behaviour ------------------------------------------------------------------------------------------------------
+def test_errors_are_reported_not_thrown(tsd, templates):
+    with tsd.Context(device=0, flavour="det") as c:
+        with pytest.raises(tsd.TsdError, match="templates not set"):
+            c.score_masks(np.zeros((1, 25, 25), np.uint8), np.zeros((1, 25, 25), np.uint8))
+        with pytest.raises(tsd.TsdError):
+            c.set_templates(np.full((6, 25, 25), 7, np.uint8), np.zeros((6, 25, 25), np.uint8))
+        with pytest.raises(tsd.TsdError):
+            c.lda_predict(np.zeros((1, 324), np.float32))
+    with pytest.raises(tsd.TsdError):
+        tsd.Context(device=99)
