@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-window scoring throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the whole post-MSER detection chain (K1 expand/filter, K2 crop+resize, K5 histogram + fold
+x2, K3 masks, K4 score, detection records) over one batch of synthetic 1360x800 BGR frames with 200 MSER-like
+candidates per frame (BASELINE.json configs[2]).  Frames are sharded by image: every rank owns
+its own batch (weak scaling), no collective on the hot path, one small gather of detection records at the end.
+
+Prints ONE JSON line (rank 0).  `value` = raw candidate windows/s, inputs resident in HBM; `e2e` = the same metric
+through the public host-buffer API (pinned host frames, H2D + D2H inside the timed region); `roofline` = the dominant
+kernel against the measured HBM peak; `cpu_baseline` = the reference pipeline (oracle/ref_port.py: cv2 + the
+reference's Python loops) on the host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NBOX, D = 800, 1360, 200, 25
+UNIQUE_FRAMES = 32
+METRIC = "candidate windows/sec (1360x800 frames, ~200 MSER candidates/frame, detection scoring)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def templates():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "det_templates.npz"))
+    return g["red6"], g["blue6"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(boxes, offsets, counts):
+    """SURVEY.md section 8(d) per-unit figures x the units one launch processes (independent of the implementation).
+    K2: in 3*min(w_c,2D)*min(h_c,2D) + out 3*D*D per aspect-passing window; k5_hist: in 3*D*D + out 8*nnz<=... credited
+    as 3*D*D + 16; fold: in 3*D*D+16 per input window, out 3*D*D+16 per survivor; K3: 3*D*D in, 2*D*D out; K4: 2*D*D in, 8 out."""
+    b = boxes.astype(np.int64)
+    w, h = b[:, 2].astype(np.float64), b[:, 3].astype(np.float64)
+    pm1 = 1.30 - 1
+    ratio = w / np.maximum(h, 1e-300)
+    ok = (0.8 < ratio) & (ratio < 1.20)
+    x1 = np.maximum(b[:, 0] - w * pm1 * 0.5, 0).astype(np.int64); y1 = np.maximum(b[:, 1] - h * pm1 * 0.5, 0).astype(np.int64)
+    x2 = (b[:, 0] + b[:, 2] + w * pm1 * 0.5).astype(np.int64); y2 = (b[:, 1] + b[:, 3] + h * pm1 * 0.5).astype(np.int64)
+    cw = np.minimum(x2, W) - np.minimum(x1, W); ch = np.minimum(y2, H) - np.minimum(y1, H)
+    k2_in = (3 * np.minimum(cw, 2 * D) * np.minimum(ch, 2 * D))[ok].sum()
+    npass, nsurv = int(ok.sum()), int(counts[2])
+    px = D * D
+    return {
+        "k1_expand_filter": int(len(b) * 33),
+        "k2_crop_resize": int(k2_in + npass * 3 * px),
+        "k5_hist": int(npass * (3 * px + 16)),
+        "k5_fold": int(npass * (3 * px + 16) + nsurv * (3 * px + 16)),
+        "k3_masks": int(nsurv * 5 * px),
+        "k4_score": int(nsurv * (2 * px + 8)),
+        "detections": int(counts[3] * 32),
+    }, npass
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU pipeline (oracle/ref_port.py) on all host cores, same config/metric.
+    Rank 0 alone runs; the other ranks exit 0."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import tsd_b200
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    red6, blue6 = templates()
+    fpc = max(1, args.cpu_frames_per_core)
+    F = cores * fpc
+    frames = tsd_b200.synth.make_frames(min(F, UNIQUE_FRAMES))
+    frames = frames[np.arange(F) % len(frames)]
+    boxes, off = tsd_b200.synth.make_boxes(F, NBOX)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=ref_port._worker_init, initargs=(red6, blue6)) as pool:
+        for _ in range(args.warmup):
+            ref_port.run_parallel(pool, frames[:cores], boxes[:off[cores]], off[:cores + 1], cores)
+        t0 = time.perf_counter()
+        ndet = 0
+        for _ in range(args.steps):
+            ndet += ref_port.run_parallel(pool, frames, boxes, off, cores)
+        dt = time.perf_counter() - t0
+    value = F * NBOX * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "frames_per_sec": F * args.steps / dt,
+        "config": {"workload": "synthetic 1360x800 BGR frames, 200 MSER-like candidates/frame, detection-only scoring (BASELINE configs[2])",
+                   "frames_per_step": F, "boxes_per_frame": NBOX},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": "%d frames x %d candidates per step (%d per core), oracle/ref_port.py = reference pipeline with cv2 + its Python loops" % (F, NBOX, fpc)},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "detections": ndet,
+    }
+    print(json.dumps(out))
+
+
+def cpu_baseline_sample(args):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1): ~64 frames."""
+    import multiprocessing as mp
+    import tsd_b200
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    red6, blue6 = templates()
+    F = max(cores, 64 // cores * cores)
+    frames = tsd_b200.synth.make_frames(min(F, UNIQUE_FRAMES))
+    frames = frames[np.arange(F) % len(frames)]
+    boxes, off = tsd_b200.synth.make_boxes(F, NBOX)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=ref_port._worker_init, initargs=(red6, blue6)) as pool:
+        ref_port.run_parallel(pool, frames[:cores], boxes[:off[cores]], off[:cores + 1], cores)      # warm the workers
+        t0 = time.perf_counter()
+        ref_port.run_parallel(pool, frames, boxes, off, cores)
+        dt = time.perf_counter() - t0
+    return {"value": F * NBOX / dt, "unit": "windows/s", "cores": cores, "kind": "port", "frames_per_sec": F / dt, "seconds": dt,
+            "sample": "%d frames x %d candidates, one worker per host core, oracle/ref_port.py (reference pipeline: cv2 + its Python loops)" % (F, NBOX)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    # The CPU baseline forks worker processes: run it BEFORE this process touches CUDA (rank 0, N=1 only)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_sample(args)
+    import torch
+    import tsd_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    red6, blue6 = templates()
+    F = args.frames
+    uniq = tsd_b200.synth.make_frames(UNIQUE_FRAMES, seed=tsd_b200.synth.FRAME_SEED + rank)
+    boxes, off = tsd_b200.synth.make_boxes(F, NBOX, seed=tsd_b200.synth.BOX_SEED + rank)
+    d_uniq = torch.from_numpy(uniq).to(dev)
+    d_frames = d_uniq[torch.arange(F, device=dev) % UNIQUE_FRAMES].contiguous()     # F distinct resident frames (3.26 MB each)
+    del d_uniq
+    d_boxes = torch.from_numpy(boxes).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    nb = int(off[-1])
+
+    ctx = tsd_b200.Context(device=local_rank, flavour="det")
+    ctx.set_templates(red6, blue6)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step():
+        ctx.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), nb)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.synchronize()
+    det, counts = ctx.fetch_detections(nb)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, per-stage events inside ----------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    ctx.set_profiling(True)
+    l0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    ctx.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - l0
+    stage_ms = dict(ctx.stage_times())
+    ctx.set_profiling(False)
+    det, counts = ctx.fetch_detections(nb)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        from tsd_b200 import sharding
+        allrec = sharding.gather_detections(det, rank * F, dist, device=dev)      # the one small NCCL gather, for the report
+        ndet_total = len(allrec)
+    else:
+        ndet_total = len(det)
+    value = world * F * NBOX * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public host-buffer API, pinned host frames, H2D + D2H inside the timed region --------------------------
+    Fe = min(args.e2e_frames, F)
+    h_frames = torch.empty((Fe, H, W, 3), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(d_frames[:Fe].cpu())
+    hf = h_frames.numpy()
+    hb, ho = boxes[:off[Fe]], off[:Fe + 1]
+    for _ in range(2):
+        edet, ecounts = ctx.detect_frames(hf, hb, ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        edet, ecounts = ctx.detect_frames(hf, hb, ho)
+    ctx.synchronize()
+    e_dt = (time.perf_counter() - t0) / args.e2e_steps
+    if dist is not None:
+        t = torch.tensor([e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.item())
+    e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(hf.nbytes + hb.nbytes + ho.nbytes),
+           "d2h_bytes_per_step": int(len(edet) * 32 + 12), "frames_per_step": Fe, "ms_per_step": e_dt * 1e3,
+           "frames_per_sec": world * Fe / e_dt, "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST, pinned host frames)"}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg, npass = algorithmic_bytes(boxes, off, counts)
+        per_stage = {k: v / args.steps for k, v in stage_ms.items()}
+        dom = max(per_stage, key=per_stage.get) if per_stage else "k2_crop_resize"
+        achieved = alg.get(dom, 0) / (per_stage.get(dom, 1e9) * 1e-3) / 1e9
+        fused_bytes = sum(alg.values())
+        out = {
+            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "frames_per_sec": world * F * args.steps / (ms * 1e-3),
+            "config": {"workload": "synthetic 1360x800 BGR frames, 200 MSER-like candidates/frame, detection-only scoring (BASELINE configs[2])",
+                       "frames_per_gpu": F, "boxes_per_frame": NBOX, "window": D, "parallelism": "frames sharded by image, dp%d" % world,
+                       "l2": "inputs larger than L2: %d resident frames (%.1f GB) per GPU, ROI bytes touched per step %.0f MB"
+                             % (F, F * H * W * 3 / 1e9, alg["k2_crop_resize"] / 1e6)},
+            "stage_counts": {"raw": int(counts[0]), "aspect_passing": int(counts[1]), "survivors": int(counts[2]), "detections": int(counts[3])},
+            "detections_all_ranks": int(ndet_total),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom, 0),
+                         "kernel_ms_per_launch": per_stage.get(dom)},
+            "stages_ms_per_step": per_stage,
+            "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in per_stage.items() if v > 0},
+            "chain": {"algorithmic_bytes_per_step": fused_bytes, "gbs": fused_bytes / (ms / args.steps * 1e-3) / 1e9,
+                      "frac_of_peak": fused_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu_base is not None:
+            out["cpu_baseline"] = cpu_base
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1024, help="resident frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-frames-per-core", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        os.environ["WORLD_SIZE_LAUNCHED"] = "1"
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

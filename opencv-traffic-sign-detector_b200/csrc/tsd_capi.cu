@@ -212,20 +212,30 @@ int64_t tsd_launch_count(tsd_ctx* c) { return c ? c->launches : 0; }
 int tsd_set_profiling(tsd_ctx* c, int on) {
     if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
     c->profiling = on != 0;
+    c->ev_used = 0;                                          // (re)start accumulating
     return TSD_OK;
 }
 
+// Sums, per stage name, the CUDA-event time between consecutive marks of every tsd_enqueue_frames call made since
+// tsd_set_profiling(ctx, 1).  Synchronises the stream.
 int tsd_stage_times(tsd_ctx* c, const char** names, float* ms, int cap) {
     if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    int n = 0;
-    for (int i = 1; i < c->ev_used && n < cap; i++, n++) {
+    static thread_local std::vector<std::string> uniq;
+    uniq.clear();
+    std::vector<float> sum;
+    for (int i = 1; i < c->ev_used; i++) {
+        if (c->ev_names[i] == "start") continue;
         float t = 0;
         cudaEventElapsedTime(&t, c->ev[i - 1], c->ev[i]);
-        names[n] = c->ev_names[i].c_str();
-        ms[n] = t;
+        size_t k = 0;
+        while (k < uniq.size() && uniq[k] != c->ev_names[i]) k++;
+        if (k == uniq.size()) { uniq.push_back(c->ev_names[i]); sum.push_back(0.f); }
+        sum[k] += t;
     }
+    int n = 0;
+    for (size_t k = 0; k < uniq.size() && n < cap; k++, n++) { names[n] = uniq[k].c_str(); ms[n] = sum[k]; }
     return n;
 }
 
@@ -713,7 +723,6 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     int32_t *detcnt = (int32_t*)c->b_detcnt.p, *detoff = (int32_t*)c->b_detoff.p;
     int32_t* coords = (int32_t*)c->b_coords.p;
     uint8_t* windows = (uint8_t*)c->b_windows.p;
-    c->ev_used = 0;
     mark(c, "start");
     // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
     TRY(dev_windows_index(c, d_boxes, d_box_offsets, nframes, H, W, c->cfg.enlarge, cnt, winoff, coords, (int32_t*)c->b_winframe.p));
