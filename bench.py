@@ -213,7 +213,7 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def step():
-        ctx.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), nb)
+        ctx.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), nb, max_boxes_per_frame=NBOX)
 
     for _ in range(max(args.warmup, 3)):
         step()

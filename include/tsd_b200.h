@@ -177,14 +177,16 @@ TSD_API int tsd_detect_frames(tsd_ctx *ctx, int mode, const uint8_t *frames, int
 
 /* Same chain, device-resident and asynchronous: enqueues the kernels on the context's stream and returns.  Results
  * stay in context-owned device buffers; fetch them with tsd_fetch_detections (which synchronises).  bench.py times
- * this call with CUDA events. */
+ * this call with CUDA events.  max_boxes_per_frame = largest box_offsets[f+1]-box_offsets[f] (sizes the per-frame
+ * pair matrix of K5); pass 0 to let the library read the offsets back (one small synchronising copy). */
 TSD_API int tsd_enqueue_frames(tsd_ctx *ctx, int mode, const uint8_t *d_frames, int nframes, int H, int W,
                                int64_t row_stride, int64_t frame_stride, const int32_t *d_boxes,
-                               const int32_t *d_box_offsets, int nboxes_total);
+                               const int32_t *d_box_offsets, int nboxes_total, int max_boxes_per_frame);
 TSD_API int tsd_fetch_detections(tsd_ctx *ctx, tsd_detection *det, int det_cap, int32_t *ndet, int32_t *counts);
 
-/* Device-side stage timing of the last tsd_enqueue_frames when profiling was enabled with tsd_set_profiling(ctx,1):
- * names[i] / ms[i] for i < returned count (CUDA events between stages; adds no host synchronisation). */
+/* Device-side stage timing: CUDA events are recorded between the stages of every tsd_enqueue_frames call made after
+ * tsd_set_profiling(ctx, 1); tsd_stage_times synchronises and returns, per stage name, the time summed over those
+ * calls (names[i] / ms[i] for i < returned count). */
 TSD_API int tsd_set_profiling(tsd_ctx *ctx, int on);
 TSD_API int tsd_stage_times(tsd_ctx *ctx, const char **names, float *ms, int cap);
 

@@ -69,7 +69,7 @@ _SIGNATURES = {
     "tsd_lda_predict": (_i, [_vp, _vp, _i, _d, _vp, _vp, _i]),
     "tsd_knn_predict": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
     "tsd_detect_frames": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i]),
-    "tsd_enqueue_frames": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _i]),
+    "tsd_enqueue_frames": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _i, _i]),
     "tsd_fetch_detections": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tsd_set_profiling": (_i, [_vp, _i]),
     "tsd_stage_times": (_i, [_vp, _vp, _vp, _i]),
@@ -81,7 +81,8 @@ EXPORTS = tuple(sorted(_SIGNATURES))
 def build(force=False):
     """Compile csrc/ for sm_100a with nvcc (in-tree .so).  Cross-compiles without a GPU."""
     src_dir = os.path.join(_PKG, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("tsd_capi.cu", "tsd_kernels.cuh")] + [os.path.join(_PKG, "..", "include", "tsd_b200.h")]
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(_PKG, "..", "include", "tsd_b200.h"))
     stale = not os.path.isfile(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", src_dir, "-s"] + (["-B"] if force else []))

@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this file: every entry point launches CUDA kernels or fails.
 #include "../../include/tsd_b200.h"
 #include "tsd_kernels.cuh"
+#include "tsd_fold2.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -54,13 +55,14 @@ struct tsd_ctx {
     int tmpl_D = 0;
     double* d_simtab = nullptr;
     int simtab_n = 0;
+    std::vector<double> h_simtab;
     double* d_ldaW = nullptr; double* d_ldab = nullptr; int lda_nfeat = 0;
     double* d_xbar = nullptr; double* d_scal = nullptr; double* d_Zt = nullptr; int32_t* d_yt = nullptr;
     int knn_nfeat = 0, knn_ntrain = 0, knn_k = 4;
     HogConst hog;
     // grow-only scratch
     DevBuf b_coords, b_winframe, b_windows, b_entries, b_meta, b_list, b_flags, b_cnt, b_winoff, b_survcnt, b_survoff,
-        b_slots, b_red, b_blue, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
+        b_slots, b_pairs, b_energy, b_red, b_blue, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
     // last enqueue
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
@@ -174,6 +176,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     CU(cudaMalloc(&c->d_simtab, sizeof(double) * n));
     CU(cudaMemcpy(c->d_simtab, f.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     c->simtab_n = n;
+    c->h_simtab = f;
     {   // HOG Gaussian window, sigma = (16+16)/8 = 4  (OpenCV HOGCache::init)
         float sigma = 4.f, sc = 1.f / (sigma * sigma * 2);
         for (int i = 0; i < 16; i++) { float di = i - 16 * 0.5f; c->hog.gauss[i] = expf(-di * di * sc); }
@@ -187,7 +190,7 @@ int tsd_destroy(tsd_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
-                      &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_red, &c->b_blue, &c->b_id, &c->b_hund,
+                      &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
@@ -289,6 +292,7 @@ int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
     CU(cudaMalloc(&c->d_simtab, sizeof(double) * n));
     CU(cudaMemcpy(c->d_simtab, f, sizeof(double) * n, cudaMemcpyHostToDevice));
     c->simtab_n = n;
+    c->h_simtab.assign(f, f + n);
     return TSD_OK;
 }
 
@@ -367,10 +371,15 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
                            const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows) {
     if (n_max == 0) return TSD_OK;
-    if (ch == 3)
-        k2_crop_resize_kernel<3><<<cdiv(n_max, 4), 128, 0, c->stream>>>(frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max, D, windows);
-    else
-        k2_crop_resize_kernel<1><<<cdiv(n_max, 4), 128, 0, c->stream>>>(frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max, D, windows);
+    const int g4 = cdiv(n_max, 4);
+#define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
+    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
+    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows);      // other window sizes: generic kernel
+    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows);
+#undef K2_ARGS
     return check_launch(c, "k2_crop_resize");
 }
 
@@ -390,15 +399,21 @@ static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* bo
     return check_launch(c, "k1_compact");
 }
 
-static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, uint32_t* entries, WinMeta* meta) {
+static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, uint32_t* entries, WinMeta* meta,
+                    float* E_T, int64_t e_stride) {
     if (n_max == 0) return TSD_OK;
-    int grid = n_max < c->sm_count * 16 ? n_max : c->sm_count * 16;
-    k5_hist_kernel<<<grid, 128, 0, c->stream>>>(windows, n_ptr, n_max, npx, c->d_tab, entries, meta);
+    int grid = cdiv(n_max, kHistWarps);
+    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    k5_hist_v2_kernel<<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, c->d_tab, entries, meta, E_T, e_stride);
     return check_launch(c, "k5_hist");
 }
 
+// K5: both (or one) passes of cleanDuplicatedDetections.  max_n = upper bound of windows per frame (host-known).
+// max_n <= 2048: all-pairs classification (k5_pairs) + warp-driven fold (k5_fold2); larger frames: the general
+// block-synchronous fold (k5_fold_kernel).
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
-                    int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count) {
+                    int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
+                    int max_n, const float* E_T, int64_t e_stride) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
@@ -406,8 +421,41 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int32_t* coords, uint32_t* ent
     P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
     P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
     if (nframes == 0) return TSD_OK;
-    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->stream>>>(P, nframes);
-    return check_launch(c, "k5_fold");
+    if (max_n > 2048) {
+        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->stream>>>(P, nframes);
+        return check_launch(c, "k5_fold");
+    }
+    int R = ((max_n > 1 ? max_n : 1) + 15) & ~15;
+    // Corner similarity can only act when sqrt(f1 f2) >= coord_lo, i.e. both f >= coord_lo^2: squared distances at or
+    // beyond `cut` are class 0 without a table lookup (f is non-increasing in d2).
+    int cut = c->simtab_n;
+    {
+        const double thr = P.coord_lo * P.coord_lo * (1.0 - 1e-9);
+        int lo_i = 0, hi_i = c->simtab_n;                    // first index with f < thr
+        while (lo_i < hi_i) { int mid = (lo_i + hi_i) / 2; if (c->h_simtab[mid] < thr) hi_i = mid; else lo_i = mid + 1; }
+        cut = lo_i > 0 ? lo_i : 1;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(k5_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * (kHistBins + 8) * 2));
+        CU(cudaFuncSetAttribute(k5_fold2_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fold2Smem<2048>)));
+        attr_done = true;
+    }
+    uint8_t* M = nullptr;
+    if (do_hist) {
+        TRY(ensure(c, c->b_pairs, (size_t)nframes * R * R));
+        M = (uint8_t*)c->b_pairs.p;
+        const int tiles = (R + kPairWarps - 1) / kPairWarps;
+        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * (kHistBins + 8) * 2, c->stream>>>(entries, meta, E_T, e_stride, offsets, nframes, npx, R, tiles,
+                                                                                                           P.hist_tol, P.hist_lo, M);
+        TRY(check_launch(c, "k5_pairs"));
+        mark(c, "k5_pairs");
+    }
+    if (max_n <= 256)
+        k5_fold2_kernel<256><<<nframes, kFold2Threads, sizeof(Fold2Smem<256>), c->stream>>>(P, nframes, M, R, cut);
+    else
+        k5_fold2_kernel<2048><<<nframes, kFold2Threads, sizeof(Fold2Smem<2048>), c->stream>>>(P, nframes, M, R, cut);
+    return check_launch(c, "k5_fold2");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -489,7 +537,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     const int n = offsets[nframes], npx = D * D, nbytes = npx * 3;
     if (n && (!windows || !coords)) return fail(TSD_E_INVALID, "NULL argument");
     Stage s(c);
-    void *dw, *dc, *doff, *dent, *dmeta, *dlist, *dflags, *dcnt, *dooff, *dow, *doc;
+    void *dw, *dc, *doff, *dent, *dmeta, *dlist, *dflags, *dcnt, *dooff, *dow, *doc, *den;
     TRY(s.in(windows, (size_t)n * nbytes, &dw));
     TRY(s.in(coords, (size_t)n * 16, &dc));
     TRY(s.in(offsets, (size_t)(nframes + 1) * 4, &doff));
@@ -497,6 +545,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
     TRY(s.alloc(&dlist, (size_t)n * 4));
     TRY(s.alloc(&dflags, (size_t)n));
+    TRY(s.alloc(&den, (size_t)(n > 0 ? n : 1) * kHistGroups * 4));
     TRY(s.alloc(&dcnt, (size_t)(nframes + 1) * 4));
     TRY(s.alloc(&dooff, (size_t)(nframes + 1) * 4));
     TRY(s.alloc(&dow, (size_t)n * nbytes));
@@ -506,11 +555,13 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
             k5_hash_kernel<<<n, 128, 0, c->stream>>>((uint8_t*)dw, n, npx, (WinMeta*)dmeta);
             TRY(check_launch(c, "k5_hash"));
         } else {
-            TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta));
+            TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta, (float*)den, n));
         }
     }
+    int max_n = 0;
+    for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
     TRY(dev_fold(c, (uint8_t*)dw, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt));
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (float*)den, n));
     TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
     if (nframes) {
         k5_gather_kernel<<<nframes, 128, 0, c->stream>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes,
@@ -540,7 +591,7 @@ int tsd_hist(tsd_ctx* c, const uint8_t* windows, int n, int D, float* hist, int 
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dh, (size_t)n * kHistBins * 4)); }
     TRY(s.alloc(&dent, (size_t)n * npx * 4));
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
-    TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta));
+    TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta, nullptr, 0));
     hist_dense_kernel<<<n, 256, 0, c->stream>>>((uint32_t*)dent, (WinMeta*)dmeta, n, npx, (float*)dh);
     TRY(check_launch(c, "hist_dense"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(hist, dh, (size_t)n * kHistBins * 4)); CU(cudaStreamSynchronize(c->stream)); }
@@ -685,7 +736,7 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 
 // ---- whole chain -------------------------------------------------------------------------------------------------
 int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
-                       const int32_t* d_boxes, const int32_t* d_box_offsets, int nb) {
+                       const int32_t* d_boxes, const int32_t* d_box_offsets, int nb, int max_boxes_per_frame) {
     if (!c || !d_frames || !d_box_offsets || nframes < 1 || nb < 0 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
     if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
     if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
@@ -694,6 +745,12 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
     CU(cudaSetDevice(c->device));
     const size_t cap = nb > 0 ? nb : 1;
+    if (max_boxes_per_frame <= 0) {                          // not given: one small D2H of the CSR offsets (synchronises)
+        std::vector<int32_t> ho(nframes + 1);
+        CU(cudaMemcpyAsync(ho.data(), d_box_offsets, (size_t)(nframes + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int f = 0; f < nframes; f++) max_boxes_per_frame = ho[f + 1] - ho[f] > max_boxes_per_frame ? ho[f + 1] - ho[f] : max_boxes_per_frame;
+    }
     TRY(ensure(c, c->b_cnt, (size_t)(nframes + 1) * 4));
     TRY(ensure(c, c->b_winoff, (size_t)(nframes + 1) * 4));
     TRY(ensure(c, c->b_survcnt, (size_t)(nframes + 1) * 4));
@@ -705,6 +762,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_windows, cap * nbytes));
     TRY(ensure(c, c->b_entries, cap * npx * 4));
     TRY(ensure(c, c->b_meta, cap * sizeof(WinMeta)));
+    TRY(ensure(c, c->b_energy, cap * kHistGroups * 4));
     TRY(ensure(c, c->b_list, cap * 4));
     TRY(ensure(c, c->b_flags, cap));
     TRY(ensure(c, c->b_slots, cap * 4));
@@ -732,10 +790,10 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, (int32_t*)c->b_winframe.p, d_nwin, nb, D, windows));
     mark(c, "k2_crop_resize");
     // K5 (DET:127-129)
-    TRY(dev_hist(c, windows, d_nwin, nb, npx, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p));
+    TRY(dev_hist(c, windows, d_nwin, nb, npx, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, (float*)c->b_energy.p, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, coords, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, winoff, nframes, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt));
+                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt, max_boxes_per_frame, (float*)c->b_energy.p, (int64_t)cap));
     TRY(dev_scan(c, survcnt, nframes, survoff));
     k5_gather_kernel<<<nframes, 32, 0, c->stream>>>(windows, (int4*)coords, winoff, (int32_t*)c->b_list.p, survoff, nframes, nbytes, nullptr, nullptr, (int32_t*)c->b_slots.p);
     TRY(check_launch(c, "k5_gather"));
@@ -809,7 +867,7 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         int32_t nb = 0;
         CU(cudaMemcpyAsync(&nb, box_offsets + nframes, 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        TRY(tsd_enqueue_frames(c, mode, frames, nframes, H, W, row_stride, frame_stride, boxes, box_offsets, nb));
+        TRY(tsd_enqueue_frames(c, mode, frames, nframes, H, W, row_stride, frame_stride, boxes, box_offsets, nb, 0));
         return tsd_fetch_detections(c, det, det_cap, ndet, counts);
     }
     const int nb = box_offsets[nframes];
@@ -819,7 +877,9 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
     TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3, &df));
     TRY(s.in(boxes, (size_t)nb * 16, &db));
     TRY(s.in(box_offsets, (size_t)(nframes + 1) * 4, &dbo));
-    TRY(tsd_enqueue_frames(c, mode, (uint8_t*)df, nframes, H, W, row_stride, frame_stride, (int32_t*)db, (int32_t*)dbo, nb));
+    int max_n = 0;
+    for (int f = 0; f < nframes; f++) max_n = box_offsets[f + 1] - box_offsets[f] > max_n ? box_offsets[f + 1] - box_offsets[f] : max_n;
+    TRY(tsd_enqueue_frames(c, mode, (uint8_t*)df, nframes, H, W, row_stride, frame_stride, (int32_t*)db, (int32_t*)dbo, nb, max_n));
     return tsd_fetch_detections(c, det, det_cap, ndet, counts);
 }
 

@@ -213,6 +213,100 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
     }
 }
 
+// K2 v2: same arithmetic, restructured for instruction count (v1 was issue-bound at ~100 instructions per output
+// byte-iteration).  One warp per window, lane = destination column; the x coefficients live in registers, the y
+// coefficients are computed by lane dy and broadcast by shuffle; each lane walks the D destination rows and reads its
+// 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
+template <int C, int D>
+__global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
+    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
+    uint8_t* __restrict__ windows) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const int4 c = coords[w];
+    const int cx = min(c.x, W), cy = min(c.y, H);
+    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
+    if (cw <= 0 || ch <= 0) return;
+    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
+    uint8_t* __restrict__ dst = windows + (int64_t)w * D * D * C + lane * C;
+    const bool act = lane < D;
+    const int li = act ? lane : 0;
+    if (cw == D && ch == D) {                               // same size: copy
+        const uint8_t* p = src + li * C;
+#pragma unroll 5
+        for (int dy = 0; dy < D; dy++) {
+            uint8_t v[C];
+#pragma unroll
+            for (int k = 0; k < C; k++) v[k] = __ldg(p + (int64_t)dy * row_stride + k);
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < C; k++) dst[dy * D * C + k] = v[k];
+            }
+        }
+        return;
+    }
+    if (cw == 2 * D && ch == 2 * D) {                       // INTER_AREA 2x2 fast path
+        const uint8_t* p = src + 2 * li * C;
+#pragma unroll 5
+        for (int dy = 0; dy < D; dy++) {
+            const uint8_t* q0 = p + (int64_t)(2 * dy) * row_stride;
+            const uint8_t* q1 = q0 + row_stride;
+            int v[C];
+#pragma unroll
+            for (int k = 0; k < C; k++) v[k] = (__ldg(q0 + k) + __ldg(q0 + C + k) + __ldg(q1 + k) + __ldg(q1 + C + k) + 2) >> 2;
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
+            }
+        }
+        return;
+    }
+    // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
+    int xs0, xd1, xa0, xa1, yr0, yr1, yb0, yb1;
+    {
+        const double scale = 1.0 / ((double)D / (double)cw);
+        float f = (float)(((double)li + 0.5) * scale - 0.5);
+        int s = (int)floorf(f); f -= (float)s;
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= cw - 1) { f = 0.f; s = cw - 1; }
+        xs0 = s * C;
+        xd1 = (min(s + 1, cw - 1) - s) * C;
+        xa0 = __float2int_rn((1.f - f) * 2048.f);
+        xa1 = __float2int_rn(f * 2048.f);
+    }
+    {
+        const double scale = 1.0 / ((double)D / (double)ch);
+        float f = (float)(((double)li + 0.5) * scale - 0.5);
+        int s = (int)floorf(f); f -= (float)s;
+        yr0 = min(max(s, 0), ch - 1);
+        yr1 = min(max(s + 1, 0), ch - 1);
+        yb0 = __float2int_rn((1.f - f) * 2048.f);
+        yb1 = __float2int_rn(f * 2048.f);
+    }
+    const uint8_t* px = src + xs0;
+#pragma unroll 5
+    for (int dy = 0; dy < D; dy++) {
+        const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
+        const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
+        const uint8_t* p0 = px + (int64_t)r0 * row_stride;
+        const uint8_t* p1 = px + (int64_t)r1 * row_stride;
+        int v[C];
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int t0 = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
+            const int t1 = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
+            v[k] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+        }
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
+        }
+    }
+}
+
 // =====================================================================================================
 // K3  getColorMaskRedOrBlue(img,'r'/'b')  (DET:63-89), SURVEY A.3.  One thread per pixel; integer HSV tables.
 // `slots` (optional) = indirection to the surviving windows inside the work buffer.
@@ -315,9 +409,10 @@ __global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict
 //   hash = 64-bit hash of the pixels (used only to pre-filter the pop-by-pixel-equality rule DET:471-477).
 // =====================================================================================================
 struct WinMeta {
-    double s1, s11;
+    double s1, s11;              // sum h, sum h^2 over the 3000 bins (f64)
+    double A, rA;                // A = s11 - s1*s1/N (one factor of compareHist's denom2), rA = sqrt(A)
     unsigned long long hash;
-    float a;
+    float a;                     // (float)(1/max count)
     int32_t nnz;
 };
 
@@ -390,7 +485,8 @@ __device__ void build_hist_block(const uint8_t* __restrict__ px, int npx, const 
     if (tid == 0) {
         double t1 = 0, t11 = 0;
         for (int i = 0; i < nw; i++) { t1 += red[i]; t11 += red[32 + i]; }
-        meta->s1 = t1; meta->s11 = t11; meta->hash = hash_all; meta->a = a; meta->nnz = nnz;
+        const double A = t11 - t1 * t1 * (1.0 / (double)kHistBins);
+        meta->s1 = t1; meta->s11 = t11; meta->A = A; meta->rA = sqrt(A); meta->hash = hash_all; meta->a = a; meta->nnz = nnz;
     }
     __syncthreads();
 }
@@ -427,6 +523,123 @@ __global__ void __launch_bounds__(128) k5_hist_kernel(const uint8_t* __restrict_
         build_hist_block(windows + (int64_t)w * npx * 3, npx, sm.sdiv, sm.hdiv, sm.hbin, sm.sbin, sm.dense, sm.red, e, meta + w);
         clear_dense_block(sm.dense, e, meta[w].nnz);
         __syncthreads();
+    }
+}
+
+// K5a v2: one WARP per window, no block barriers.  Instead of a dense 3000-bin array the warp keeps a 3000-bit
+// occupancy bitmap (94 words) with per-word prefix popcounts: rank(bin) is a perfect hash into a compact count array, and
+// walking the set bits in order emits the (bin, count) entries sorted by bin.  Also emits, per window, the energies
+// E[g] = sqrt(sum_{bin in group g} h^2) of kHistGroups = 25 bin groups (two H rows each), transposed [g][window], which
+// give k5_pairs a Cauchy-Schwarz upper bound of the histogram dot product (sum_g E_x[g] E_y[g] >= sum_b x_b y_b).
+constexpr int kHistGroups = 25;                      // group = bin / 120
+constexpr int kHistWarps = 4;
+
+struct HistWarpSmem {
+    uint32_t bitmap[96];
+    uint32_t prefix[96];
+    uint32_t counts[kMaxPx];
+    uint16_t binbuf[kMaxPx];
+    float energy[32];
+};
+
+__global__ void __launch_bounds__(kHistWarps * 32) k5_hist_v2_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
+                                                                     int n_max, int npx, const Tables* __restrict__ tab,
+                                                                     uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
+                                                                     float* __restrict__ E_T, int64_t e_stride) {
+    __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    __shared__ uint8_t s_hbin[256], s_sbin[256];
+    __shared__ HistWarpSmem s_w[kHistWarps];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        s_sdiv[i] = tab->sdiv[i]; s_hdiv[i] = tab->hdiv[i]; s_hbin[i] = tab->hbin[i]; s_sbin[i] = tab->sbin[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    HistWarpSmem& sw = s_w[wid];
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int nwarps = gridDim.x * kHistWarps;
+    for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps) {
+        const uint8_t* __restrict__ px = windows + (int64_t)w * npx * 3;
+        for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
+        if (lane < 32) sw.energy[lane] = 0.f;
+        __syncwarp();
+        // pass A: bins + occupancy bitmap + pixel hash
+        unsigned long long hsh = 0;
+        for (int p = lane; p < npx; p += 32) {
+            const int b = __ldg(px + 3 * p), g = __ldg(px + 3 * p + 1), r = __ldg(px + 3 * p + 2);
+            int H, S, V;
+            bgr2hsv(b, g, r, s_sdiv, s_hdiv, H, S, V);
+            const int bin = (int)s_hbin[H] * kHistS + (int)s_sbin[S];
+            sw.binbuf[p] = (uint16_t)bin;
+            atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
+            hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(b | (g << 8) | (r << 16)));
+        }
+        __syncwarp();
+        // per-word prefix popcounts (lane owns words 3*lane .. 3*lane+2)
+        const uint32_t w0 = sw.bitmap[3 * lane], w1 = sw.bitmap[3 * lane + 1], w2 = sw.bitmap[3 * lane + 2];
+        const int c0 = __popc(w0), c1 = __popc(w1), c2 = __popc(w2);
+        int incl = c0 + c1 + c2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int excl = incl - (c0 + c1 + c2);
+        const int nnz = __shfl_sync(0xffffffffu, incl, 31);
+        sw.prefix[3 * lane] = excl; sw.prefix[3 * lane + 1] = excl + c0; sw.prefix[3 * lane + 2] = excl + c0 + c1;
+        for (int i = lane; i < nnz; i += 32) sw.counts[i] = 0;
+        __syncwarp();
+        // pass B: counts through the rank hash
+        for (int p = lane; p < npx; p += 32) {
+            const int bin = sw.binbuf[p];
+            const uint32_t word = sw.bitmap[bin >> 5];
+            atomicAdd(&sw.counts[sw.prefix[bin >> 5] + __popc(word & ((1u << (bin & 31)) - 1))], 1u);
+        }
+        __syncwarp();
+        unsigned mx = 0;
+        for (int i = lane; i < nnz; i += 32) mx = max(mx, sw.counts[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        // normalize: scale = 1/(max-min) in f64 (min == 0), a = (float)scale (cv2.normalize NORM_MINMAX -> convertTo)
+        const double scale = ((double)mx - 0.0) > DBL_EPSILON ? 1.0 / ((double)mx - 0.0) : 0.0;
+        const float a = (float)scale;
+        // emit entries sorted by bin; moments in bin order per lane, then a fixed shuffle tree (deterministic)
+        uint32_t* __restrict__ e = entries + (int64_t)w * npx;
+        double s1 = 0, s11 = 0;
+        int idx = excl;
+        float eg = 0.f; int cur_g = -1;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            uint32_t word = t == 0 ? w0 : (t == 1 ? w1 : w2);
+            const int bbase = (3 * lane + t) * 32;
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int bin = bbase + bit;
+                const uint32_t cnt = sw.counts[idx];
+                e[idx] = ((uint32_t)bin << 16) | cnt;
+                idx++;
+                const float hf = (float)cnt * a;
+                const double h = (double)hf;
+                s1 += h; s11 += h * h;
+                const int g = bin / 120;
+                if (g != cur_g) { if (cur_g >= 0) atomicAdd(&sw.energy[cur_g], eg); cur_g = g; eg = 0.f; }
+                eg += hf * hf;
+            }
+        }
+        if (cur_g >= 0) atomicAdd(&sw.energy[cur_g], eg);
+        s1 = warp_sum(s1); s11 = warp_sum(s11);
+        unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
+            hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const double A = s11 - s1 * s1 * (1.0 / (double)kHistBins);
+            WinMeta m;
+            m.s1 = s1; m.s11 = s11; m.A = A; m.rA = sqrt(A); m.hash = hsh; m.a = a; m.nnz = nnz;
+            meta[w] = m;
+        }
+        if (E_T && lane < kHistGroups) E_T[(int64_t)lane * e_stride + w] = sqrtf(sw.energy[lane]) * 1.00001f;   // inflated: only ever an upper bound
+        __syncwarp();
     }
 }
 

@@ -248,12 +248,13 @@ class Context:
         return det[:nd.value].copy(), counts
 
     def enqueue_frames(self, d_frames, nframes, H, W, d_boxes, d_box_offsets, nboxes_total, mode=RUN_DETECT,
-                       row_stride=None, frame_stride=None):
-        """Asynchronous, device-resident chain (integer device pointers, e.g. torch tensor .data_ptr())."""
+                       row_stride=None, frame_stride=None, max_boxes_per_frame=0):
+        """Asynchronous, device-resident chain (integer device pointers, e.g. torch tensor .data_ptr()).
+        max_boxes_per_frame: largest per-frame candidate count (0 = let the library read the offsets back)."""
         rs = W * 3 if row_stride is None else int(row_stride)
         fs = H * rs if frame_stride is None else int(frame_stride)
         check(self._L.tsd_enqueue_frames(self._h, int(mode), ptr(int(d_frames)), int(nframes), int(H), int(W), rs, fs,
-                                         ptr(int(d_boxes)), ptr(int(d_box_offsets)), int(nboxes_total)))
+                                         ptr(int(d_boxes)), ptr(int(d_box_offsets)), int(nboxes_total), int(max_boxes_per_frame)))
 
     def fetch_detections(self, cap):
         det = np.zeros(max(int(cap), 1), DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)

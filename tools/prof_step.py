@@ -1,0 +1,37 @@
+"""Small driver for ncu / timing experiments: N steps of the device-resident detection chain on synthetic frames."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tsd_b200
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=256)
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--boxes", type=int, default=200)
+ap.add_argument("--H", type=int, default=800)
+ap.add_argument("--W", type=int, default=1360)
+ap.add_argument("--times", action="store_true")
+a = ap.parse_args()
+g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "det_templates.npz"))
+U = min(16, a.frames)
+uniq = tsd_b200.synth.make_frames(U, a.H, a.W)
+boxes, off = tsd_b200.synth.make_boxes(a.frames, a.boxes, a.H, a.W)
+dev = torch.device("cuda", 0)
+d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(a.frames, device=dev) % U].contiguous()
+d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+ctx = tsd_b200.Context(0, "det")
+ctx.set_templates(g["red6"], g["blue6"])
+if a.times:
+    ctx.set_profiling(True)
+for _ in range(a.steps):
+    ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=a.boxes)
+ctx.synchronize()
+if a.times:
+    print({k: round(v / a.steps, 4) for k, v in ctx.stage_times()})
+det, counts = ctx.fetch_detections(int(off[-1]))
+print("counts", counts.tolist(), "ndet", len(det))
