@@ -1,0 +1,19 @@
+"""Per-kernel summary of an .ncu-rep (raw page): duration, DRAM bytes, throughput %, occupancy, instructions."""
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr = rows[0]
+keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'smsp__inst_executed.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum', 'lts__t_bytes.sum',
+        'launch__grid_size', 'launch__block_size']
+units = rows[1]
+idx = {k: hdr.index(k) for k in keys if k in hdr}
+for r in rows[2:]:
+    print({k.split('.')[0].replace('__', '.'): (r[i][:60] if k == 'Kernel Name' else r[i] + ' ' + units[i]) for k, i in idx.items()})
