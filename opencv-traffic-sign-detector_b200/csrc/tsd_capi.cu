@@ -3,7 +3,7 @@
 // There is no CPU fallback anywhere in this file: every entry point launches CUDA kernels or fails.
 #include "../../include/tsd_b200.h"
 #include "tsd_kernels.cuh"
-#include "tsd_fold2.cuh"
+#include "tsd_k5.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -368,17 +368,18 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
     return check_launch(c, "k1_expand");
 }
 
+// out_stride = bytes between output windows: D*D*ch (public packed layout) or win_stride() (internal, zero padded)
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
-                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows) {
+                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride) {
     if (n_max == 0) return TSD_OK;
     const int g4 = cdiv(n_max, 4);
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
-    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows);
-    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows);      // other window sizes: generic kernel
-    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows);
+    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
+    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
     return check_launch(c, "k2_crop_resize");
 }
@@ -399,33 +400,50 @@ static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* bo
     return check_launch(c, "k1_compact");
 }
 
-static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, uint32_t* entries, WinMeta* meta,
+// ws = bytes between windows (packed or padded); entries are written with stride ent_stride(npx) words
+static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, int ws, uint32_t* entries, WinMeta* meta,
                     float* E_T, int64_t e_stride) {
     if (n_max == 0) return TSD_OK;
     int grid = cdiv(n_max, kHistWarps);
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-    k5_hist_v2_kernel<<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, c->d_tab, entries, meta, E_T, e_stride);
+    if (npx <= 640)
+        k5_hist_kernel<640><<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+    else
+        k5_hist_kernel<1024><<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     return check_launch(c, "k5_hist");
 }
 
-// K5: both (or one) passes of cleanDuplicatedDetections.  max_n = upper bound of windows per frame (host-known).
-// max_n <= 2048: all-pairs classification (k5_pairs) + warp-driven fold (k5_fold2); larger frames: the general
-// block-synchronous fold (k5_fold_kernel).
-static int dev_fold(tsd_ctx* c, uint8_t* windows, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
+// K5: both (or one) passes of cleanDuplicatedDetections.  max_n = upper bound of windows per frame (host-known), ncap = total
+// windows (rows of the pair-class bit matrix).  max_n <= 1024: all-pairs classification (k5_pairs) + one warp per frame
+// (k5_fold_warp); larger frames: the general block-synchronous fold (k5_fold_kernel).
+template <int RMAX, int CAP>
+static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut) {
+    const int warps = RMAX <= 256 ? kFoldWarps : 2;
+    const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<RMAX, CAP>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k5_fold_warp_kernel<RMAX, CAP><<<cdiv(nframes, warps), warps * 32, smem, c->stream>>>(P, nframes, M, RW, cut);
+    return check_launch(c, "k5_fold_warp");
+}
+
+static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, const float* E_T, int64_t e_stride) {
+                    int max_n, size_t ncap, const float* E_T, int64_t e_stride) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
-    P.npx = npx; P.do_hist = do_hist; P.do_coords = do_coords;
+    P.npx = npx; P.ws = ws; P.es = ent_stride(npx); P.do_hist = do_hist; P.do_coords = do_coords;
     P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
     P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
     if (nframes == 0) return TSD_OK;
-    if (max_n > 2048) {
+    if (max_n > 1024) {
         k5_fold_kernel<<<nframes, kFoldThreads, 0, c->stream>>>(P, nframes);
         return check_launch(c, "k5_fold");
     }
-    int R = ((max_n > 1 ? max_n : 1) + 15) & ~15;
+    const int RW = ((max_n > 1 ? max_n : 1) + 31) / 32;
     // Corner similarity can only act when sqrt(f1 f2) >= coord_lo, i.e. both f >= coord_lo^2: squared distances at or
     // beyond `cut` are class 0 without a table lookup (f is non-increasing in d2).
     int cut = c->simtab_n;
@@ -435,27 +453,23 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int32_t* coords, uint32_t* ent
         while (lo_i < hi_i) { int mid = (lo_i + hi_i) / 2; if (c->h_simtab[mid] < thr) hi_i = mid; else lo_i = mid + 1; }
         cut = lo_i > 0 ? lo_i : 1;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU(cudaFuncSetAttribute(k5_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * (kHistBins + 8) * 2));
-        CU(cudaFuncSetAttribute(k5_fold2_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fold2Smem<2048>)));
-        attr_done = true;
-    }
-    uint8_t* M = nullptr;
+    uint32_t* M = nullptr;
     if (do_hist) {
-        TRY(ensure(c, c->b_pairs, (size_t)nframes * R * R));
-        M = (uint8_t*)c->b_pairs.p;
-        const int tiles = (R + kPairWarps - 1) / kPairWarps;
-        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * (kHistBins + 8) * 2, c->stream>>>(entries, meta, E_T, e_stride, offsets, nframes, npx, R, tiles,
-                                                                                                           P.hist_tol, P.hist_lo, M);
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU(cudaFuncSetAttribute(k5_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * kDenseLen * 2));
+            attr_done = true;
+        }
+        TRY(ensure(c, c->b_pairs, (ncap > 0 ? ncap : 1) * 2 * RW * sizeof(uint32_t)));
+        M = (uint32_t*)c->b_pairs.p;
+        const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
+        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * kDenseLen * 2, c->stream>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles,
+                                                                                                     P.hist_tol, P.hist_lo, M);
         TRY(check_launch(c, "k5_pairs"));
         mark(c, "k5_pairs");
     }
-    if (max_n <= 256)
-        k5_fold2_kernel<256><<<nframes, kFold2Threads, sizeof(Fold2Smem<256>), c->stream>>>(P, nframes, M, R, cut);
-    else
-        k5_fold2_kernel<2048><<<nframes, kFold2Threads, sizeof(Fold2Smem<2048>), c->stream>>>(P, nframes, M, R, cut);
-    return check_launch(c, "k5_fold2");
+    if (max_n <= 256) return npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut);
+    return npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -484,14 +498,14 @@ int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W
     if (row_stride < (int64_t)W * channels || frame_stride < row_stride * (H - 1) + (int64_t)W * channels) return fail(TSD_E_INVALID, "bad strides");
     if (n && (!coords || !win_frame || !windows)) return fail(TSD_E_INVALID, "NULL argument");
     CU(cudaSetDevice(c->device));
-    if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows);
+    if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows, D * D * channels);
     Stage s(c);
     void *df, *dc, *dwf, *dw;
     TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * channels, &df));
     TRY(s.in(coords, (size_t)n * 16, &dc));
     TRY(s.in(win_frame, (size_t)n * 4, &dwf));
     TRY(s.alloc(&dw, (size_t)n * D * D * channels));
-    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, channels, (int32_t*)dc, (int32_t*)dwf, nullptr, n, D, (uint8_t*)dw));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, channels, (int32_t*)dc, (int32_t*)dwf, nullptr, n, D, (uint8_t*)dw, D * D * channels));
     TRY(s.out(windows, dw, (size_t)n * D * D * channels));
     CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
@@ -515,7 +529,7 @@ int tsd_windows(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, in
     TRY(s.alloc(&dwf, (size_t)nb * 4));
     TRY(s.alloc(&dw, (size_t)nb * D * D * 3));
     TRY(dev_windows_index(c, (int32_t*)db, (int32_t*)dbo, nframes, H, W, enlarge, (int32_t*)dcnt, (int32_t*)dwo, (int32_t*)dc, (int32_t*)dwf));
-    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, 3, (int32_t*)dc, (int32_t*)dwf, (int32_t*)dwo + nframes, nb, D, (uint8_t*)dw));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, 3, (int32_t*)dc, (int32_t*)dwf, (int32_t*)dwo + nframes, nb, D, (uint8_t*)dw, D * D * 3));
     TRY(s.out(win_offsets, dwo, (size_t)(nframes + 1) * 4));
     CU(cudaStreamSynchronize(c->stream));
     const int tot = win_offsets[nframes];
@@ -534,14 +548,18 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     if (!c || !offsets || !out_offsets || nframes < 0 || D < 2 || D > kMaxD) return fail(TSD_E_INVALID, "bad argument");
     if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_dedup takes host pointers; use tsd_enqueue_frames for device-resident batches");
     CU(cudaSetDevice(c->device));
-    const int n = offsets[nframes], npx = D * D, nbytes = npx * 3;
+    const int n = offsets[nframes], npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     if (n && (!windows || !coords)) return fail(TSD_E_INVALID, "NULL argument");
     Stage s(c);
     void *dw, *dc, *doff, *dent, *dmeta, *dlist, *dflags, *dcnt, *dooff, *dow, *doc, *den;
-    TRY(s.in(windows, (size_t)n * nbytes, &dw));
+    TRY(s.alloc(&dw, (size_t)n * ws));                       // internal layout: 16-byte aligned windows, zero pad
+    if (n) {
+        CU(cudaMemsetAsync(dw, 0, (size_t)n * ws, c->stream));
+        CU(cudaMemcpy2DAsync(dw, ws, windows, nbytes, nbytes, n, cudaMemcpyHostToDevice, c->stream));
+    }
     TRY(s.in(coords, (size_t)n * 16, &dc));
     TRY(s.in(offsets, (size_t)(nframes + 1) * 4, &doff));
-    TRY(s.alloc(&dent, (size_t)n * npx * 4));
+    TRY(s.alloc(&dent, (size_t)n * es * 4));
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
     TRY(s.alloc(&dlist, (size_t)n * 4));
     TRY(s.alloc(&dflags, (size_t)n));
@@ -552,19 +570,19 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     TRY(s.alloc(&doc, (size_t)n * 16));
     if (n) {
         if (by_coords) {
-            k5_hash_kernel<<<n, 128, 0, c->stream>>>((uint8_t*)dw, n, npx, (WinMeta*)dmeta);
+            k5_hash_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dw, n, npx, ws, (WinMeta*)dmeta);
             TRY(check_launch(c, "k5_hash"));
         } else {
-            TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta, (float*)den, n));
+            TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, ws, (uint32_t*)dent, (WinMeta*)dmeta, (float*)den, n));
         }
     }
     int max_n = 0;
     for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
-    TRY(dev_fold(c, (uint8_t*)dw, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (float*)den, n));
+    TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (size_t)n, (float*)den, n));
     TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
     if (nframes) {
-        k5_gather_kernel<<<nframes, 128, 0, c->stream>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes,
+        k5_gather_kernel<<<nframes, 128, 0, c->stream>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
                                                          (uint8_t*)dow, (int4*)doc, nullptr);
         TRY(check_launch(c, "k5_gather"));
     }
@@ -589,10 +607,10 @@ int tsd_hist(tsd_ctx* c, const uint8_t* windows, int n, int D, float* hist, int 
     Stage s(c);
     void *dw = (void*)windows, *dh = (void*)hist, *dent, *dmeta;
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dh, (size_t)n * kHistBins * 4)); }
-    TRY(s.alloc(&dent, (size_t)n * npx * 4));
+    TRY(s.alloc(&dent, (size_t)n * ent_stride(npx) * 4));
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
-    TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, (uint32_t*)dent, (WinMeta*)dmeta, nullptr, 0));
-    hist_dense_kernel<<<n, 256, 0, c->stream>>>((uint32_t*)dent, (WinMeta*)dmeta, n, npx, (float*)dh);
+    TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, npx * 3, (uint32_t*)dent, (WinMeta*)dmeta, nullptr, 0));      // public layout: packed windows
+    hist_dense_kernel<<<n, 256, 0, c->stream>>>((uint32_t*)dent, (WinMeta*)dmeta, n, ent_stride(npx), (float*)dh);
     TRY(check_launch(c, "hist_dense"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(hist, dh, (size_t)n * kHistBins * 4)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -608,7 +626,7 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx)); }
     int grid = cdiv((int64_t)n * npx, 256);
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
-    k3_masks_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db);
+    k3_masks_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db);
     TRY(check_launch(c, "k3_masks"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -664,7 +682,7 @@ int tsd_bgr2gray(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* gray, int
     if (mem == TSD_MEM_HOST) { TRY(s.in(bgr, (size_t)npx * 3, &di)); TRY(s.alloc(&dout, (size_t)npx)); }
     int grid = cdiv(npx, 256);
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
-    k6_gray_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, nullptr, nullptr, 1, (int)npx, (uint8_t*)dout);
+    k6_gray_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, nullptr, nullptr, 1, (int)npx, 0, (uint8_t*)dout);
     TRY(check_launch(c, "k6_gray"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(gray, dout, (size_t)npx)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -740,7 +758,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     if (!c || !d_frames || !d_box_offsets || nframes < 1 || nb < 0 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
     if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
     if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
-    const int D = c->cfg.window, npx = D * D, nbytes = npx * 3;
+    const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     if (mode == TSD_RUN_DETECT && (!c->have_templates || c->tmpl_D != D)) return fail(TSD_E_STATE, "templates not set for D=%d", D);
     if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
     CU(cudaSetDevice(c->device));
@@ -759,8 +777,8 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_detoff, (size_t)(nframes + 1) * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));
-    TRY(ensure(c, c->b_windows, cap * nbytes));
-    TRY(ensure(c, c->b_entries, cap * npx * 4));
+    TRY(ensure(c, c->b_windows, cap * ws));
+    TRY(ensure(c, c->b_entries, cap * es * 4));
     TRY(ensure(c, c->b_meta, cap * sizeof(WinMeta)));
     TRY(ensure(c, c->b_energy, cap * kHistGroups * 4));
     TRY(ensure(c, c->b_list, cap * 4));
@@ -787,15 +805,15 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     mark(c, "k1_expand_filter");
     const int32_t* d_nwin = winoff + nframes;
     // K2 (DET:123-124)
-    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, (int32_t*)c->b_winframe.p, d_nwin, nb, D, windows));
+    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, (int32_t*)c->b_winframe.p, d_nwin, nb, D, windows, ws));
     mark(c, "k2_crop_resize");
     // K5 (DET:127-129)
-    TRY(dev_hist(c, windows, d_nwin, nb, npx, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, (float*)c->b_energy.p, (int64_t)cap));
+    TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, (float*)c->b_energy.p, (int64_t)cap));
     mark(c, "k5_hist");
-    TRY(dev_fold(c, windows, coords, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, winoff, nframes, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt, max_boxes_per_frame, (float*)c->b_energy.p, (int64_t)cap));
+    TRY(dev_fold(c, windows, ws, coords, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, winoff, nframes, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
+                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt, max_boxes_per_frame, cap, (float*)c->b_energy.p, (int64_t)cap));
     TRY(dev_scan(c, survcnt, nframes, survoff));
-    k5_gather_kernel<<<nframes, 32, 0, c->stream>>>(windows, (int4*)coords, winoff, (int32_t*)c->b_list.p, survoff, nframes, nbytes, nullptr, nullptr, (int32_t*)c->b_slots.p);
+    k5_gather_kernel<<<nframes, 32, 0, c->stream>>>(windows, (int4*)coords, winoff, (int32_t*)c->b_list.p, survoff, nframes, nbytes, ws, nullptr, nullptr, (int32_t*)c->b_slots.p);
     TRY(check_launch(c, "k5_gather"));
     mark(c, "k5_fold");
     const int32_t* d_nsurv = survoff + nframes;
@@ -803,7 +821,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         // K3 + K4 (DET:708-716)
         int grid = cdiv((int64_t)cap * npx, 256);
         if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k3_masks_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p);
+        k3_masks_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p);
         TRY(check_launch(c, "k3_masks"));
         mark(c, "k3_masks");
         k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p, d_nsurv, nb, npx, c->d_tmpl,
@@ -813,7 +831,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     } else {
         int grid = cdiv((int64_t)cap * npx, 256);
         if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k6_gray_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, (uint8_t*)c->b_gray.p);
+        k6_gray_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, (uint8_t*)c->b_gray.p);
         TRY(check_launch(c, "k6_gray"));
         mark(c, "k6_gray");
         k7_hog_kernel<<<cdiv(cap, kHogWarps), kHogWarps * 32, 0, c->stream>>>((uint8_t*)c->b_gray.p, d_nsurv, nb, c->hog, (float*)c->b_hog.p);

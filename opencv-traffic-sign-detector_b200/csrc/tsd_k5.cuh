@@ -1,0 +1,571 @@
+// tsd_k5.cuh -- K5: cleanDuplicatedDetections (DET:177-223) as three kernels.
+//
+//  k5_hist_kernel  : one WARP per window -> sparse min-max-normalised H-S histogram (calculateHistAndNormalize,
+//                    DET:575-586): entries (bin << 16 | count) sorted by bin, f64 moments, pixel hash, and the energies
+//                    of 25 bin groups (Cauchy-Schwarz bound used by k5_pairs).
+//  k5_pairs_kernel : ALL pairs (i < j) of a frame's windows -> two BIT rows per item j over the earlier items i:
+//                    del[j] (CORREL > tol: the newer window replaces the older one) and mrg[j] (tol*0.8823 <= CORREL <= tol).
+//                    cv2.compareHist(CORREL) (DET:200-202) is decided from the EXACT integer dot product of the bin
+//                    counts, which bounds the f64 value to ~1e-7; only pairs within 1e-6 of a threshold take the exact f64
+//                    path, so every class equals the one the exact evaluation gives.
+//  k5_fold_warp    : the sequential fold itself, one WARP per frame.  The survivor list is a bit set in list (= index)
+//                    order, one 32-bit word per lane (<= 1024 windows per frame); an item without merge costs a handful of
+//                    instructions (AND the item's rows with the alive set).  A merge (rare) averages the pixels, rebuilds
+//                    the item's histogram, re-classifies it against the survivors after the merge position and -- once the
+//                    item is final -- against every later item (their bit rows described the un-merged histogram).
+//                    Pass 2 (corner similarity, DET:209-213) runs in the same warp from coordinates in shared memory.
+#pragma once
+#include "tsd_kernels.cuh"
+
+namespace tsd {
+
+constexpr int kHistGroups = 25;                      // group = bin / 120 (two H rows)
+constexpr int kClsUnsure = 3;
+
+__device__ __forceinline__ int classify(double sim, double tol, double lo) {
+    return sim > tol ? 1 : ((lo <= sim && sim <= tol) ? 2 : 0);
+}
+
+// cv2.compareHist(h1, h2, HISTCMP_CORREL) from the sparse dot product and the cached moments (symmetric in h1, h2)
+__device__ __forceinline__ double correl_from(double s12, double s1x, double Ax, double s1y, double Ay) {
+    const double scale = 1.0 / (double)kHistBins;
+    double num = s12 - s1x * s1y * scale;
+    double den2 = Ax * Ay;                                   // (s11 - s1*s1*scale) * (s22 - s2*s2*scale)
+    return fabs(den2) > DBL_EPSILON ? num / sqrt(den2) : 1.0;
+}
+
+// Class from the EXACT integer dot product I = sum_b cnt_x[b]*cnt_y[b].  The f64 value the reference computes is
+// s12 = sum fl32(cnt_x a_x) * fl32(cnt_y a_y) = a_x a_y I (1 + e), |e| <= 2^-23 + O(1e-16); the class is decided here
+// when the approximation is further than 2e-6 (relative to sqrt(denom2)) from both thresholds, else kClsUnsure.
+__device__ __forceinline__ int classify_from_int(int I, const WinMeta& x, const WinMeta& y, double tol, double lo) {
+    const double scale = 1.0 / (double)kHistBins;
+    const double den2 = x.A * y.A;
+    if (!(fabs(den2) > DBL_EPSILON)) return classify(1.0, tol, lo);
+    if (!(den2 > 0.0) || !(x.A > 0.0) || !(y.A > 0.0)) return kClsUnsure;
+    const double num = (double)x.a * (double)y.a * (double)I - x.s1 * y.s1 * scale;
+    const double r = x.rA * y.rA;                            // sqrt(denom2) to ~1e-16
+    const double m = 2e-6 * r + 1e-300;
+    const double hi_t = tol * r, lo_t = lo * r;
+    if (num > hi_t + m) return 1;
+    if (num < lo_t - m) return 0;
+    if (num > lo_t + m && num < hi_t - m) return 2;
+    return kClsUnsure;
+}
+
+// Cauchy-Schwarz bound from the group energies: can the pair (x, y) reach the merge band at all?
+// ub >= s12 (energies are inflated by 1e-5), so (ub - s1x s1y / N) / sqrt(Ax Ay) >= CORREL; below lo -> class 0.
+__device__ __forceinline__ bool prunable(float ub, const WinMeta& x, double s1y, double Ay, double rAy, double lo) {
+    const double den2 = x.A * Ay;
+    if (!(den2 > DBL_EPSILON) || !(x.A > 0.0) || !(Ay > 0.0)) return false;
+    const double num_ub = (double)ub * 1.00001 - x.s1 * s1y * (1.0 / (double)kHistBins);
+    return num_ub < lo * (x.rA * rAy) * 0.99999 - 1e-300;
+}
+
+__device__ __forceinline__ WinMeta load_meta_cg(const WinMeta* p) {      // 3 x 128-bit loads (metas are rewritten inside the fold: no __ldg)
+    WinMeta m;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&m);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    return m;
+}
+
+// =====================================================================================================================
+// Histogram of one window by one warp.  Scratch (per warp, shared memory):
+//   bitmap[96]  occupancy of the 3000 bins; prefix[96] exclusive popcounts -> rank(bin) = perfect hash into cnt[]
+//   binbuf[p]   bin of pixel p;  cnt[r] count of the r-th occupied bin;  binof[r] that bin.
+// CAP = capacity in pixels (640 for D=25, 1024 for D=32).
+// =====================================================================================================================
+template <int CAP>
+struct HistScratch {
+    uint32_t bitmap[96];
+    uint32_t cnt[CAP];
+    uint16_t prefix[96];
+    uint16_t binbuf[CAP];
+    uint16_t binof[CAP];
+};
+
+struct HsvLut {                 // per CTA
+    int32_t sdiv[256], hdiv[256];
+    uint8_t hbin[256];
+};
+
+__device__ __forceinline__ void load_hsv_lut(HsvLut& t, const Tables* __restrict__ tab) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { t.sdiv[i] = tab->sdiv[i]; t.hdiv[i] = tab->hdiv[i]; t.hbin[i] = tab->hbin[i]; }
+}
+
+// px: window pixels (global; may have been rewritten by this warp -> plain loads), e: entries out (global, es words,
+// zero-padded to a multiple of 4), meta out, Eg: optional group energies (E_T + w, stride e_stride).
+// Returns nnz.  All 32 lanes must call.  On return sw.cnt / sw.binof hold the entries (used to fill a dense copy).
+template <int CAP>
+__device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const HsvLut& lut, HistScratch<CAP>& sw,
+                                               uint32_t* __restrict__ e, WinMeta* meta, float* Eg, int64_t e_stride) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
+    __syncwarp();
+    // pass A: bin of every pixel + occupancy bitmap + pixel hash
+    uint32_t hsh = 0;
+#pragma unroll 4
+    for (int p = lane; p < npx; p += 32) {
+        const int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
+        int H, S, V;
+        bgr2hsv(b, g, r, lut.sdiv, lut.hdiv, H, S, V);
+        const int bin = (int)lut.hbin[H] * kHistS + ((S * kHistS) >> 8);   // floor(S*60/256.0) exactly (60/256 is a dyadic rational)
+        sw.binbuf[p] = (uint16_t)bin;
+        atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
+        hsh += pix_hash32(p, (uint32_t)(b | (g << 8) | (r << 16)));
+    }
+    __syncwarp();
+    // per-word exclusive prefix popcounts (lane owns words 3*lane .. 3*lane+2)
+    const uint32_t w0 = sw.bitmap[3 * lane], w1 = sw.bitmap[3 * lane + 1], w2 = sw.bitmap[3 * lane + 2];
+    const int c0 = __popc(w0), c1 = __popc(w1), c2 = __popc(w2);
+    int incl = c0 + c1 + c2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int excl = incl - (c0 + c1 + c2);
+    const int nnz = __shfl_sync(0xffffffffu, incl, 31);
+    sw.prefix[3 * lane] = (uint16_t)excl; sw.prefix[3 * lane + 1] = (uint16_t)(excl + c0); sw.prefix[3 * lane + 2] = (uint16_t)(excl + c0 + c1);
+    const int nnz4 = (nnz + 3) & ~3;
+    for (int i = lane; i < nnz4; i += 32) sw.cnt[i] = 0;
+    __syncwarp();
+    // pass B: counts through the rank hash; binof[rank] = bin (all writers of a rank store the same value)
+#pragma unroll 4
+    for (int p = lane; p < npx; p += 32) {
+        const int bin = sw.binbuf[p];
+        const uint32_t word = sw.bitmap[bin >> 5];
+        const int r = (int)sw.prefix[bin >> 5] + __popc(word & ((1u << (bin & 31)) - 1));
+        atomicAdd(&sw.cnt[r], 1u);
+        sw.binof[r] = (uint16_t)bin;
+    }
+    __syncwarp();
+    unsigned mx = 0;
+    for (int i = lane; i < nnz; i += 32) mx = max(mx, sw.cnt[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // normalize: scale = 1/(max-min) in f64 (min == 0: npx < 3000 bins), a = (float)scale (cv2.normalize NORM_MINMAX -> convertTo)
+    const double scale = ((double)mx - 0.0) > DBL_EPSILON ? 1.0 / ((double)mx - 0.0) : 0.0;
+    const float a = (float)scale;
+    // entries in rank (= bin) order, lane-strided; moments per lane in that order, then a fixed shuffle tree (deterministic)
+    double s1 = 0, s11 = 0;
+    for (int r = lane; r < nnz4; r += 32) {
+        uint32_t v = 0;
+        if (r < nnz) {
+            const uint32_t c = sw.cnt[r];
+            v = ((uint32_t)sw.binof[r] << 16) | c;
+            const double h = (double)((float)c * a);
+            s1 += h; s11 += h * h;
+        }
+        e[r] = v;
+    }
+    s1 = warp_sum(s1); s11 = warp_sum(s11);
+    hsh = warp_sum_u(hsh);
+    if (Eg) {
+        // group g = bins [120 g, 120 g + 120): contiguous rank range; lane g sums its range (deterministic, no atomics)
+        float eg = 0.f;
+        if (lane < kHistGroups) {
+            const int bs = 120 * lane, be = 120 * lane + 120;
+            const int rs = (int)sw.prefix[bs >> 5] + __popc(sw.bitmap[bs >> 5] & ((1u << (bs & 31)) - 1));
+            const int re = lane == kHistGroups - 1 ? nnz : (int)sw.prefix[be >> 5] + __popc(sw.bitmap[be >> 5] & ((1u << (be & 31)) - 1));
+            for (int r = rs; r < re; r++) { const float hf = (float)sw.cnt[r] * a; eg += hf * hf; }
+            Eg[(int64_t)lane * e_stride] = sqrtf(eg) * 1.00001f;       // inflated: only ever used as an upper bound
+        }
+    }
+    if (lane == 0) {
+        const double A = s11 - s1 * s1 * (1.0 / (double)kHistBins);
+        WinMeta m;
+        m.s1 = s1; m.s11 = s11; m.A = A; m.rA = sqrt(A); m.a = a; m.nnz = nnz; m.hash = hsh; m.pad_ = 0;
+        *meta = m;
+    }
+    __syncwarp();
+    return nnz;
+}
+
+constexpr int kHistWarps = 4;
+
+template <int CAP>
+__global__ void __launch_bounds__(kHistWarps * 32) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
+                                                                  int n_max, int npx, int ws, int es, const Tables* __restrict__ tab,
+                                                                  uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
+                                                                  float* __restrict__ E_T, int64_t e_stride) {
+    __shared__ HsvLut lut;
+    __shared__ HistScratch<CAP> s_w[kHistWarps];
+    load_hsv_lut(lut, tab);
+    __syncthreads();
+    const int wid = threadIdx.x >> 5;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int nwarps = gridDim.x * kHistWarps;
+    for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps)
+        hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
+                             E_T ? E_T + w : nullptr, e_stride);
+}
+
+// =====================================================================================================================
+// k5_pairs: one warp per item j (its dense histogram, u16, in shared memory); 32 earlier items per step, one per lane,
+// pruned by the energy bound; surviving pairs are evaluated warp-wide (coalesced entry loads), two pairs in flight.
+// Output: M[(base + j)][0..RW) = delete bits over il, M[(base + j)][RW..2RW) = merge bits.
+// =====================================================================================================================
+constexpr int kPairWarps = 8;
+constexpr int kDenseLen = kHistBins + 8;
+
+__device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_d, const uint32_t* eo, int nnz_o, float a_o) {
+    const int lane = threadIdx.x & 31;
+    double s12 = 0;
+    for (int e = lane; e < nnz_o; e += 32) {
+        const uint32_t v = __ldcg(eo + e);
+        const float hd = (float)dense[v >> 16] * a_d;
+        const float ho = (float)(v & 0xffffu) * a_o;
+        s12 += (double)hd * (double)ho;
+    }
+    return warp_sum(s12);
+}
+
+__global__ void __launch_bounds__(kPairWarps * 32) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+                                                                   const float* __restrict__ E_T, int64_t e_stride,
+                                                                   const int32_t* __restrict__ offsets, int nframes, int es, int RW,
+                                                                   int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x / tiles_per_frame, tile = blockIdx.x - f * tiles_per_frame;
+    if (f >= nframes) return;
+    const int base = offsets[f], n = offsets[f + 1] - base;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jl = tile * kPairWarps + wid;
+    if (jl >= n || jl == 0 || n > RW * 32) return;          // warps are independent: no block barrier below
+    uint16_t* dense = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)wid * kDenseLen;
+    for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(dense)[b] = 0;
+    __syncwarp();
+    const WinMeta mj = meta[base + jl];
+    {
+        const uint32_t* ej = entries + (int64_t)(base + jl) * es;
+        for (int e = lane; e < mj.nnz; e += 32) { const uint32_t v = __ldg(ej + e); dense[v >> 16] = (uint16_t)(v & 0xffffu); }
+    }
+    const float Ej = lane < kHistGroups ? __ldg(E_T + (int64_t)lane * e_stride + base + jl) : 0.f;
+    __syncwarp();
+    uint32_t* Mrow = M + (int64_t)(base + jl) * 2 * RW;
+    for (int i0 = 0; i0 < jl; i0 += 32) {
+        const int il = i0 + lane;
+        const bool valid = il < jl;
+        const int wi = base + (valid ? il : 0);
+        // lane-parallel bound for 32 earlier windows at once
+        float ub = 0.f;
+#pragma unroll
+        for (int g = 0; g < kHistGroups; g++) ub += __shfl_sync(0xffffffffu, Ej, g) * __ldg(E_T + (int64_t)g * e_stride + wi);
+        const WinMeta mi = meta[wi];
+        int c = 0;
+        bool need = false;
+        if (valid) {
+            const double den2 = mj.A * mi.A;
+            if (!(fabs(den2) > DBL_EPSILON)) c = classify(1.0, tol, lo);          // compareHist's degenerate branch
+            else need = !prunable(ub, mj, mi.s1, mi.A, mi.rA, lo);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        int Ik = 0;
+        while (todo) {
+            // up to 4 pairs per round; every lane loads 4 consecutive entries (128-bit) of each, so one round has all the
+            // entry loads of 4 pairs (<= 128 entries per load instruction) in flight together
+            int kk[4], nn[4];
+            const uint4* ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                kk[u] = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - 1;                           // (0 & anything stays 0)
+                nn[u] = kk[u] >= 0 ? (__shfl_sync(0xffffffffu, mi.nnz, kk[u] & 31) + 3) >> 2 : 0;      // uint4 count (zero padded)
+                ee[u] = reinterpret_cast<const uint4*>(entries + (int64_t)(base + i0 + (kk[u] & 31)) * es);
+            }
+            int acc[4] = {0, 0, 0, 0};
+            const int nmax = max(max(nn[0], nn[1]), max(nn[2], nn[3]));
+            for (int e = lane; e < nmax; e += 32) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = e < nn[u] ? __ldg(ee[u] + e) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    acc[u] += (int)dense[v[u].x >> 16] * (int)(v[u].x & 0xffffu) + (int)dense[v[u].y >> 16] * (int)(v[u].y & 0xffffu) +
+                              (int)dense[v[u].z >> 16] * (int)(v[u].z & 0xffffu) + (int)dense[v[u].w >> 16] * (int)(v[u].w & 0xffffu);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (lane == kk[u]) Ik = acc[u];
+        }
+        if (need) c = classify_from_int(Ik, mj, mi, tol, lo);
+        unsigned unsure = __ballot_sync(0xffffffffu, need && c == kClsUnsure);
+        while (unsure) {                                    // rare: within 2e-6 of a threshold -> exact f64 evaluation
+            const int k = __ffs(unsure) - 1;
+            unsure &= unsure - 1;
+            const int nnz_k = __shfl_sync(0xffffffffu, mi.nnz, k);
+            const float a_k = __shfl_sync(0xffffffffu, mi.a, k);
+            const double s12 = exact_s12_warp(dense, mj.a, entries + (int64_t)(base + i0 + k) * es, nnz_k, a_k);
+            if (lane == k) c = classify(correl_from(s12, mj.s1, mj.A, mi.s1, mi.A), tol, lo);
+        }
+        const unsigned bd = __ballot_sync(0xffffffffu, valid && c == 1), bm = __ballot_sync(0xffffffffu, valid && c == 2);
+        if (lane == 0) { Mrow[i0 >> 5] = bd; Mrow[RW + (i0 >> 5)] = bm; }
+    }
+}
+
+// =====================================================================================================================
+// The fold: one warp per frame.
+// =====================================================================================================================
+constexpr int kFoldWarps = 4;                          // default warps (= frames in flight) per CTA; the kernel reads blockDim
+
+template <int RMAX, int CAP>
+struct FoldWarpSmem {
+    int4 coords[RMAX];           // current coords of every item (merged coords are written here and to global)
+    uint32_t hash[RMAX];         // current pixel hash of every item
+    uint16_t dense[kDenseLen];   // dense counts of the item being merged
+    HistScratch<CAP> hs;
+};
+
+// per-lane class of (dense item d) vs (sparse item o): integer dot, exact f64 fallback
+__device__ __forceinline__ int pair_class_lane(const uint16_t* dense, const WinMeta& md, const uint32_t* eo, const WinMeta& mo,
+                                               double tol, double lo) {
+    int acc = 0;
+    const int n4 = (mo.nnz + 3) >> 2;                       // entries are zero-padded to a multiple of 4
+    const uint4* e4 = reinterpret_cast<const uint4*>(eo);
+#pragma unroll 8
+    for (int i = 0; i < n4; i++) {
+        const uint4 v = e4[i];                              // plain (L1-coherent within the SM): only this warp touches the frame's data
+        acc += (int)dense[v.x >> 16] * (int)(v.x & 0xffffu) + (int)dense[v.y >> 16] * (int)(v.y & 0xffffu) +
+               (int)dense[v.z >> 16] * (int)(v.z & 0xffffu) + (int)dense[v.w >> 16] * (int)(v.w & 0xffffu);
+    }
+    int c = classify_from_int(acc, md, mo, tol, lo);
+    if (c == kClsUnsure) {
+        double s12 = 0;
+        for (int i = 0; i < mo.nnz; i++) {
+            const uint32_t v = eo[i];
+            s12 += (double)((float)dense[v >> 16] * md.a) * (double)((float)(v & 0xffffu) * mo.a);
+        }
+        c = classify(correl_from(s12, md.s1, md.A, mo.s1, mo.A), tol, lo);
+    }
+    return c;
+}
+
+// cv2.addWeighted(a, .5, b, .5, 0) on 4 packed bytes: round-half-even of (a+b)/2 (DET:219)
+__device__ __forceinline__ uint32_t avg_rne4(uint32_t a, uint32_t b) {
+    const uint32_t fl = (a & b) + (((a ^ b) >> 1) & 0x7f7f7f7fu);    // floor((a+b)/2) per byte
+    return fl + ((a ^ b) & fl & 0x01010101u);                         // halves round to even
+}
+
+// item[slot_i] = avg(item[slot_i], item[slot_k]) in place, whole padded window (pad bytes stay 0); returns the new pixel hash
+__device__ __forceinline__ uint32_t merge_pixels_warp(uint8_t* ipx, const uint8_t* kpx, int ws, int npx) {
+    const int lane = threadIdx.x & 31;
+    uint4* a4 = reinterpret_cast<uint4*>(ipx);
+    const uint4* b4 = reinterpret_cast<const uint4*>(kpx);
+    for (int i = lane; i < (ws >> 4); i += 32) {
+        uint4 a = __ldcg(a4 + i);
+        const uint4 b = __ldcg(b4 + i);
+        a.x = avg_rne4(a.x, b.x); a.y = avg_rne4(a.y, b.y); a.z = avg_rne4(a.z, b.z); a.w = avg_rne4(a.w, b.w);
+        a4[i] = a;
+    }
+    __syncwarp();
+    uint32_t hsh = 0;
+    for (int p = lane; p < npx; p += 32) hsh += pix_hash32(p, (uint32_t)(ipx[3 * p] | (ipx[3 * p + 1] << 8) | (ipx[3 * p + 2] << 16)));
+    return warp_sum_u(hsh);
+}
+
+__device__ __forceinline__ bool pixels_equal_warp(const uint8_t* a, const uint8_t* b, int ws) {
+    const int lane = threadIdx.x & 31;
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    bool eq = true;
+    for (int i = lane; i < (ws >> 4); i += 32) {
+        const uint4 x = __ldcg(a4 + i), y = __ldcg(b4 + i);
+        eq &= x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w;
+    }
+    return __all_sync(0xffffffffu, eq);
+}
+
+// pop-by-pixel-equality (DET:183-185,471-477) on the alive bit set A (lane w = items 32w..32w+31, list order = index order):
+// for every marked position p, in increasing order, remove the FIRST alive entry whose pixels equal p's.  Returns new A.
+template <int RMAX, int CAP>
+__device__ __forceinline__ unsigned fold_apply_deletions(unsigned A, unsigned D, const FoldWarpSmem<RMAX, CAP>& sm, const uint8_t* windows,
+                                                         int base, int ws) {
+    const int lane = threadIdx.x & 31;
+    unsigned lanes = __ballot_sync(0xffffffffu, D != 0);
+    while (lanes) {
+        const int L = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        unsigned w = __shfl_sync(0xffffffffu, D, L);
+        while (w) {
+            const int bit = __ffs(w) - 1;
+            w &= w - 1;
+            const int p = 32 * L + bit;
+            const uint32_t hp = sm.hash[p];
+            int victim = p;
+            for (int t = 0; t <= L && victim == p; t++) {
+                unsigned aw = __shfl_sync(0xffffffffu, A, t);
+                if (t == L) aw &= (1u << bit) - 1;
+                const int q = 32 * t + lane;
+                unsigned cm = __ballot_sync(0xffffffffu, ((aw >> lane) & 1u) && sm.hash[q] == hp);
+                while (cm) {                                // candidates in list order; hash collisions are verified away
+                    const int qq = 32 * t + __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    if (pixels_equal_warp(windows + (int64_t)(base + qq) * ws, windows + (int64_t)(base + p) * ws, ws)) { victim = qq; break; }
+                }
+            }
+            if (lane == (victim >> 5)) A &= ~(1u << (victim & 31));
+        }
+    }
+    return A;
+}
+
+template <int RMAX, int CAP>
+__global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut) {
+    const int nwarp = blockDim.x >> 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HsvLut& lut = *reinterpret_cast<HsvLut*>(smem_raw);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FoldWarpSmem<RMAX, CAP>& sm = reinterpret_cast<FoldWarpSmem<RMAX, CAP>*>(smem_raw + ((sizeof(HsvLut) + 15) & ~15))[wid];
+    load_hsv_lut(lut, P.tab);
+    for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.dense)[b] = 0;
+    __syncthreads();
+    const int ws = P.ws, es = P.es;
+    for (int f = blockIdx.x * nwarp + wid; f < nframes; f += gridDim.x * nwarp) {
+        const int base = P.offsets[f], n = P.offsets[f + 1] - base;
+        if (n > RMAX || n > RW * 32) { if (lane == 0) P.out_count[f] = -1; continue; }    // host picks RMAX / RW large enough
+        for (int p = lane; p < n; p += 32) { sm.coords[p] = P.coords[base + p]; sm.hash[p] = P.meta[base + p].hash; }
+        __syncwarp();
+        const int nwords = (n + 31) >> 5;
+        unsigned A = 0;                                      // survivors, list order = item order
+        if (P.do_hist) {
+            const uint32_t* Mf = M + (int64_t)base * 2 * RW;
+            unsigned nd = 0, nm = 0;
+            if (n > 1 && lane < RW) { nd = __ldcg(Mf + 2 * RW + lane); nm = __ldcg(Mf + 3 * RW + lane); }
+            if (n > 0 && lane == 0) A = 1u;
+            for (int j = 1; j < n; j++) {
+                unsigned vd = nd, vm = nm;
+                if (j + 1 < n && lane < RW) { nd = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + lane); nm = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + RW + lane); }
+                unsigned D = 0, scan = 0xffffffffu;
+                bool dirty = false;
+                int4 ic = make_int4(0, 0, 0, 0);
+                WinMeta mj;
+                mj.nnz = 0;
+                const int slot = base + j;
+                while (true) {
+                    const unsigned m = vm & A & scan, d = vd & A & scan;
+                    const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
+                    if (!bm) { D |= d; break; }
+                    // ---- merge with the first survivor (list order) in the merge band (DET:217-221) ----
+                    const int L = __ffs(bm) - 1;
+                    const int bit = __ffs(__shfl_sync(0xffffffffu, m, L)) - 1;
+                    const int fm = 32 * L + bit;
+                    if (lane < L) D |= d;
+                    else if (lane == L) D |= (d & ((1u << bit) - 1)) | (1u << bit);
+                    uint8_t* ipx = P.windows + (int64_t)slot * ws;
+                    uint32_t* ient = P.entries + (int64_t)slot * es;
+                    if (!dirty) ic = sm.coords[j];
+                    else {                                   // clear the previous dense copy of this item (hs still holds its bins)
+                        for (int r = lane; r < mj.nnz; r += 32) sm.dense[sm.hs.binof[r]] = 0;
+                        __syncwarp();
+                    }
+                    const uint32_t hsh = merge_pixels_warp(ipx, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                    const int4 kc = sm.coords[fm];
+                    ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);   // Python // (coords >= 0)
+                    __syncwarp();
+                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, lut, sm.hs, ient, P.meta + slot, nullptr, 0);
+                    for (int r = lane; r < nnz; r += 32) sm.dense[sm.hs.binof[r]] = (uint16_t)sm.hs.cnt[r];
+                    if (lane == 0) sm.hash[j] = hsh;
+                    __syncwarp();
+                    mj = load_meta_cg(P.meta + slot);
+                    // re-classify the updated item against the survivors after the merge position
+                    scan = lane < L ? 0u : (lane == L ? (bit == 31 ? 0u : ~((2u << bit) - 1)) : 0xffffffffu);
+                    const unsigned arem = A & scan;
+                    for (int t = L; t <= ((j - 1) >> 5); t++) {
+                        const unsigned aw = __shfl_sync(0xffffffffu, arem, t);
+                        if (!aw) continue;
+                        int c = 0;
+                        if ((aw >> lane) & 1u) {
+                            const int q = base + 32 * t + lane;
+                            const WinMeta mq = load_meta_cg(P.meta + q);
+                            c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)q * es, mq, P.hist_tol, P.hist_lo);
+                        }
+                        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
+                        if (lane == t) { vd = bd; vm = bmm; }
+                    }
+                    dirty = true;
+                }
+                if (dirty) {
+                    if (lane == 0) { sm.coords[j] = ic; P.coords[slot] = ic; }
+                    // the item is final: its class against every LATER item (their bit rows described the un-merged histogram)
+                    const unsigned bitj = 1u << (j & 31);
+                    for (int t = j >> 5; t < nwords; t++) {
+                        const int q2 = 32 * t + lane;
+                        if (q2 > j && q2 < n) {
+                            const WinMeta mq = load_meta_cg(P.meta + base + q2);
+                            const int c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)(base + q2) * es, mq, P.hist_tol, P.hist_lo);
+                            uint32_t* r = M + (int64_t)(base + q2) * 2 * RW + (j >> 5);
+                            const uint32_t od = __ldcg(r), om = __ldcg(r + RW);
+                            r[0] = (od & ~bitj) | (c == 1 ? bitj : 0u);
+                            r[RW] = (om & ~bitj) | (c == 2 ? bitj : 0u);
+                        }
+                    }
+                    __syncwarp();
+                    for (int r = lane; r < mj.nnz; r += 32) sm.dense[sm.hs.binof[r]] = 0;
+                    __syncwarp();
+                    if (j + 1 < n && lane < RW) { nd = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + lane); nm = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + RW + lane); }
+                }
+                if (__any_sync(0xffffffffu, D != 0)) A = fold_apply_deletions<RMAX, CAP>(A, D, sm, P.windows, base, ws);
+                if (lane == (j >> 5)) A |= 1u << (j & 31);
+            }
+        } else {
+            if (lane < nwords) A = (lane == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1) : 0xffffffffu;
+        }
+        if (P.do_coords) {
+            const unsigned A1 = A;
+            unsigned A2 = 0;
+            const double tol = P.coord_tol, lo = P.coord_lo;
+            for (int tj = 0; tj < nwords; tj++) {
+                unsigned wj = __shfl_sync(0xffffffffu, A1, tj);
+                while (wj) {
+                    const int j = 32 * tj + __ffs(wj) - 1;
+                    wj &= wj - 1;
+                    int4 ic = sm.coords[j];
+                    unsigned D = 0;
+                    bool dirty = false;
+                    int start = 0;                           // first list position still to scan
+                    int t = 0;
+                    while (t <= tj) {
+                        unsigned aw = __shfl_sync(0xffffffffu, A2, t);
+                        if (t == (start >> 5)) aw &= ~((1u << (start & 31)) - 1);
+                        if (!aw) { t++; continue; }
+                        int c = 0;
+                        if ((aw >> lane) & 1u) c = classify(coord_sim(ic, sm.coords[32 * t + lane], P.simtab, sim_cut), tol, lo);
+                        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
+                        if (!bmm) { if (lane == t) D |= bd; t++; continue; }
+                        // ---- merge (DET:217-221): pixels, coords; later comparisons use the updated item ----
+                        const int bit = __ffs(bmm) - 1, fm = 32 * t + bit;
+                        if (lane == t) D |= (bd & ((1u << bit) - 1)) | (1u << bit);
+                        const uint32_t hsh = merge_pixels_warp(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                        const int4 kc = sm.coords[fm];
+                        ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);
+                        if (lane == 0) sm.hash[j] = hsh;
+                        dirty = true;
+                        start = fm + 1;
+                        t = start >> 5;
+                        __syncwarp();
+                    }
+                    if (dirty) {
+                        if (lane == 0) { sm.coords[j] = ic; P.coords[base + j] = ic; P.meta[base + j].hash = sm.hash[j]; }
+                        __syncwarp();
+                    }
+                    if (__any_sync(0xffffffffu, D != 0)) A2 = fold_apply_deletions<RMAX, CAP>(A2, D, sm, P.windows, base, ws);
+                    if (lane == (j >> 5)) A2 |= 1u << (j & 31);
+                }
+            }
+            A = A2;
+        }
+        // survivors -> list (slots in list order) + count
+        const int cnt = __popc(A);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        int o = incl - cnt;
+        unsigned w = A;
+        while (w) { const int bit = __ffs(w) - 1; w &= w - 1; P.list[base + o++] = base + 32 * lane + bit; }
+        if (lane == 31) P.out_count[f] = incl;
+        __syncwarp();
+    }
+}
+
+}  // namespace tsd

@@ -15,6 +15,19 @@ constexpr int kHistH = 50, kHistS = 60, kHistBins = kHistH * kHistS;   // DET:57
 constexpr int kMaxD = 32;
 constexpr int kMaxPx = kMaxD * kMaxD;
 
+// Internal layouts are padded so that every window / sparse histogram starts on a 16-byte boundary (128-bit loads):
+// window stride = D*D*C bytes rounded up to 16 (1875 -> 1888; pad bytes are ZERO), entry stride = D*D words rounded up to 4.
+__host__ __device__ inline int win_stride(int npx, int C) { return (npx * C + 15) & ~15; }
+__host__ __device__ inline int ent_stride(int npx) { return (npx + 3) & ~3; }
+
+// order-independent pixel-content hash: sum over pixels of mix(position, bgr).  Equal windows -> equal hash; used only as a
+// pre-filter of the pop-by-pixel-equality rule (DET:471-477), candidates are always verified byte by byte.
+__device__ __forceinline__ uint32_t pix_hash32(int p, uint32_t bgr) {
+    uint32_t x = (bgr ^ ((uint32_t)p * 0x9E3779B1u)) * 0x85EBCA6Bu;
+    x ^= x >> 15;
+    return x * 0xC2B2AE35u;
+}
+
 // ---- small tables (global memory, L2-resident; staged to shared memory by the kernels that index them per lane)
 struct Tables {
     int32_t sdiv[256];      // rne((255<<12)/i)         OpenCV RGB2HSV_b
@@ -152,7 +165,7 @@ template <int C>
 __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    int D, uint8_t* __restrict__ windows) {
+    int D, uint8_t* __restrict__ windows, int out_stride) {
     __shared__ int16_t s_xo[4][kMaxD], s_xa0[4][kMaxD], s_xa1[4][kMaxD];
     __shared__ int16_t s_y0[4][kMaxD], s_y1[4][kMaxD], s_yb0[4][kMaxD], s_yb1[4][kMaxD];
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,9 +176,10 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
     const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
-    uint8_t* __restrict__ dst = windows + (int64_t)w * D * D * C;
+    uint8_t* __restrict__ dst = windows + (int64_t)w * out_stride;
     const int rowlen = D * C, total = D * rowlen;
-    if (cw <= 0 || ch <= 0) return;                         // filtered out by K1 (cv2.resize would raise)
+    if (cw <= 0 || ch <= 0) return;
+    for (int i = total + lane; i < out_stride; i += 32) dst[i] = 0;     // pad bytes of the internal layout are zero                         // filtered out by K1 (cv2.resize would raise)
     if (cw == D && ch == D) {                               // same size: copy
         for (int i = lane; i < total; i += 32) { int y = i / rowlen, r = i - y * rowlen; dst[i] = src[(int64_t)y * row_stride + r]; }
         return;
@@ -221,7 +235,7 @@ template <int C, int D>
 __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows) {
+    uint8_t* __restrict__ windows, int out_stride) {
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
@@ -231,7 +245,8 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
     if (cw <= 0 || ch <= 0) return;
     const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
-    uint8_t* __restrict__ dst = windows + (int64_t)w * D * D * C + lane * C;
+    uint8_t* __restrict__ dst = windows + (int64_t)w * out_stride + lane * C;
+    if (D * D * C + lane < out_stride) windows[(int64_t)w * out_stride + D * D * C + lane] = 0;    // zero pad (< 16 bytes)
     const bool act = lane < D;
     const int li = act ? lane : 0;
     if (cw == D && ch == D) {                               // same size: copy
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
 // `slots` (optional) = indirection to the surviving windows inside the work buffer.
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k3_masks_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
-                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx,
+                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws,
                                                        const Tables* __restrict__ tab, HsvBounds hb,
                                                        uint8_t* __restrict__ red, uint8_t* __restrict__ blue) {
     __shared__ int32_t s_sdiv[256], s_hdiv[256];
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(256) k3_masks_kernel(const uint8_t* __restrict
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = (int)(i / npx), p = (int)(i - (int64_t)w * npx);
         int slot = slots ? slots[w] : w;
-        const uint8_t* px = windows + ((int64_t)slot * npx + p) * 3;
+        const uint8_t* px = windows + (int64_t)slot * ws + p * 3;
         int H, S, V;
         bgr2hsv(px[0], px[1], px[2], s_sdiv, s_hdiv, H, S, V);
         bool r0 = H >= hb.red_lo[0][0] && H <= hb.red_hi[0][0] && S >= hb.red_lo[0][1] && S <= hb.red_hi[0][1] &&
@@ -408,17 +423,20 @@ __global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict
 //   because npx <= 1024 < 3000 bins, so the MINMAX shift is +0);  s1 = sum h, s11 = sum h^2 in f64;
 //   hash = 64-bit hash of the pixels (used only to pre-filter the pop-by-pixel-equality rule DET:471-477).
 // =====================================================================================================
-struct WinMeta {
+struct __align__(16) WinMeta {
     double s1, s11;              // sum h, sum h^2 over the 3000 bins (f64)
     double A, rA;                // A = s11 - s1*s1/N (one factor of compareHist's denom2), rA = sqrt(A)
-    unsigned long long hash;
     float a;                     // (float)(1/max count)
     int32_t nnz;
+    uint32_t hash;               // pix_hash32 sum
+    uint32_t pad_;
 };
+static_assert(sizeof(WinMeta) == 48, "WinMeta layout");
 
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-    return x;
+__device__ __forceinline__ uint32_t warp_sum_u(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 // Block-wide: histogram of one window.  dense[kHistBins] (shared, zero on entry, left holding the counts),
@@ -427,27 +445,20 @@ __device__ void build_hist_block(const uint8_t* __restrict__ px, int npx, const 
                                  const uint8_t* s_hbin, const uint8_t* s_sbin, uint32_t* dense, double* red,
                                  uint32_t* __restrict__ entries, WinMeta* __restrict__ meta) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    unsigned long long hsh = 0;
+    uint32_t hsh = 0;
     for (int p = tid; p < npx; p += nt) {
         int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
         int H, S, V;
         bgr2hsv(b, g, r, s_sdiv, s_hdiv, H, S, V);
         atomicAdd(&dense[(int)s_hbin[H] * kHistS + (int)s_sbin[S]], 1u);
-        hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(b | (g << 8) | (r << 16)));
+        hsh += pix_hash32(p, (uint32_t)(b | (g << 8) | (r << 16)));
     }
-    // hash: order-independent sum of per-pixel mixes
-    unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
-    // reduce hash with 64-bit adds through shuffles
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
-        hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
-    }
-    unsigned long long* red_u = reinterpret_cast<unsigned long long*>(red);
+    hsh = warp_sum_u(hsh);                                  // order-independent sum of per-pixel mixes
+    uint32_t* red_u = reinterpret_cast<uint32_t*>(red);
     __syncthreads();
     if (lane == 0) red_u[wid] = hsh;
     __syncthreads();
-    unsigned long long hash_all = 0;
+    uint32_t hash_all = 0;
     for (int i = 0; i < nw; i++) hash_all += red_u[i];
     __syncthreads();
     // max count + per-warp nnz over contiguous bin ranges (deterministic, sorted-by-bin output)
@@ -486,7 +497,7 @@ __device__ void build_hist_block(const uint8_t* __restrict__ px, int npx, const 
         double t1 = 0, t11 = 0;
         for (int i = 0; i < nw; i++) { t1 += red[i]; t11 += red[32 + i]; }
         const double A = t11 - t1 * t1 * (1.0 / (double)kHistBins);
-        meta->s1 = t1; meta->s11 = t11; meta->A = A; meta->rA = sqrt(A); meta->hash = hash_all; meta->a = a; meta->nnz = nnz;
+        meta->s1 = t1; meta->s11 = t11; meta->A = A; meta->rA = sqrt(A); meta->hash = hash_all; meta->a = a; meta->nnz = nnz; meta->pad_ = 0;
     }
     __syncthreads();
 }
@@ -510,170 +521,28 @@ __device__ __forceinline__ void load_tables_block(HistSmem& sm, const Tables* __
     for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sm.dense[i] = 0;
 }
 
-// K5a: sparse histogram + meta of every window (one CTA of 128 threads per window, grid-stride).
-__global__ void __launch_bounds__(128) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
-                                                      int n_max, int npx, const Tables* __restrict__ tab,
-                                                      uint32_t* __restrict__ entries, WinMeta* __restrict__ meta) {
-    __shared__ HistSmem sm;
-    load_tables_block(sm, tab);
-    __syncthreads();
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    for (int w = blockIdx.x; w < n; w += gridDim.x) {
-        uint32_t* e = entries + (int64_t)w * npx;
-        build_hist_block(windows + (int64_t)w * npx * 3, npx, sm.sdiv, sm.hdiv, sm.hbin, sm.sbin, sm.dense, sm.red, e, meta + w);
-        clear_dense_block(sm.dense, e, meta[w].nnz);
-        __syncthreads();
-    }
-}
-
-// K5a v2: one WARP per window, no block barriers.  Instead of a dense 3000-bin array the warp keeps a 3000-bit
-// occupancy bitmap (94 words) with per-word prefix popcounts: rank(bin) is a perfect hash into a compact count array, and
-// walking the set bits in order emits the (bin, count) entries sorted by bin.  Also emits, per window, the energies
-// E[g] = sqrt(sum_{bin in group g} h^2) of kHistGroups = 25 bin groups (two H rows each), transposed [g][window], which
-// give k5_pairs a Cauchy-Schwarz upper bound of the histogram dot product (sum_g E_x[g] E_y[g] >= sum_b x_b y_b).
-constexpr int kHistGroups = 25;                      // group = bin / 120
-constexpr int kHistWarps = 4;
-
-struct HistWarpSmem {
-    uint32_t bitmap[96];
-    uint32_t prefix[96];
-    uint32_t counts[kMaxPx];
-    uint16_t binbuf[kMaxPx];
-    float energy[32];
-};
-
-__global__ void __launch_bounds__(kHistWarps * 32) k5_hist_v2_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
-                                                                     int n_max, int npx, const Tables* __restrict__ tab,
-                                                                     uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
-                                                                     float* __restrict__ E_T, int64_t e_stride) {
-    __shared__ int32_t s_sdiv[256], s_hdiv[256];
-    __shared__ uint8_t s_hbin[256], s_sbin[256];
-    __shared__ HistWarpSmem s_w[kHistWarps];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        s_sdiv[i] = tab->sdiv[i]; s_hdiv[i] = tab->hdiv[i]; s_hbin[i] = tab->hbin[i]; s_sbin[i] = tab->sbin[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    HistWarpSmem& sw = s_w[wid];
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    const int nwarps = gridDim.x * kHistWarps;
-    for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps) {
-        const uint8_t* __restrict__ px = windows + (int64_t)w * npx * 3;
-        for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
-        if (lane < 32) sw.energy[lane] = 0.f;
-        __syncwarp();
-        // pass A: bins + occupancy bitmap + pixel hash
-        unsigned long long hsh = 0;
-        for (int p = lane; p < npx; p += 32) {
-            const int b = __ldg(px + 3 * p), g = __ldg(px + 3 * p + 1), r = __ldg(px + 3 * p + 2);
-            int H, S, V;
-            bgr2hsv(b, g, r, s_sdiv, s_hdiv, H, S, V);
-            const int bin = (int)s_hbin[H] * kHistS + (int)s_sbin[S];
-            sw.binbuf[p] = (uint16_t)bin;
-            atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
-            hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(b | (g << 8) | (r << 16)));
-        }
-        __syncwarp();
-        // per-word prefix popcounts (lane owns words 3*lane .. 3*lane+2)
-        const uint32_t w0 = sw.bitmap[3 * lane], w1 = sw.bitmap[3 * lane + 1], w2 = sw.bitmap[3 * lane + 2];
-        const int c0 = __popc(w0), c1 = __popc(w1), c2 = __popc(w2);
-        int incl = c0 + c1 + c2;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        const int excl = incl - (c0 + c1 + c2);
-        const int nnz = __shfl_sync(0xffffffffu, incl, 31);
-        sw.prefix[3 * lane] = excl; sw.prefix[3 * lane + 1] = excl + c0; sw.prefix[3 * lane + 2] = excl + c0 + c1;
-        for (int i = lane; i < nnz; i += 32) sw.counts[i] = 0;
-        __syncwarp();
-        // pass B: counts through the rank hash
-        for (int p = lane; p < npx; p += 32) {
-            const int bin = sw.binbuf[p];
-            const uint32_t word = sw.bitmap[bin >> 5];
-            atomicAdd(&sw.counts[sw.prefix[bin >> 5] + __popc(word & ((1u << (bin & 31)) - 1))], 1u);
-        }
-        __syncwarp();
-        unsigned mx = 0;
-        for (int i = lane; i < nnz; i += 32) mx = max(mx, sw.counts[i]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        // normalize: scale = 1/(max-min) in f64 (min == 0), a = (float)scale (cv2.normalize NORM_MINMAX -> convertTo)
-        const double scale = ((double)mx - 0.0) > DBL_EPSILON ? 1.0 / ((double)mx - 0.0) : 0.0;
-        const float a = (float)scale;
-        // emit entries sorted by bin; moments in bin order per lane, then a fixed shuffle tree (deterministic)
-        uint32_t* __restrict__ e = entries + (int64_t)w * npx;
-        double s1 = 0, s11 = 0;
-        int idx = excl;
-        float eg = 0.f; int cur_g = -1;
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            uint32_t word = t == 0 ? w0 : (t == 1 ? w1 : w2);
-            const int bbase = (3 * lane + t) * 32;
-            while (word) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                const int bin = bbase + bit;
-                const uint32_t cnt = sw.counts[idx];
-                e[idx] = ((uint32_t)bin << 16) | cnt;
-                idx++;
-                const float hf = (float)cnt * a;
-                const double h = (double)hf;
-                s1 += h; s11 += h * h;
-                const int g = bin / 120;
-                if (g != cur_g) { if (cur_g >= 0) atomicAdd(&sw.energy[cur_g], eg); cur_g = g; eg = 0.f; }
-                eg += hf * hf;
-            }
-        }
-        if (cur_g >= 0) atomicAdd(&sw.energy[cur_g], eg);
-        s1 = warp_sum(s1); s11 = warp_sum(s11);
-        unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
-            hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const double A = s11 - s1 * s1 * (1.0 / (double)kHistBins);
-            WinMeta m;
-            m.s1 = s1; m.s11 = s11; m.A = A; m.rA = sqrt(A); m.hash = hsh; m.a = a; m.nnz = nnz;
-            meta[w] = m;
-        }
-        if (E_T && lane < kHistGroups) E_T[(int64_t)lane * e_stride + w] = sqrtf(sw.energy[lane]) * 1.00001f;   // inflated: only ever an upper bound
-        __syncwarp();
-    }
-}
-
 // dense float32 [n][50][60] normalised histograms (tsd_hist, parity artefact of calculateHistAndNormalize)
-__global__ void hist_dense_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta, int n, int npx,
+__global__ void hist_dense_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta, int n, int es,
                                   float* __restrict__ out) {
     int w = blockIdx.x;
     if (w >= n) return;
     float* o = out + (int64_t)w * kHistBins;
     for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) o[i] = 0.f;
     __syncthreads();
-    const uint32_t* e = entries + (int64_t)w * npx;
+    const uint32_t* e = entries + (int64_t)w * es;
     float a = meta[w].a;
     for (int i = threadIdx.x; i < meta[w].nnz; i += blockDim.x) o[e[i] >> 16] = (float)(e[i] & 0xffffu) * a;
 }
 
-// pixel hash only (pass-2-only entry point)
-__global__ void __launch_bounds__(128) k5_hash_kernel(const uint8_t* __restrict__ windows, int n, int npx, WinMeta* __restrict__ meta) {
-    __shared__ unsigned long long red_u[4];
-    int w = blockIdx.x;
+// pixel hash only (pass-2-only entry point): one warp per window
+__global__ void __launch_bounds__(128) k5_hash_kernel(const uint8_t* __restrict__ windows, int n, int npx, int ws, WinMeta* __restrict__ meta) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
-    const uint8_t* px = windows + (int64_t)w * npx * 3;
-    unsigned long long hsh = 0;
-    for (int p = threadIdx.x; p < npx; p += blockDim.x)
-        hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(px[3 * p] | (px[3 * p + 1] << 8) | (px[3 * p + 2] << 16)));
-    unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
-        hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
-    }
-    if ((threadIdx.x & 31) == 0) red_u[threadIdx.x >> 5] = hsh;
-    __syncthreads();
-    if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red_u[i]; meta[w].hash = t; }
+    const uint8_t* px = windows + (int64_t)w * ws;
+    uint32_t hsh = 0;
+    for (int p = lane; p < npx; p += 32) hsh += pix_hash32(p, (uint32_t)(px[3 * p] | (px[3 * p + 1] << 8) | (px[3 * p + 2] << 16)));
+    hsh = warp_sum_u(hsh);
+    if (lane == 0) meta[w].hash = hsh;
 }
 
 // ---- the fold ----------------------------------------------------------------------------------------
@@ -689,7 +558,7 @@ struct FoldParams {
     const double* simtab;        // f(d2), d2 < simtab_n (DET:459-462)
     int simtab_n;
     const Tables* tab;
-    int npx;
+    int npx, ws, es;             // pixels per window; window stride (bytes); entry stride (words)
     int do_hist, do_coords;      // which passes to run (DET:127 then DET:129)
     double hist_tol, hist_lo, coord_tol, coord_lo;   // lo = tol * 0.8823 (DET:217), computed on the host in f64
 };
@@ -723,14 +592,14 @@ __device__ void apply_deletions_block(FoldSmem& sm, const FoldParams& P, int32_t
     for (int p = 0; p < S; p++) {
         if (flags[p] != 1) continue;                        // uniform across the block (global memory, synced)
         const int slot_d = list[p];
-        const unsigned long long hd = P.meta[slot_d].hash;
+        const uint32_t hd = P.meta[slot_d].hash;
         if (tid == 0) sm.victim = p;
         __syncthreads();
         // earlier live entries (flag 0 or 1) with equal hash -> verify bytes; smallest position wins
         for (int q = tid; q < p; q += blockDim.x) {
             if (flags[q] != 2 && P.meta[list[q]].hash == hd) {
-                const uint8_t* A = P.windows + (int64_t)list[q] * nbytes;
-                const uint8_t* B = P.windows + (int64_t)slot_d * nbytes;
+                const uint8_t* A = P.windows + (int64_t)list[q] * P.ws;
+                const uint8_t* B = P.windows + (int64_t)slot_d * P.ws;
                 bool eq = true;
                 for (int i = 0; i < nbytes; i++) if (A[i] != B[i]) { eq = false; break; }
                 if (eq) atomicMin(&sm.victim, q);
@@ -802,8 +671,8 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
             for (int it = 0; it < nin; it++) {
                 const int slot = from_list ? list[it] : base + it;
                 __syncthreads();                            // list[it] read before anyone overwrites it below
-                uint8_t* ipx = P.windows + (int64_t)slot * nbytes;
-                uint32_t* ient = P.entries + (int64_t)slot * P.npx;
+                uint8_t* ipx = P.windows + (int64_t)slot * P.ws;
+                uint32_t* ient = P.entries + (int64_t)slot * P.es;
                 if (tid == 0) sm.icoords = P.coords[slot];
                 if (!by_coords) {
                     const int nnz = P.meta[slot].nnz;
@@ -829,7 +698,7 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
                         for (int p = start + wid; p < end; p += nw) {
                             const int sj = list[p];
                             const WinMeta mj = P.meta[sj];
-                            const uint32_t* ej = P.entries + (int64_t)sj * P.npx;
+                            const uint32_t* ej = P.entries + (int64_t)sj * P.es;
                             double s12 = 0;
                             for (int e = lane; e < mj.nnz; e += 32) {
                                 uint32_t v = ej[e];
@@ -858,7 +727,7 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
                     if (fm < end) {
                         // merge (DET:217-221): pixels = addWeighted(.5,.5) round-half-even, coords = floor mean
                         const int sk = list[fm];
-                        const uint8_t* kpx = P.windows + (int64_t)sk * nbytes;
+                        const uint8_t* kpx = P.windows + (int64_t)sk * P.ws;
                         if (!by_coords) clear_dense_block(sm.h.dense, ient, P.meta[slot].nnz);
                         for (int i = tid; i < nbytes; i += blockDim.x) {
                             int s = ipx[i] + kpx[i];
@@ -875,19 +744,14 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
                             build_hist_block(ipx, P.npx, sm.h.sdiv, sm.h.hdiv, sm.h.hbin, sm.h.sbin, sm.h.dense, sm.h.red, ient, P.meta + slot);
                         } else {
                             // keep the pixel hash current for the pop-by-equality rule
-                            unsigned long long hsh = 0;
+                            uint32_t hsh = 0;
                             for (int p = tid; p < P.npx; p += blockDim.x)
-                                hsh += mix64(((unsigned long long)p << 24) | (unsigned long long)(ipx[3 * p] | (ipx[3 * p + 1] << 8) | (ipx[3 * p + 2] << 16)));
-                            unsigned hl = (unsigned)hsh, hh = (unsigned)(hsh >> 32);
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                unsigned long long other = ((unsigned long long)__shfl_xor_sync(0xffffffffu, hh, o) << 32) | __shfl_xor_sync(0xffffffffu, hl, o);
-                                hsh += other; hl = (unsigned)hsh; hh = (unsigned)(hsh >> 32);
-                            }
-                            unsigned long long* ru = reinterpret_cast<unsigned long long*>(sm.h.red);
+                                hsh += pix_hash32(p, (uint32_t)(ipx[3 * p] | (ipx[3 * p + 1] << 8) | (ipx[3 * p + 2] << 16)));
+                            hsh = warp_sum_u(hsh);
+                            uint32_t* ru = reinterpret_cast<uint32_t*>(sm.h.red);
                             if (lane == 0) ru[wid] = hsh;
                             __syncthreads();
-                            if (tid == 0) { unsigned long long t = 0; for (int i = 0; i < nw; i++) t += ru[i]; P.meta[slot].hash = t; }
+                            if (tid == 0) { uint32_t t = 0; for (int i = 0; i < nw; i++) t += ru[i]; P.meta[slot].hash = t; }
                             __syncthreads();
                         }
                         start = fm + 1;
@@ -923,7 +787,7 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
 // gather survivors (list -> compact CSR output).  One CTA per frame.
 __global__ void k5_gather_kernel(const uint8_t* __restrict__ windows, const int4* __restrict__ coords,
                                  const int32_t* __restrict__ in_offsets, const int32_t* __restrict__ list,
-                                 const int32_t* __restrict__ out_offsets, int nframes, int nbytes,
+                                 const int32_t* __restrict__ out_offsets, int nframes, int nbytes, int ws,
                                  uint8_t* __restrict__ out_windows, int4* __restrict__ out_coords, int32_t* __restrict__ out_slots) {
     int f = blockIdx.x;
     if (f >= nframes) return;
@@ -932,8 +796,8 @@ __global__ void k5_gather_kernel(const uint8_t* __restrict__ windows, const int4
     for (int r = 0; r < cnt; r++) {
         const int slot = l[r];
         if (out_windows) {
-            const uint8_t* s = windows + (int64_t)slot * nbytes;
-            uint8_t* d = out_windows + (int64_t)(o0 + r) * nbytes;
+            const uint8_t* s = windows + (int64_t)slot * ws;
+            uint8_t* d = out_windows + (int64_t)(o0 + r) * nbytes;     // public layout: packed
             for (int i = threadIdx.x; i < nbytes; i += blockDim.x) d[i] = s[i];
         }
         if (threadIdx.x == 0) {
@@ -947,13 +811,12 @@ __global__ void k5_gather_kernel(const uint8_t* __restrict__ windows, const int4
 // K6  cv2.cvtColor(BGR2GRAY)  (REC:388), SURVEY A.6
 // =====================================================================================================
 __global__ void k6_gray_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
-                               const int32_t* __restrict__ n_ptr, int n_max, int npx, uint8_t* __restrict__ gray) {
+                               const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws, uint8_t* __restrict__ gray) {
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int64_t total = (int64_t)n * npx;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t src = i;
-        if (slots) { int w = (int)(i / npx); src = (int64_t)slots[w] * npx + (i - (int64_t)w * npx); }
-        const uint8_t* p = windows + src * 3;
+        const int w = (int)(i / npx);
+        const uint8_t* p = windows + (int64_t)(slots ? slots[w] : w) * ws + (i - (int64_t)w * npx) * 3;
         gray[i] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
     }
 }

@@ -26,7 +26,12 @@ d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(a.frames, device=dev) % U
 d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
 ctx = tsd_b200.Context(0, "det")
 ctx.set_templates(g["red6"], g["blue6"])
+def one():
+    ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=a.boxes)
 if a.times:
+    for _ in range(3):
+        one()
+    ctx.synchronize()
     ctx.set_profiling(True)
 for _ in range(a.steps):
     ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=a.boxes)
