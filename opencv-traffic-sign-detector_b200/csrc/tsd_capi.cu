@@ -62,10 +62,11 @@ struct tsd_ctx {
     HogConst hog;
     // grow-only scratch
     DevBuf b_coords, b_winframe, b_windows, b_entries, b_meta, b_list, b_flags, b_cnt, b_winoff, b_survcnt, b_survoff,
-        b_slots, b_pairs, b_energy, b_red, b_blue, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
+        b_slots, b_pairs, b_energy, b_red, b_blue, b_bits, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
     // last enqueue
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
+    int k2_variant = 2;          // TSD_K2=v2|v3|v4 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
     int ev_used = 0;
@@ -153,6 +154,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
     t.sdiv[0] = t.hdiv[0] = 0;
@@ -190,7 +192,7 @@ int tsd_destroy(tsd_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
-                      &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_id, &c->b_hund,
+                      &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
@@ -374,7 +376,20 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     if (n_max == 0) return TSD_OK;
     const int g4 = cdiv(n_max, 4);
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
-    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    // TSD_K2 = v2 | v3 | v4 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all three are bit-identical.
+    // v3 (staged through shared memory with cp.async) needs 16-byte aligned rows: its 128-bit chunks never leave the frame buffer.
+    const bool fast = c->k2_variant == 3 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
+    const int gk = cdiv(n_max, kK2Warps);
+    const bool v4 = c->k2_variant == 4 && ((uintptr_t)windows % 16 == 0);
+    if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 1 && D == 32) k2_crop_resize_v3_kernel<1, 32><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 3 && D == 25) k2_crop_resize_v4_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
     else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
     else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
     else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
@@ -624,9 +639,10 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
     Stage s(c);
     void *dw = (void*)windows, *dr = red, *db = blue;
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx)); }
-    int grid = cdiv((int64_t)n * npx, 256);
-    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
-    k3_masks_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db);
+    int grid = cdiv((int64_t)n * 32, 256);
+    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    k3_masks_v2_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db,
+                                                    npx, nullptr);       // public layout: packed windows and masks
     TRY(check_launch(c, "k3_masks"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -662,7 +678,7 @@ int tsd_score_masks(tsd_ctx* c, const uint8_t* red, const uint8_t* blue, int n, 
         if (scores) TRY(s.alloc(&ds, (size_t)n * 12 * 4));
         TRY(s.alloc(&di, (size_t)n * 4)); TRY(s.alloc(&dh, (size_t)n * 4)); TRY(s.alloc(&de, (size_t)n));
     }
-    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, c->d_tmpl,
+    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, npx, c->d_tmpl,
                                                                         c->cfg.score_tol_hundredths, (int32_t*)ds, (int32_t*)di, (int32_t*)dh, (uint8_t*)de);
     TRY(check_launch(c, "k4_score"));
     if (mem == TSD_MEM_HOST) {
@@ -759,6 +775,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
     if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
     const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
+    const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
     if (mode == TSD_RUN_DETECT && (!c->have_templates || c->tmpl_D != D)) return fail(TSD_E_STATE, "templates not set for D=%d", D);
     if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
     CU(cudaSetDevice(c->device));
@@ -789,8 +806,9 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_emit, cap));
     TRY(ensure(c, c->b_det, cap * sizeof(DetRec)));
     if (mode == TSD_RUN_DETECT) {
-        TRY(ensure(c, c->b_red, cap * npx));
-        TRY(ensure(c, c->b_blue, cap * npx));
+        TRY(ensure(c, c->b_red, cap * ms));
+        TRY(ensure(c, c->b_blue, cap * ms));
+        TRY(ensure(c, c->b_bits, cap * 2 * NW * 4));
     } else {
         TRY(ensure(c, c->b_gray, cap * npx));
         TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
@@ -819,13 +837,21 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     const int32_t* d_nsurv = survoff + nframes;
     if (mode == TSD_RUN_DETECT) {
         // K3 + K4 (DET:708-716)
-        int grid = cdiv((int64_t)cap * npx, 256);
-        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k3_masks_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p);
+        int grid = cdiv((int64_t)cap * 32, 256);
+        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        k3_masks_v2_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p,
+                                                        (uint8_t*)c->b_blue.p, ms, (uint32_t*)c->b_bits.p);
         TRY(check_launch(c, "k3_masks"));
         mark(c, "k3_masks");
-        k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p, d_nsurv, nb, npx, c->d_tmpl,
-                                                                             c->cfg.score_tol_hundredths, nullptr, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
+        if (NW == 20)
+            k4_score_bits_kernel<20><<<cdiv(cap, 128), 128, 0, c->stream>>>((uint32_t*)c->b_bits.p, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths,
+                                                                             (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
+        else if (NW == 32)
+            k4_score_bits_kernel<32><<<cdiv(cap, 128), 128, 0, c->stream>>>((uint32_t*)c->b_bits.p, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths,
+                                                                             (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
+        else
+            k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p, d_nsurv, nb, npx, ms, c->d_tmpl,
+                                                                                 c->cfg.score_tol_hundredths, nullptr, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
         TRY(check_launch(c, "k4_score"));
         mark(c, "k4_score");
     } else {

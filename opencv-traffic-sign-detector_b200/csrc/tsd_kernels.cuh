@@ -322,34 +322,313 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
     }
 }
 
+// K2 v4: v2 (direct gather through L1) + two cheap savings: (1) the horizontal pass of a source row is reused by the next
+// destination row when both touch it (for the typical 1.4x down-scale that removes 28 % of the byte loads and multiplies),
+// (2) the destination window is assembled in shared memory and leaves as 128-bit stores (zero pad included).
+template <int C, int D>
+__global__ void __launch_bounds__(128) k2_crop_resize_v4_kernel(
+    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
+    uint8_t* __restrict__ windows, int out_stride) {
+    constexpr int OUTB = (D * D * C + 15) & ~15;
+    __shared__ __align__(16) uint8_t s_out[4][OUTB];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + wl;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const int4 c = coords[w];
+    const int cx = min(c.x, W), cy = min(c.y, H);
+    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
+    if (cw <= 0 || ch <= 0) return;
+    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
+    uint8_t* __restrict__ gout = windows + (int64_t)w * out_stride;
+    uint8_t* so = s_out[wl];
+    const bool act = lane < D;
+    const int li = act ? lane : 0;
+    if (lane < OUTB - D * D * C) so[D * D * C + lane] = 0;   // zero pad of the internal layout
+    uint8_t* sp = so + li * C;
+    if (cw == D && ch == D) {                               // same size: copy
+        const uint8_t* p = src + li * C;
+#pragma unroll 5
+        for (int dy = 0; dy < D; dy++) {
+#pragma unroll
+            for (int k = 0; k < C; k++) { const uint8_t v = __ldg(p + (int64_t)dy * row_stride + k); if (act) sp[dy * D * C + k] = v; }
+        }
+    } else if (cw == 2 * D && ch == 2 * D) {                // INTER_AREA 2x2 fast path
+        const uint8_t* p = src + 2 * li * C;
+#pragma unroll 5
+        for (int dy = 0; dy < D; dy++) {
+            const uint8_t* q0 = p + (int64_t)(2 * dy) * row_stride;
+            const uint8_t* q1 = q0 + row_stride;
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                const int v = (__ldg(q0 + k) + __ldg(q0 + C + k) + __ldg(q1 + k) + __ldg(q1 + C + k) + 2) >> 2;
+                if (act) sp[dy * D * C + k] = (uint8_t)v;
+            }
+        }
+    } else {
+        // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
+        int xs0, xd1, xa0, xa1, yr0, yr1, yb0, yb1;
+        {
+            const double scale = 1.0 / ((double)D / (double)cw);
+            float f = (float)(((double)li + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= cw - 1) { f = 0.f; s = cw - 1; }
+            xs0 = s * C;
+            xd1 = (min(s + 1, cw - 1) - s) * C;
+            xa0 = __float2int_rn((1.f - f) * 2048.f);
+            xa1 = __float2int_rn(f * 2048.f);
+        }
+        {
+            const double scale = 1.0 / ((double)D / (double)ch);
+            float f = (float)(((double)li + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            yr0 = min(max(s, 0), ch - 1);
+            yr1 = min(max(s + 1, 0), ch - 1);
+            yb0 = __float2int_rn((1.f - f) * 2048.f);
+            yb1 = __float2int_rn(f * 2048.f);
+        }
+        const uint8_t* px = src + xs0;
+        int prev_r1 = -1;
+        int T1p[C];
+#pragma unroll
+        for (int k = 0; k < C; k++) T1p[k] = 0;
+#pragma unroll 5
+        for (int dy = 0; dy < D; dy++) {
+            const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
+            const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
+            int T0[C], T1[C];
+            if (r0 == prev_r1) {                            // warp-uniform: row r0 was this lane's lower row one step ago
+#pragma unroll
+                for (int k = 0; k < C; k++) T0[k] = T1p[k];
+            } else {
+                const uint8_t* p0 = px + (int64_t)r0 * row_stride;
+#pragma unroll
+                for (int k = 0; k < C; k++) T0[k] = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
+            }
+            if (r1 == r0) {
+#pragma unroll
+                for (int k = 0; k < C; k++) T1[k] = T0[k];
+            } else {
+                const uint8_t* p1 = px + (int64_t)r1 * row_stride;
+#pragma unroll
+                for (int k = 0; k < C; k++) T1[k] = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
+            }
+            prev_r1 = r1;
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                T1p[k] = T1[k];
+                const int v = (((b0 * (T0[k] >> 4)) >> 16) + ((b1 * (T1[k] >> 4)) >> 16) + 2) >> 2;
+                if (act) sp[dy * D * C + k] = (uint8_t)v;
+            }
+        }
+    }
+    __syncwarp();
+    if (out_stride == OUTB) {                               // internal layout: 128-bit stores
+        const uint4* s4 = reinterpret_cast<const uint4*>(so);
+        uint4* g4 = reinterpret_cast<uint4*>(gout);
+        for (int i = lane; i < OUTB / 16; i += 32) g4[i] = s4[i];
+    } else {                                                // packed public layout
+        for (int i = lane; i < D * D * C; i += 32) gout[i] = so[i];
+    }
+}
+
+// K2 v3: the crop is first STAGED in shared memory with 128-bit cp.async loads (only the rows the resize touches, whole
+// row segments, 16-byte aligned chunks), then every tap is a shared-memory byte read.  v2 was bound by the LSU issue rate of
+// its 12 global byte loads per output pixel row; here the global side moves 16 bytes per load and the horizontal pass of a
+// source row is reused by the next destination row when both touch it.  The destination rows are processed in two halves so
+// that the staging buffer holds at most D+3 source rows (shared memory per warp stays under 8 KB -> 28 warps per SM).
+// The output window is assembled in shared memory and written with 128-bit stores (zero pad included).  Needs
+// row_stride % 16 == 0, W*C % 16 == 0 and a 16-byte aligned frame base (host checks, else v2); crops wider than kK2Pitch
+// bytes per row take the direct-gather path of v2 inside this kernel (same arithmetic).
+constexpr int kK2Pitch = 208;                         // staged bytes per row (crop width * C + alignment slack)
+constexpr int kK2Warps = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int C, int D>
+__global__ void __launch_bounds__(kK2Warps * 32) k2_crop_resize_v3_kernel(
+    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
+    uint8_t* __restrict__ windows, int out_stride) {
+    constexpr int HALF = (D + 1) / 2;
+    constexpr int MAXSLOT = 2 * HALF + 2;
+    constexpr int OUTB = (D * D * C + 15) & ~15;
+    __shared__ __align__(16) uint8_t s_reg[kK2Warps][MAXSLOT * kK2Pitch];
+    __shared__ __align__(16) uint8_t s_out[kK2Warps][OUTB];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = blockIdx.x * kK2Warps + wl;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const int4 c = coords[w];
+    const int cx = min(c.x, W), cy = min(c.y, H);
+    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
+    if (cw <= 0 || ch <= 0) return;
+    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
+    uint8_t* __restrict__ gout = windows + (int64_t)w * out_stride;
+    const bool act = lane < D;
+    const int li = act ? lane : 0;
+    const bool same = cw == D && ch == D, area = cw == 2 * D && ch == 2 * D;
+    // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
+    int xs0 = li * C, xd1 = 0, xa0 = 2048, xa1 = 0, yr0 = li, yr1 = li, yb0 = 2048, yb1 = 0;
+    if (area) { xs0 = 2 * li * C; xd1 = C; xa1 = 2048; yr0 = 2 * li; yr1 = 2 * li + 1; }
+    else if (!same) {
+        {
+            const double scale = 1.0 / ((double)D / (double)cw);
+            float f = (float)(((double)li + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= cw - 1) { f = 0.f; s = cw - 1; }
+            xs0 = s * C;
+            xd1 = (min(s + 1, cw - 1) - s) * C;
+            xa0 = __float2int_rn((1.f - f) * 2048.f);
+            xa1 = __float2int_rn(f * 2048.f);
+        }
+        {
+            const double scale = 1.0 / ((double)D / (double)ch);
+            float f = (float)(((double)li + 0.5) * scale - 0.5);
+            int s = (int)floorf(f); f -= (float)s;
+            yr0 = min(max(s, 0), ch - 1);
+            yr1 = min(max(s + 1, 0), ch - 1);
+            yb0 = __float2int_rn((1.f - f) * 2048.f);
+            yb1 = __float2int_rn(f * 2048.f);
+        }
+    }
+    const int o = (int)((uintptr_t)src & 15);               // same for every row: row_stride % 16 == 0
+    const bool staged = o + cw * C <= kK2Pitch;
+    const int cpr = (o + cw * C + 15) >> 4;                  // 16-byte chunks per staged row
+    uint8_t* reg = s_reg[wl];
+    uint8_t* so = s_out[wl];
+    if (lane < OUTB - D * D * C) so[D * D * C + lane] = 0;   // zero pad of the internal layout
+    const uint8_t* sx = reg + o + xs0;
+    const uint8_t* gx = src + xs0;
+    int prev_r1 = -1;
+    int T1p[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) T1p[k] = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int dy0 = half * HALF, dy1 = half ? D : HALF;
+        const int rfirst = __shfl_sync(0xffffffffu, yr0, dy0), rlast = __shfl_sync(0xffffffffu, yr1, dy1 - 1);
+        const bool dense_rows = rlast - rfirst + 1 <= MAXSLOT;   // slot = row - rfirst ; else slot = 2*(dy-dy0) (+1)
+        if (staged) {
+            __syncwarp();                                    // the previous half's taps are done
+            const int nslots = dense_rows ? rlast - rfirst + 1 : 2 * (dy1 - dy0);
+            const int total = nslots * cpr;
+            const uint8_t* g0 = src - o;
+            for (int i0 = 0; i0 < total; i0 += 32) {         // uniform trip count: every lane takes part in the shuffles
+                const int i = i0 + lane;
+                const bool ok = i < total;
+                const int sl = ok ? i / cpr : 0, ck = i - sl * cpr;
+                const int ra = __shfl_sync(0xffffffffu, yr0, (dy0 + (sl >> 1)) & 31), rb = __shfl_sync(0xffffffffu, yr1, (dy0 + (sl >> 1)) & 31);
+                const int row = dense_rows ? rfirst + sl : ((sl & 1) ? rb : ra);
+                if (ok) cp_async16(reg + sl * kK2Pitch + ck * 16, g0 + (int64_t)row * row_stride + ck * 16);
+            }
+            cp_async_wait_all();
+            __syncwarp();
+        }
+        for (int dy = dy0; dy < dy1; dy++) {
+            const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
+            const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
+            int T0[C], T1[C];
+            if (staged) {
+                const int s0 = dense_rows ? r0 - rfirst : 2 * (dy - dy0), s1 = dense_rows ? r1 - rfirst : 2 * (dy - dy0) + 1;
+                if (r0 == prev_r1) {
+#pragma unroll
+                    for (int k = 0; k < C; k++) T0[k] = T1p[k];
+                } else {
+                    const uint8_t* p = sx + s0 * kK2Pitch;
+#pragma unroll
+                    for (int k = 0; k < C; k++) T0[k] = p[k] * xa0 + p[xd1 + k] * xa1;
+                }
+                if (r1 == r0) {
+#pragma unroll
+                    for (int k = 0; k < C; k++) T1[k] = T0[k];
+                } else {
+                    const uint8_t* p = sx + s1 * kK2Pitch;
+#pragma unroll
+                    for (int k = 0; k < C; k++) T1[k] = p[k] * xa0 + p[xd1 + k] * xa1;
+                }
+            } else {
+                const uint8_t* p0 = gx + (int64_t)r0 * row_stride;
+                const uint8_t* p1 = gx + (int64_t)r1 * row_stride;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    T0[k] = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
+                    T1[k] = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
+                }
+            }
+            prev_r1 = r1;
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                T1p[k] = T1[k];
+                int v;
+                if (same) v = T0[k] >> 11;                                     // copy: p * 2048 >> 11
+                else if (area) v = (((T0[k] + T1[k]) >> 11) + 2) >> 2;         // (s00+s01+s10+s11+2)>>2, all four weights 2048
+                else v = (((b0 * (T0[k] >> 4)) >> 16) + ((b1 * (T1[k] >> 4)) >> 16) + 2) >> 2;
+                if (act) so[(dy * D + lane) * C + k] = (uint8_t)v;
+            }
+        }
+    }
+    __syncwarp();
+    // 128-bit stores of the assembled window (internal layout) or byte stores (packed public layout)
+    if (out_stride == OUTB) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(so);
+        uint4* g4 = reinterpret_cast<uint4*>(gout);
+        for (int i = lane; i < OUTB / 16; i += 32) g4[i] = s4[i];
+    } else {
+        for (int i = lane; i < D * D * C; i += 32) gout[i] = so[i];
+    }
+}
+
 // =====================================================================================================
 // K3  getColorMaskRedOrBlue(img,'r'/'b')  (DET:63-89), SURVEY A.3.  One thread per pixel; integer HSV tables.
 // `slots` (optional) = indirection to the surviving windows inside the work buffer.
 // =====================================================================================================
-__global__ void __launch_bounds__(256) k3_masks_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
-                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws,
-                                                       const Tables* __restrict__ tab, HsvBounds hb,
-                                                       uint8_t* __restrict__ red, uint8_t* __restrict__ blue) {
+// K3 v2: one warp per window, lane-strided pixels (coalesced byte loads, stride 3), mask bytes written with stride `ms`
+// (npx for the public packed layout, padded to 16 for the internal one) and, optionally, the same masks bit-packed
+// (pixel p -> word p>>5, bit p&31; [w][0..NW) red, [w][NW..2NW) blue) which is what K4 consumes inside the chain.
+__global__ void __launch_bounds__(256) k3_masks_v2_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
+                                                          const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws,
+                                                          const Tables* __restrict__ tab, HsvBounds hb, uint8_t* __restrict__ red,
+                                                          uint8_t* __restrict__ blue, int ms, uint32_t* __restrict__ bits) {
     __shared__ int32_t s_sdiv[256], s_hdiv[256];
     s_sdiv[threadIdx.x & 255] = tab->sdiv[threadIdx.x & 255];
     s_hdiv[threadIdx.x & 255] = tab->hdiv[threadIdx.x & 255];
     __syncthreads();
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    const int64_t total = (int64_t)n * npx;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int w = (int)(i / npx), p = (int)(i - (int64_t)w * npx);
-        int slot = slots ? slots[w] : w;
-        const uint8_t* px = windows + (int64_t)slot * ws + p * 3;
-        int H, S, V;
-        bgr2hsv(px[0], px[1], px[2], s_sdiv, s_hdiv, H, S, V);
-        bool r0 = H >= hb.red_lo[0][0] && H <= hb.red_hi[0][0] && S >= hb.red_lo[0][1] && S <= hb.red_hi[0][1] &&
-                  V >= hb.red_lo[0][2] && V <= hb.red_hi[0][2];
-        bool r1 = H >= hb.red_lo[1][0] && H <= hb.red_hi[1][0] && S >= hb.red_lo[1][1] && S <= hb.red_hi[1][1] &&
-                  V >= hb.red_lo[1][2] && V <= hb.red_hi[1][2];
-        bool bl = H >= hb.blue_lo[0] && H <= hb.blue_hi[0] && S >= hb.blue_lo[1] && S <= hb.blue_hi[1] &&
-                  V >= hb.blue_lo[2] && V <= hb.blue_hi[2];
-        red[i] = (r0 || r1) ? 255 : 0;                      // cv2.add saturates
-        blue[i] = bl ? 255 : 0;
+    const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int NW = (npx + 31) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+        const uint8_t* __restrict__ px = windows + (int64_t)(slots ? slots[w] : w) * ws;
+        uint8_t* __restrict__ ro = red + (int64_t)w * ms;
+        uint8_t* __restrict__ bo = blue + (int64_t)w * ms;
+        uint32_t myr = 0, myb = 0;
+#pragma unroll 4
+        for (int i = 0; i < NW; i++) {
+            const int p = i * 32 + lane;
+            const bool valid = p < npx;
+            const int pp = valid ? p : 0;
+            const int b = __ldg(px + 3 * pp), g = __ldg(px + 3 * pp + 1), r = __ldg(px + 3 * pp + 2);
+            int H, S, V;
+            bgr2hsv(b, g, r, s_sdiv, s_hdiv, H, S, V);
+            const bool r0 = H >= hb.red_lo[0][0] && H <= hb.red_hi[0][0] && S >= hb.red_lo[0][1] && S <= hb.red_hi[0][1] &&
+                            V >= hb.red_lo[0][2] && V <= hb.red_hi[0][2];
+            const bool r1 = H >= hb.red_lo[1][0] && H <= hb.red_hi[1][0] && S >= hb.red_lo[1][1] && S <= hb.red_hi[1][1] &&
+                            V >= hb.red_lo[1][2] && V <= hb.red_hi[1][2];
+            const bool bl = H >= hb.blue_lo[0] && H <= hb.blue_hi[0] && S >= hb.blue_lo[1] && S <= hb.blue_hi[1] &&
+                            V >= hb.blue_lo[2] && V <= hb.blue_hi[2];
+            const bool rr = r0 || r1;                       // cv2.add of the two bands saturates at 255
+            if (valid) { ro[p] = rr ? 255 : 0; bo[p] = bl ? 255 : 0; }
+            const unsigned wr = __ballot_sync(0xffffffffu, valid && rr), wb = __ballot_sync(0xffffffffu, valid && bl);
+            if (lane == i) { myr = wr; myb = wb; }
+        }
+        if (bits && lane < NW) { bits[(int64_t)w * 2 * NW + lane] = myr; bits[(int64_t)w * 2 * NW + NW + lane] = myb; }
     }
 }
 
@@ -379,7 +658,7 @@ struct ScoreTemplates {
 };
 
 __global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict__ red, const uint8_t* __restrict__ blue,
-                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx,
+                                                       const int32_t* __restrict__ n_ptr, int n_max, int npx, int ms,
                                                        const ScoreTemplates* __restrict__ tmpl, int tol_hundredths,
                                                        int32_t* __restrict__ scores, int32_t* __restrict__ id,
                                                        int32_t* __restrict__ hundredths, uint8_t* __restrict__ emit) {
@@ -387,8 +666,8 @@ __global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     if (w >= n) return;
-    const uint8_t* r = red + (int64_t)w * npx;
-    const uint8_t* b = blue + (int64_t)w * npx;
+    const uint8_t* r = red + (int64_t)w * ms;
+    const uint8_t* b = blue + (int64_t)w * ms;
     const int nwords = (npx + 31) >> 5;
     int tp = 0;
     for (int i = 0; i < nwords; i++) {
@@ -414,6 +693,51 @@ __global__ void __launch_bounds__(128) k4_score_kernel(const uint8_t* __restrict
         hundredths[w] = s;
         emit[w] = s > tol_hundredths ? 1 : 0;
     }
+}
+
+// K4 v2 (inside the chain): the same decision from K3's bit-packed masks.  One THREAD per window: 2*NW mask words in
+// registers (128-bit loads), 12 x NW template words in shared memory (broadcast reads), popcounts, LUT, decision.
+template <int NW>
+__global__ void __launch_bounds__(128) k4_score_bits_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ n_ptr, int n_max,
+                                                            const ScoreTemplates* __restrict__ tmpl, int tol_hundredths,
+                                                            int32_t* __restrict__ id, int32_t* __restrict__ hundredths, uint8_t* __restrict__ emit) {
+    __shared__ uint32_t s_t[12][NW];
+    for (int i = threadIdx.x; i < 12 * NW; i += blockDim.x) s_t[i / NW][i % NW] = tmpl->bits[i / NW][i % NW];
+    __syncthreads();
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    static_assert(NW % 4 == 0, "mask words are loaded 4 at a time");
+    const uint4* src = reinterpret_cast<const uint4*>(bits + (int64_t)w * 2 * NW);
+    int tp[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) tp[k] = 0;
+#pragma unroll
+    for (int q = 0; q < NW / 4; q++) {
+        const uint4 vr = __ldg(src + q), vb = __ldg(src + NW / 4 + q);
+        const uint32_t wr[4] = {vr.x, vr.y, vr.z, vr.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                tp[k] += __popc(wr[u] & s_t[k][4 * q + u]);
+                tp[6 + k] += __popc(wb[u] & s_t[6 + k][4 * q + u]);
+            }
+        }
+    }
+    // first strict maximum within each group of 6 (DET:249-259); red wins only if strictly better (DET:236)
+    int best_r = -1, id_r = 0, best_b = -1, id_b = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int sr = (int)__ldg(&tmpl->lut[k][tp[k]]), sb = (int)__ldg(&tmpl->lut[6 + k][tp[6 + k]]);
+        if (sr > best_r) { best_r = sr; id_r = k + 1; }
+        if (sb > best_b) { best_b = sb; id_b = k + 1; }
+    }
+    const bool red_wins = best_r > best_b;
+    const int sc = red_wins ? best_r : best_b;
+    id[w] = red_wins ? id_r : id_b;
+    hundredths[w] = sc;
+    emit[w] = sc > tol_hundredths ? 1 : 0;
 }
 
 // =====================================================================================================
