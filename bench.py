@@ -42,61 +42,84 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """Per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, divided by the
+    aspect-passing windows of that capture) recorded under profiles/; scaled by the run's window count in the report."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def templates():
     g = np.load(os.path.join(ROOT, "tests", "golden", "det_templates.npz"))
     return g["red6"], g["blue6"]
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every 10 ms DURING the timed region (B200_PROFILING.md recipe;
+    an nvidia-smi subprocess takes longer to start than the timed region lasts)."""
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.t, self.h = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # torch device index -> NVML index through the PCI bus id (CUDA_VISIBLE_DEVICES may remap)
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for k in range(pynvml.nvmlDeviceGetCount()):
+                    hk = pynvml.nvmlDeviceGetHandleByIndex(k)
+                    if pynvml.nvmlDeviceGetPciInfo(hk).bus == bus:
+                        self.h = hk
+                        break
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r, _ in self.samples))
+        sm = [c for c, _, _ in self.samples]
         try:
-            self.proc.wait(timeout=5)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            mx = None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "power_w_max": max((p for _, _, p in self.samples), default=None), "reasons": reasons}
 
 
-def algorithmic_bytes(boxes, offsets, counts):
+def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7):
     """SURVEY.md section 8(d) per-unit figures x the units one launch processes (independent of the implementation).
-    K2: in 3*min(w_c,2D)*min(h_c,2D) + out 3*D*D per aspect-passing window; k5_hist: in 3*D*D + out 8*nnz<=... credited
-    as 3*D*D + 16; fold: in 3*D*D+16 per input window, out 3*D*D+16 per survivor; K3: 3*D*D in, 2*D*D out; K4: 2*D*D in, 8 out."""
+    K2: in 3*min(w_c,2D)*min(h_c,2D) + out 3*D*D per aspect-passing window; k5_hist: 3*D*D + 16 per window; k5_pairs:
+    the sparse histograms + moments + energies read once, bit rows written; k5_fold: in 3*D*D+16 per input window, out
+    3*D*D+16 per survivor; K3: 3*D*D in, 2*D*D out; K4: 2*D*D in, 8 out (the chain's K4 reads K3's bit-packed masks, which
+    is less; it is credited with the SURVEY figure)."""
     b = boxes.astype(np.int64)
     w, h = b[:, 2].astype(np.float64), b[:, 3].astype(np.float64)
     pm1 = 1.30 - 1
@@ -112,6 +135,9 @@ def algorithmic_bytes(boxes, offsets, counts):
         "k1_expand_filter": int(len(b) * 33),
         "k2_crop_resize": int(k2_in + npass * 3 * px),
         "k5_hist": int(npass * (3 * px + 16)),
+        # every window's sparse histogram (4 B per non-zero bin) + moments (48 B) + group energies (100 B) read once,
+        # two bit rows written per window
+        "k5_pairs": int(4 * hist_entries + npass * (48 + 100 + 8 * row_words)),
         "k5_fold": int(npass * (3 * px + 16) + nsurv * (3 * px + 16)),
         "k3_masks": int(nsurv * 5 * px),
         "k4_score": int(nsurv * (2 * px + 8)),
@@ -245,6 +271,7 @@ def run_b200(args, rank, world, local_rank):
     stage_ms = dict(ctx.stage_times())
     ctx.set_profiling(False)
     det, counts = ctx.fetch_detections(nb)
+    hist_entries = ctx.stat_hist_entries()
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,7 +286,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- e2e: public host-buffer API, pinned host frames, H2D + D2H inside the timed region --------------------------
     Fe = min(args.e2e_frames, F)
     h_frames = torch.empty((Fe, H, W, 3), dtype=torch.uint8).pin_memory()
-    h_frames.copy_(d_frames[:Fe].cpu())
+    for f0 in range(0, Fe, 256):
+        h_frames[f0:f0 + 256].copy_(d_frames[f0:f0 + 256])
     hf = h_frames.numpy()
     hb, ho = boxes[:off[Fe]], off[:Fe + 1]
     for _ in range(2):
@@ -276,11 +304,15 @@ def run_b200(args, rank, world, local_rank):
         e_dt = float(t.item())
     e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(hf.nbytes + hb.nbytes + ho.nbytes),
            "d2h_bytes_per_step": int(len(edet) * 32 + 12), "frames_per_step": Fe, "ms_per_step": e_dt * 1e3,
-           "frames_per_sec": world * Fe / e_dt, "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST, pinned host frames)"}
+           "frames_per_sec": world * Fe / e_dt,
+           "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST): page-locked host frames are read in place by K2 over PCIe "
+                  "(only candidate ROIs cross the bus), boxes H2D, detection records D2H; h2d_bytes_per_step counts the whole "
+                  "host input (frames + boxes) the call consumes"}
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        alg, npass = algorithmic_bytes(boxes, off, counts)
+        alg, npass = algorithmic_bytes(boxes, off, counts, hist_entries, (NBOX + 31) // 32)
+        traffic = load_traffic()
         per_stage = {k: v / args.steps for k, v in stage_ms.items()}
         dom = max(per_stage, key=per_stage.get) if per_stage else "k2_crop_resize"
         achieved = alg.get(dom, 0) / (per_stage.get(dom, 1e9) * 1e-3) / 1e9
@@ -296,7 +328,8 @@ def run_b200(args, rank, world, local_rank):
             "stage_counts": {"raw": int(counts[0]), "aspect_passing": int(counts[1]), "survivors": int(counts[2]), "detections": int(counts[3])},
             "detections_all_ranks": int(ndet_total),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom, 0),
+                         "traffic": traffic.get(dom, {}).get("dram_bytes_per_window", 0) * npass or None,
+                         "traffic_source": traffic.get(dom, {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom, 0),
                          "kernel_ms_per_launch": per_stage.get(dom)},
             "stages_ms_per_step": per_stage,
             "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in per_stage.items() if v > 0},
@@ -319,8 +352,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="resident frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--frames", type=int, default=4096, help="resident frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

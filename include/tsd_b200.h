@@ -78,6 +78,11 @@ TSD_API int tsd_destroy(tsd_ctx *ctx);
 /* The context's cudaStream_t (as void*), so callers (torch) can order their own work with it. */
 TSD_API void *tsd_stream(tsd_ctx *ctx);
 TSD_API int tsd_synchronize(tsd_ctx *ctx);
+/* Page-lock a caller-owned host buffer (cudaHostRegister, mapped).  tsd_detect_frames with TSD_MEM_HOST reads page-locked
+ * frames IN PLACE over PCIe (only the candidate ROIs are transferred); pageable frames are copied whole, in chunks that
+ * overlap the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */
+TSD_API int tsd_host_register(void *p, int64_t bytes);
+TSD_API int tsd_host_unregister(void *p);
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 TSD_API int64_t tsd_launch_count(tsd_ctx *ctx);
 
@@ -183,6 +188,10 @@ TSD_API int tsd_enqueue_frames(tsd_ctx *ctx, int mode, const uint8_t *d_frames, 
                                int64_t row_stride, int64_t frame_stride, const int32_t *d_boxes,
                                const int32_t *d_box_offsets, int nboxes_total, int max_boxes_per_frame);
 TSD_API int tsd_fetch_detections(tsd_ctx *ctx, tsd_detection *det, int det_cap, int32_t *ndet, int32_t *counts);
+
+/* Measurement helper: total number of non-zero histogram bins over the windows of the last tsd_enqueue_frames call
+ * (the bytes k5_pairs has to read at least once).  Synchronises. */
+TSD_API int tsd_stat_hist_entries(tsd_ctx *ctx, int64_t *total);
 
 /* Device-side stage timing: CUDA events are recorded between the stages of every tsd_enqueue_frames call made after
  * tsd_set_profiling(ctx, 1); tsd_stage_times synchronises and returns, per stage name, the time summed over those

@@ -52,6 +52,9 @@ _SIGNATURES = {
     "tsd_stream": (_vp, [_vp]),
     "tsd_synchronize": (_i, [_vp]),
     "tsd_launch_count": (_i64, [_vp]),
+    "tsd_host_register": (_i, [_vp, _i64]),
+    "tsd_stat_hist_entries": (_i, [_vp, C.POINTER(C.c_int64)]),
+    "tsd_host_unregister": (_i, [_vp]),
     "tsd_set_templates": (_i, [_vp, _vp, _vp]),
     "tsd_set_similarity_table": (_i, [_vp, _vp, _i]),
     "tsd_set_lda": (_i, [_vp, _vp, _vp, _i]),

@@ -82,6 +82,14 @@ class Context:
     def synchronize(self):
         check(self._L.tsd_synchronize(self._h))
 
+    def pin(self, array):
+        """Page-lock a caller-owned C-contiguous numpy array so that detect_frames reads it in place over PCIe
+        (only candidate ROIs are transferred).  Call unpin(array) before the array is freed."""
+        check(self._L.tsd_host_register(ptr(array), int(array.nbytes)))
+
+    def unpin(self, array):
+        check(self._L.tsd_host_unregister(ptr(array)))
+
     @property
     def launch_count(self):
         return int(self._L.tsd_launch_count(self._h))
@@ -260,6 +268,12 @@ class Context:
         det = np.zeros(max(int(cap), 1), DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)
         check(self._L.tsd_fetch_detections(self._h, ptr(det), len(det), C.byref(nd), ptr(counts)))
         return det[:nd.value].copy(), counts
+
+    def stat_hist_entries(self):
+        """Total non-zero histogram bins over the windows of the last enqueue_frames call (measurement helper)."""
+        t = C.c_int64()
+        check(self._L.tsd_stat_hist_entries(self._h, C.byref(t)))
+        return int(t.value)
 
     def set_profiling(self, on=True):
         check(self._L.tsd_set_profiling(self._h, int(bool(on))))

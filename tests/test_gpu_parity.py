@@ -256,6 +256,36 @@ def test_chain_properties_full_size(ctx_det, tsd):
     assert counts[0] == F * 200 and counts[0] >= counts[1] >= counts[2] >= counts[3]
 
 
+def test_host_paths_agree(tsd, templates, oracle, monkeypatch):
+    """tsd_detect_frames with host buffers: pageable frames (copied whole, in chunks that overlap the chain; 3 frames per
+    chunk here so several chunks and a ragged tail are exercised), page-locked frames (read in place over PCIe by K2) and
+    the device-resident path must give identical records, equal to the oracle's."""
+    red6, blue6 = templates
+    F = 10
+    frames = tsd.synth.make_frames(F)
+    boxes, off = tsd.synth.make_boxes(F, 200)
+    exp = []
+    for f in range(F):
+        o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    monkeypatch.setenv("TSD_CHUNK_FRAMES", "3")
+    with tsd.Context(0, "det") as ctx:
+        ctx.set_templates(red6, blue6)
+        d_pageable, c_pageable = ctx.detect_frames(frames, boxes, off)
+        pinned = np.ascontiguousarray(frames.copy())
+        ctx.pin(pinned)
+        try:
+            d_pinned, c_pinned = ctx.detect_frames(pinned, boxes, off)
+        finally:
+            ctx.unpin(pinned)
+    monkeypatch.setenv("TSD_ZEROCOPY", "0")
+    with tsd.Context(0, "det") as ctx:
+        ctx.set_templates(red6, blue6)
+        d_copy, c_copy = ctx.detect_frames(frames, boxes, off)
+    assert _records(d_pageable) == exp and _records(d_pinned) == exp and _records(d_copy) == exp
+    assert c_pageable.tolist() == c_pinned.tolist() == c_copy.tolist()
+
+
 # ---- recognition --------------------------------------------------------------------------------------------------------
 def test_k6_k7_k8_recognition_golden(ctx_rec, rec_golden, rec_frames, oracle):
     g = rec_golden
