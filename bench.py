@@ -265,8 +265,18 @@ def run_b200(args, rank, world, local_rank):
     ev1.record(stream)
     ctx.synchronize()
     barrier()
-    clocks = sampler.stop()
+    n_timed = len(sampler.samples)
     ms = ev0.elapsed_time(ev1)
+    # NVML answers in ~10-30 ms, so a short timed region yields few samples: keep sampling over an UNTIMED window of
+    # the same steps (>= 0.5 s of the same load) and report both counts
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.5:
+        for _ in range(4):
+            step()
+        ctx.synchronize()
+    clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = n_timed
+    clocks["note"] = "NVML, 10 ms period; samples span the timed region plus 0.5 s of the same steps run untimed right after it"
     launches = ctx.launch_count - l0
     stage_ms = dict(ctx.stage_times())
     ctx.set_profiling(False)
