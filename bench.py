@@ -252,10 +252,12 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, per-stage events inside ----------------
+    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream ----------------------------------------
+    # (a step splits its frames into chunks that alternate between two streams, so the latency-bound fold of one chunk
+    #  overlaps the throughput-bound kernels of the next; the per-kernel times for the roofline come from a second pass
+    #  of K steps, right after, with the chunks serialised and CUDA events between the stages)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
-    ctx.set_profiling(True)
     l0 = ctx.launch_count
     barrier()
     sampler.start()
@@ -267,6 +269,17 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     n_timed = len(sampler.samples)
     ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - l0
+    ctx.set_profiling(True)                                  # second pass: same K steps, serialised, per-stage CUDA events
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record(stream)
+    for _ in range(args.steps):
+        step()
+    evp1.record(stream)
+    ctx.synchronize()
+    stage_ms = dict(ctx.stage_times())
+    ms_serial = evp0.elapsed_time(evp1)
+    ctx.set_profiling(False)
     # NVML answers in ~10-30 ms, so a short timed region yields few samples: keep sampling over an UNTIMED window of
     # the same steps (>= 0.5 s of the same load) and report both counts
     t_load = time.perf_counter()
@@ -277,9 +290,6 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     clocks["samples_in_timed_region"] = n_timed
     clocks["note"] = "NVML, 10 ms period; samples span the timed region plus 0.5 s of the same steps run untimed right after it"
-    launches = ctx.launch_count - l0
-    stage_ms = dict(ctx.stage_times())
-    ctx.set_profiling(False)
     det, counts = ctx.fetch_detections(nb)
     hist_entries = ctx.stat_hist_entries()
     if dist is not None:
@@ -341,7 +351,7 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": traffic.get(dom, {}).get("dram_bytes_per_window", 0) * npass or None,
                          "traffic_source": traffic.get(dom, {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom, 0),
                          "kernel_ms_per_launch": per_stage.get(dom)},
-            "stages_ms_per_step": per_stage,
+            "stages_ms_per_step": per_stage, "ms_per_step_serialised": ms_serial / args.steps,
             "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in per_stage.items() if v > 0},
             "chain": {"algorithmic_bytes_per_step": fused_bytes, "gbs": fused_bytes / (ms / args.steps * 1e-3) / 1e9,
                       "frac_of_peak": fused_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},

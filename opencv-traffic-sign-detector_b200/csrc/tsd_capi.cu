@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,16 @@ struct DevBuf {
 struct tsd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t cur = nullptr;              // the stream kernels are launched on (== stream except inside a chunked enqueue)
+    cudaStream_t cs[2] = {nullptr, nullptr}; // chunk streams: consecutive chunks of a batch alternate, so the latency-bound fold
+                                             // of one chunk overlaps the throughput-bound kernels (and PCIe reads) of the next
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int stream_chunk = -1;                   // TSD_STREAM_CHUNK: frames per chunk (0 = auto, -1 = never chunk = default: measured slower,
+                                             // the fold's shared memory footprint keeps other kernels from co-residing)
+    struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; };
+    std::vector<ChunkInfo> chunks;           // of the last enqueue
+    DevBuf b_summary, b_order;
+    size_t order_off = 0;                   // offset (ints) of the current chunk inside b_order
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf b_stage[2], b_hboxes, b_hoff;
@@ -104,7 +115,7 @@ static void mark(tsd_ctx* c, const char* name) {
         c->ev_names.push_back("");
     }
     c->ev_names[c->ev_used] = name;
-    cudaEventRecord(c->ev[c->ev_used], c->stream);
+    cudaEventRecord(c->ev[c->ev_used], c->cur);
     c->ev_used++;
 }
 
@@ -157,6 +168,13 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     if (c->cfg.window < 2 || c->cfg.window > kMaxD) { delete c; return fail(TSD_E_INVALID, "window %d not in [2,%d]", c->cfg.window, kMaxD); }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->cur = c->stream;
+    for (int i = 0; i < 2; i++) {
+        CU(cudaStreamCreateWithFlags(&c->cs[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    { const char* e = getenv("TSD_STREAM_CHUNK"); if (e) c->stream_chunk = atoi(e); }
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
@@ -214,7 +232,9 @@ int tsd_destroy(tsd_ctx* c) {
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff};
+    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order};
+    for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (DevBuf* b : more) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -401,7 +421,7 @@ static HsvBounds bounds_of(const tsd_config& cfg) {
 // ---- device-pointer implementations --------------------------------------------------------------------------------
 static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, int32_t* coords, uint8_t* valid) {
     if (n == 0) return TSD_OK;
-    k1_expand_kernel<<<cdiv(n, 256), 256, 0, c->stream>>>((const int4*)boxes, n, enlarge - 1.0, c->cfg.aspect_lo, c->cfg.aspect_hi, (int4*)coords, valid);
+    k1_expand_kernel<<<cdiv(n, 256), 256, 0, c->cur>>>((const int4*)boxes, n, enlarge - 1.0, c->cfg.aspect_lo, c->cfg.aspect_hi, (int4*)coords, valid);
     return check_launch(c, "k1_expand");
 }
 
@@ -416,26 +436,26 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     const bool fast = c->k2_variant == 3 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
     const int gk = cdiv(n_max, kK2Warps);
     const bool v4 = c->k2_variant == 4 && ((uintptr_t)windows % 16 == 0);
-    if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 1 && D == 32) k2_crop_resize_v3_kernel<1, 32><<<gk, kK2Warps * 32, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 3 && D == 25) k2_crop_resize_v4_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->stream>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
-    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->stream>>>(K2_ARGS, D, windows, out_stride);
+    if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (fast && ch == 1 && D == 32) k2_crop_resize_v3_kernel<1, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 3 && D == 25) k2_crop_resize_v4_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
+    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
     return check_launch(c, "k2_crop_resize");
 }
 
 static int dev_scan(tsd_ctx* c, const int32_t* counts, int n, int32_t* offsets) {
-    scan_offsets_kernel<<<1, 1024, 0, c->stream>>>(counts, n, offsets);
+    scan_offsets_kernel<<<1, 1024, 0, c->cur>>>(counts, n, offsets);
     return check_launch(c, "scan_offsets");
 }
 
@@ -443,10 +463,10 @@ static int dev_scan(tsd_ctx* c, const int32_t* counts, int n, int32_t* offsets) 
 static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* box_offsets, int nframes, int H, int W, double enlarge,
                              int32_t* counts, int32_t* win_offsets, int32_t* coords, int32_t* win_frame) {
     const double pm1 = enlarge - 1.0;
-    k1_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, counts);
+    k1_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->cur>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, counts);
     TRY(check_launch(c, "k1_count"));
     TRY(dev_scan(c, counts, nframes, win_offsets));
-    k1_compact_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, win_offsets, (int4*)coords, win_frame);
+    k1_compact_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->cur>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, win_offsets, (int4*)coords, win_frame);
     return check_launch(c, "k1_compact");
 }
 
@@ -457,9 +477,9 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
     int grid = cdiv(n_max, kHistWarps);
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     if (npx <= 640)
-        k5_hist_kernel<640><<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<640><<<grid, kHistWarps * 32, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     else
-        k5_hist_kernel<1024><<<grid, kHistWarps * 32, 0, c->stream>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<1024><<<grid, kHistWarps * 32, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     return check_launch(c, "k5_hist");
 }
 
@@ -467,30 +487,40 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
 // windows (rows of the pair-class bit matrix).  max_n <= 1024: all-pairs classification (k5_pairs) + one warp per frame
 // (k5_fold_warp); larger frames: the general block-synchronous fold (k5_fold_kernel).
 template <int RMAX, int CAP>
-static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut) {
+static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost) {
     const int warps = RMAX <= 256 ? kFoldWarps : 2;
     const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<RMAX, CAP>);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int per_sm = 0;
+    if (!per_sm) {
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_fold_warp_kernel<RMAX, CAP>, warps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
     }
-    k5_fold_warp_kernel<RMAX, CAP><<<cdiv(nframes, warps), warps * 32, smem, c->stream>>>(P, nframes, M, RW, cut);
+    // longest-first frame order + work counter (context scratch: [nframes] order, [1] counter)
+    TRY(ensure(c, c->b_order, (c->order_off + nframes + 1) * 4));
+    int32_t* order = (int32_t*)c->b_order.p + c->order_off;
+    int32_t* counter = order + nframes;
+    k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter);
+    TRY(check_launch(c, "k5_order"));
+    int grid = cdiv(nframes, warps);
+    if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
+    k5_fold_warp_kernel<RMAX, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter);
     return check_launch(c, "k5_fold_warp");
 }
 
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, size_t ncap, const float* E_T, int64_t e_stride) {
+                    int max_n, size_t ncap, size_t m_row0, float* E_T, int64_t e_stride) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
     P.npx = npx; P.ws = ws; P.es = ent_stride(npx); P.do_hist = do_hist; P.do_coords = do_coords;
+    P.E_T = E_T; P.e_stride = e_stride;
     P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
     P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
     if (nframes == 0) return TSD_OK;
     if (max_n > 1024) {
-        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->stream>>>(P, nframes);
+        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes);
         return check_launch(c, "k5_fold");
     }
     const int RW = ((max_n > 1 ? max_n : 1) + 31) / 32;
@@ -504,22 +534,25 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         cut = lo_i > 0 ? lo_i : 1;
     }
     uint32_t* M = nullptr;
+    int32_t* cost = nullptr;
     if (do_hist) {
         static bool attr_done = false;
         if (!attr_done) {
             CU(cudaFuncSetAttribute(k5_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * kDenseLen * 2));
             attr_done = true;
         }
-        TRY(ensure(c, c->b_pairs, (ncap > 0 ? ncap : 1) * 2 * RW * sizeof(uint32_t)));
-        M = (uint32_t*)c->b_pairs.p;
+        TRY(ensure(c, c->b_pairs, (m_row0 + (ncap > 0 ? ncap : 1)) * 2 * RW * sizeof(uint32_t)));     // (already large enough inside a chunked enqueue)
+        M = (uint32_t*)c->b_pairs.p + m_row0 * 2 * RW;
+        cost = out_count;                                    // [nframes] scratch until the fold writes the survivor counts (order is built first)
+        CU(cudaMemsetAsync(cost, 0, (size_t)nframes * 4, c->cur));
         const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
-        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * kDenseLen * 2, c->stream>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles,
-                                                                                                     P.hist_tol, P.hist_lo, M);
+        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * kDenseLen * 2, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles,
+                                                                                                     P.hist_tol, P.hist_lo, M, cost);
         TRY(check_launch(c, "k5_pairs"));
         mark(c, "k5_pairs");
     }
-    if (max_n <= 256) return npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut);
-    return npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut);
+    if (max_n <= 256) return npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
+    return npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -620,7 +653,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     TRY(s.alloc(&doc, (size_t)n * 16));
     if (n) {
         if (by_coords) {
-            k5_hash_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dw, n, npx, ws, (WinMeta*)dmeta);
+            k5_hash_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->cur>>>((uint8_t*)dw, n, npx, ws, (WinMeta*)dmeta);
             TRY(check_launch(c, "k5_hash"));
         } else {
             TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, ws, (uint32_t*)dent, (WinMeta*)dmeta, (float*)den, n));
@@ -628,11 +661,12 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     }
     int max_n = 0;
     for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
+    c->order_off = 0;
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (size_t)n, (float*)den, n));
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (size_t)n, 0, (float*)den, n));
     TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
     if (nframes) {
-        k5_gather_kernel<<<nframes, 128, 0, c->stream>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
+        k5_gather_kernel<<<nframes, 128, 0, c->cur>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
                                                          (uint8_t*)dow, (int4*)doc, nullptr);
         TRY(check_launch(c, "k5_gather"));
     }
@@ -660,7 +694,7 @@ int tsd_hist(tsd_ctx* c, const uint8_t* windows, int n, int D, float* hist, int 
     TRY(s.alloc(&dent, (size_t)n * ent_stride(npx) * 4));
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
     TRY(dev_hist(c, (uint8_t*)dw, nullptr, n, npx, npx * 3, (uint32_t*)dent, (WinMeta*)dmeta, nullptr, 0));      // public layout: packed windows
-    hist_dense_kernel<<<n, 256, 0, c->stream>>>((uint32_t*)dent, (WinMeta*)dmeta, n, ent_stride(npx), (float*)dh);
+    hist_dense_kernel<<<n, 256, 0, c->cur>>>((uint32_t*)dent, (WinMeta*)dmeta, n, ent_stride(npx), (float*)dh);
     TRY(check_launch(c, "hist_dense"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(hist, dh, (size_t)n * kHistBins * 4)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -676,7 +710,7 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx)); }
     int grid = cdiv((int64_t)n * 32, 256);
     if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-    k3_masks_v2_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db,
+    k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db,
                                                     npx, nullptr);       // public layout: packed windows and masks
     TRY(check_launch(c, "k3_masks"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
@@ -692,7 +726,7 @@ int tsd_bgr2hsv(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* hsv, int m
     if (mem == TSD_MEM_HOST) { TRY(s.in(bgr, (size_t)npx * 3, &di)); TRY(s.alloc(&dout, (size_t)npx * 3)); }
     int grid = cdiv(npx, 256);
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
-    bgr2hsv_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, npx, c->d_tab, (uint8_t*)dout);
+    bgr2hsv_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)di, npx, c->d_tab, (uint8_t*)dout);
     TRY(check_launch(c, "bgr2hsv"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(hsv, dout, (size_t)npx * 3)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -713,7 +747,7 @@ int tsd_score_masks(tsd_ctx* c, const uint8_t* red, const uint8_t* blue, int n, 
         if (scores) TRY(s.alloc(&ds, (size_t)n * 12 * 4));
         TRY(s.alloc(&di, (size_t)n * 4)); TRY(s.alloc(&dh, (size_t)n * 4)); TRY(s.alloc(&de, (size_t)n));
     }
-    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, npx, c->d_tmpl,
+    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->cur>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, npx, c->d_tmpl,
                                                                         c->cfg.score_tol_hundredths, (int32_t*)ds, (int32_t*)di, (int32_t*)dh, (uint8_t*)de);
     TRY(check_launch(c, "k4_score"));
     if (mem == TSD_MEM_HOST) {
@@ -733,7 +767,7 @@ int tsd_bgr2gray(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* gray, int
     if (mem == TSD_MEM_HOST) { TRY(s.in(bgr, (size_t)npx * 3, &di)); TRY(s.alloc(&dout, (size_t)npx)); }
     int grid = cdiv(npx, 256);
     if (grid > c->sm_count * 32) grid = c->sm_count * 32;
-    k6_gray_kernel<<<grid, 256, 0, c->stream>>>((uint8_t*)di, nullptr, nullptr, 1, (int)npx, 0, (uint8_t*)dout);
+    k6_gray_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)di, nullptr, nullptr, 1, (int)npx, 0, (uint8_t*)dout);
     TRY(check_launch(c, "k6_gray"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(gray, dout, (size_t)npx)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -746,7 +780,7 @@ int tsd_hog(tsd_ctx* c, const uint8_t* gray, int n, float* desc, int mem) {
     Stage s(c);
     void *dg = (void*)gray, *dd = desc;
     if (mem == TSD_MEM_HOST) { TRY(s.in(gray, (size_t)n * 1024, &dg)); TRY(s.alloc(&dd, (size_t)n * TSD_HOG_LEN * 4)); }
-    k7_hog_kernel<<<cdiv(n, kHogWarps), kHogWarps * 32, 0, c->stream>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dd);
+    k7_hog_kernel<<<cdiv(n, kHogWarps), kHogWarps * 32, 0, c->cur>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dd);
     TRY(check_launch(c, "k7_hog"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(desc, dd, (size_t)n * TSD_HOG_LEN * 4)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -755,7 +789,7 @@ int tsd_hog(tsd_ctx* c, const uint8_t* gray, int n, float* desc, int mem) {
 static int dev_lda(tsd_ctx* c, const float* X, const int32_t* n_ptr, int n_max, double tol, double* logits, int32_t* labels) {
     int grid = cdiv((int64_t)n_max * 32, 256);
     if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-    k8_lda_kernel<<<grid, 256, (size_t)c->lda_nfeat * 6 * sizeof(double), c->stream>>>(X, n_ptr, n_max, c->lda_nfeat, c->d_ldaW, c->d_ldab, tol, logits, labels);
+    k8_lda_kernel<<<grid, 256, (size_t)c->lda_nfeat * 6 * sizeof(double), c->cur>>>(X, n_ptr, n_max, c->lda_nfeat, c->d_ldaW, c->d_ldab, tol, logits, labels);
     return check_launch(c, "k8_lda");
 }
 
@@ -792,7 +826,7 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
         if (Z) TRY(s.alloc(&dz, (size_t)n * 6 * 8));
         TRY(s.alloc(&dy, (size_t)n * 4));
     }
-    k8_knn_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->stream>>>((float*)dx, n, c->knn_nfeat, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt,
+    k8_knn_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->cur>>>((float*)dx, n, c->knn_nfeat, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt,
                                                                       c->knn_ntrain, c->knn_k, (double*)dz, (int32_t*)dy);
     TRY(check_launch(c, "k8_knn"));
     if (mem == TSD_MEM_HOST) {
@@ -804,29 +838,134 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 }
 
 // ---- whole chain -------------------------------------------------------------------------------------------------
+// One chunk of frames through the whole chain on c->cur.  wo = first window slot of the chunk in the per-window scratch,
+// fo = first entry of the chunk in the per-frame scratch arrays (cf + 1 entries), nbcap = upper bound of the chunk's boxes.
+static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, int H, int W, int64_t row_stride, int64_t frame_stride,
+                         const int32_t* d_boxes, const int32_t* d_box_offsets, int nbcap, int maxb, size_t wo, int fo, int chunk_index) {
+    const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
+    const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
+    const int nb = nbcap;
+    const size_t cap = nbcap > 0 ? nbcap : 1;
+    int32_t *cnt = (int32_t*)c->b_cnt.p + fo, *winoff = (int32_t*)c->b_winoff.p + fo, *survcnt = (int32_t*)c->b_survcnt.p + fo, *survoff = (int32_t*)c->b_survoff.p + fo;
+    int32_t *detcnt = (int32_t*)c->b_detcnt.p + fo, *detoff = (int32_t*)c->b_detoff.p + fo;
+    int32_t* coords = (int32_t*)c->b_coords.p + wo * 4;
+    int32_t* winframe = (int32_t*)c->b_winframe.p + wo;
+    uint8_t* windows = (uint8_t*)c->b_windows.p + wo * ws;
+    uint32_t* entries = (uint32_t*)c->b_entries.p + wo * es;
+    WinMeta* meta = (WinMeta*)c->b_meta.p + wo;
+    float* energy = (float*)c->b_energy.p + wo * kHistGroups;          // [25][cap] block of this chunk
+    int32_t *list = (int32_t*)c->b_list.p + wo, *slots = (int32_t*)c->b_slots.p + wo, *id = (int32_t*)c->b_id.p + wo, *hund = (int32_t*)c->b_hund.p + wo;
+    uint8_t *flags = (uint8_t*)c->b_flags.p + wo, *emit = (uint8_t*)c->b_emit.p + wo;
+    DetRec* det = (DetRec*)c->b_det.p + wo;
+    c->order_off = (size_t)fo;
+    mark(c, "start");
+    // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
+    TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
+    mark(c, "k1_expand_filter");
+    const int32_t* d_nwin = winoff + cf;
+    // K2 (DET:123-124)
+    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
+    mark(c, "k2_crop_resize");
+    // K5 (DET:127-129)
+    TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
+    mark(c, "k5_hist");
+    TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
+                 list, flags, survcnt, maxb, cap, wo, energy, (int64_t)cap));
+    TRY(dev_scan(c, survcnt, cf, survoff));
+    k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
+    TRY(check_launch(c, "k5_gather"));
+    mark(c, "k5_fold");
+    const int32_t* d_nsurv = survoff + cf;
+    if (mode == TSD_RUN_DETECT) {
+        // K3 + K4 (DET:708-716)
+        uint8_t *red = (uint8_t*)c->b_red.p + wo * ms, *blue = (uint8_t*)c->b_blue.p + wo * ms;
+        uint32_t* bits = (uint32_t*)c->b_bits.p + wo * 2 * NW;
+        int grid = cdiv((int64_t)cap * 32, 256);
+        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
+        TRY(check_launch(c, "k3_masks"));
+        mark(c, "k3_masks");
+        if (NW == 20)
+            k4_score_bits_kernel<20><<<cdiv(cap, 128), 128, 0, c->cur>>>(bits, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths, id, hund, emit);
+        else if (NW == 32)
+            k4_score_bits_kernel<32><<<cdiv(cap, 128), 128, 0, c->cur>>>(bits, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths, id, hund, emit);
+        else
+            k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->cur>>>(red, blue, d_nsurv, nb, npx, ms, c->d_tmpl, c->cfg.score_tol_hundredths, nullptr, id, hund, emit);
+        TRY(check_launch(c, "k4_score"));
+        mark(c, "k4_score");
+    } else {
+        uint8_t* gray = (uint8_t*)c->b_gray.p + wo * npx;
+        float* hog = (float*)c->b_hog.p + wo * TSD_HOG_LEN;
+        int grid = cdiv((int64_t)cap * npx, 256);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        k6_gray_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, gray);
+        TRY(check_launch(c, "k6_gray"));
+        mark(c, "k6_gray");
+        k7_hog_kernel<<<cdiv(cap, kHogWarps), kHogWarps * 32, 0, c->cur>>>(gray, d_nsurv, nb, c->hog, hog);
+        TRY(check_launch(c, "k7_hog"));
+        mark(c, "k7_hog");
+        TRY(dev_lda(c, hog, d_nsurv, nb, c->cfg.proba_tol, nullptr, id));
+        mark(c, "k8_lda");
+        // a survivor becomes a record when the classifier says "sign" (label != 0); no score in this flavour
+        CU(cudaMemsetAsync(hund, 0, cap * 4, c->cur));
+        label_emit_kernel<<<cdiv(cap, 256), 256, 0, c->cur>>>(id, d_nsurv, nb, emit);
+        TRY(check_launch(c, "label_emit"));
+    }
+    det_count_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, survoff, cf, detcnt);
+    TRY(check_launch(c, "det_count"));
+    TRY(dev_scan(c, detcnt, cf, detoff));
+    det_write_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, id, hund, (int4*)coords, slots, survoff, detoff, cf, (int)cap, det,
+                                                                        winoff + cf, survoff + cf, (int32_t*)c->b_summary.p + 4 * chunk_index);
+    TRY(check_launch(c, "det_write"));
+    mark(c, "detections");
+    return TSD_OK;
+}
+
 int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
                        const int32_t* d_boxes, const int32_t* d_box_offsets, int nb, int max_boxes_per_frame) {
     if (!c || !d_frames || !d_box_offsets || nframes < 1 || nb < 0 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
     if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
     if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
-    const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
-    const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
+    const int D = c->cfg.window, npx = D * D, ws = win_stride(npx, 3), es = ent_stride(npx);
+    const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;
     if (mode == TSD_RUN_DETECT && (!c->have_templates || c->tmpl_D != D)) return fail(TSD_E_STATE, "templates not set for D=%d", D);
     if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
     CU(cudaSetDevice(c->device));
-    const size_t cap = nb > 0 ? nb : 1;
+    // ---- chunking: consecutive chunks alternate between two streams ------------------------------------------------
+    int CFr = nframes;
+    if (!c->profiling && c->stream_chunk >= 0) {
+        CFr = c->stream_chunk > 0 ? c->stream_chunk : (nframes + 7) / 8;
+        if (c->stream_chunk == 0 && CFr < 256) CFr = 256;
+        if (CFr > nframes) CFr = nframes;
+    }
+    const int nchunks = (nframes + CFr - 1) / CFr;
+    std::vector<int32_t> ho;
     if (max_boxes_per_frame <= 0) {                          // not given: one small D2H of the CSR offsets (synchronises)
-        std::vector<int32_t> ho(nframes + 1);
+        ho.resize(nframes + 1);
         CU(cudaMemcpyAsync(ho.data(), d_box_offsets, (size_t)(nframes + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         for (int f = 0; f < nframes; f++) max_boxes_per_frame = ho[f + 1] - ho[f] > max_boxes_per_frame ? ho[f + 1] - ho[f] : max_boxes_per_frame;
     }
-    TRY(ensure(c, c->b_cnt, (size_t)(nframes + 1) * 4));
-    TRY(ensure(c, c->b_winoff, (size_t)(nframes + 1) * 4));
-    TRY(ensure(c, c->b_survcnt, (size_t)(nframes + 1) * 4));
-    TRY(ensure(c, c->b_survoff, (size_t)(nframes + 1) * 4));
-    TRY(ensure(c, c->b_detcnt, (size_t)(nframes + 1) * 4));
-    TRY(ensure(c, c->b_detoff, (size_t)(nframes + 1) * 4));
+    c->chunks.clear();
+    size_t wtot = 0;
+    for (int k = 0; k < nchunks; k++) {
+        tsd_ctx::ChunkInfo ci;
+        ci.f0 = k * CFr; ci.cf = nframes - ci.f0 < CFr ? nframes - ci.f0 : CFr;
+        // boxes of the chunk: exact when the offsets are on the host, else bounded by cf * max_boxes_per_frame (and by nb)
+        ci.nbcap = !ho.empty() ? ho[ci.f0 + ci.cf] - ho[ci.f0] : (nchunks == 1 ? nb : (int)std::min<int64_t>((int64_t)ci.cf * max_boxes_per_frame, nb));
+        ci.wo = wtot; ci.fo = ci.f0 + k;
+        wtot += (size_t)((ci.nbcap > 0 ? ci.nbcap : 1) + 3) & ~(size_t)3;     // keeps every chunk's slices 16-byte aligned
+        c->chunks.push_back(ci);
+    }
+    const size_t cap = wtot, fcap = (size_t)nframes + nchunks;
+    TRY(ensure(c, c->b_cnt, fcap * 4));
+    TRY(ensure(c, c->b_winoff, fcap * 4));
+    TRY(ensure(c, c->b_survcnt, fcap * 4));
+    TRY(ensure(c, c->b_survoff, fcap * 4));
+    TRY(ensure(c, c->b_detcnt, fcap * 4));
+    TRY(ensure(c, c->b_detoff, fcap * 4));
+    TRY(ensure(c, c->b_summary, (size_t)nchunks * 16));
+    TRY(ensure(c, c->b_order, fcap * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));
     TRY(ensure(c, c->b_windows, cap * ws));
@@ -848,70 +987,29 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(ensure(c, c->b_gray, cap * npx));
         TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
     }
-    int32_t *cnt = (int32_t*)c->b_cnt.p, *winoff = (int32_t*)c->b_winoff.p, *survcnt = (int32_t*)c->b_survcnt.p, *survoff = (int32_t*)c->b_survoff.p;
-    int32_t *detcnt = (int32_t*)c->b_detcnt.p, *detoff = (int32_t*)c->b_detoff.p;
-    int32_t* coords = (int32_t*)c->b_coords.p;
-    uint8_t* windows = (uint8_t*)c->b_windows.p;
-    mark(c, "start");
-    // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
-    TRY(dev_windows_index(c, d_boxes, d_box_offsets, nframes, H, W, c->cfg.enlarge, cnt, winoff, coords, (int32_t*)c->b_winframe.p));
-    mark(c, "k1_expand_filter");
-    const int32_t* d_nwin = winoff + nframes;
-    // K2 (DET:123-124)
-    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, (int32_t*)c->b_winframe.p, d_nwin, nb, D, windows, ws));
-    mark(c, "k2_crop_resize");
-    // K5 (DET:127-129)
-    TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, (float*)c->b_energy.p, (int64_t)cap));
-    mark(c, "k5_hist");
-    TRY(dev_fold(c, windows, ws, coords, (uint32_t*)c->b_entries.p, (WinMeta*)c->b_meta.p, winoff, nframes, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 (int32_t*)c->b_list.p, (uint8_t*)c->b_flags.p, survcnt, max_boxes_per_frame, cap, (float*)c->b_energy.p, (int64_t)cap));
-    TRY(dev_scan(c, survcnt, nframes, survoff));
-    k5_gather_kernel<<<nframes, 32, 0, c->stream>>>(windows, (int4*)coords, winoff, (int32_t*)c->b_list.p, survoff, nframes, nbytes, ws, nullptr, nullptr, (int32_t*)c->b_slots.p);
-    TRY(check_launch(c, "k5_gather"));
-    mark(c, "k5_fold");
-    const int32_t* d_nsurv = survoff + nframes;
-    if (mode == TSD_RUN_DETECT) {
-        // K3 + K4 (DET:708-716)
-        int grid = cdiv((int64_t)cap * 32, 256);
-        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-        k3_masks_v2_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), (uint8_t*)c->b_red.p,
-                                                        (uint8_t*)c->b_blue.p, ms, (uint32_t*)c->b_bits.p);
-        TRY(check_launch(c, "k3_masks"));
-        mark(c, "k3_masks");
-        if (NW == 20)
-            k4_score_bits_kernel<20><<<cdiv(cap, 128), 128, 0, c->stream>>>((uint32_t*)c->b_bits.p, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths,
-                                                                             (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
-        else if (NW == 32)
-            k4_score_bits_kernel<32><<<cdiv(cap, 128), 128, 0, c->stream>>>((uint32_t*)c->b_bits.p, d_nsurv, nb, c->d_tmpl, c->cfg.score_tol_hundredths,
-                                                                             (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
-        else
-            k4_score_kernel<<<cdiv((int64_t)cap * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_red.p, (uint8_t*)c->b_blue.p, d_nsurv, nb, npx, ms, c->d_tmpl,
-                                                                                 c->cfg.score_tol_hundredths, nullptr, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (uint8_t*)c->b_emit.p);
-        TRY(check_launch(c, "k4_score"));
-        mark(c, "k4_score");
-    } else {
-        int grid = cdiv((int64_t)cap * npx, 256);
-        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k6_gray_kernel<<<grid, 256, 0, c->stream>>>(windows, (int32_t*)c->b_slots.p, d_nsurv, nb, npx, ws, (uint8_t*)c->b_gray.p);
-        TRY(check_launch(c, "k6_gray"));
-        mark(c, "k6_gray");
-        k7_hog_kernel<<<cdiv(cap, kHogWarps), kHogWarps * 32, 0, c->stream>>>((uint8_t*)c->b_gray.p, d_nsurv, nb, c->hog, (float*)c->b_hog.p);
-        TRY(check_launch(c, "k7_hog"));
-        mark(c, "k7_hog");
-        TRY(dev_lda(c, (float*)c->b_hog.p, d_nsurv, nb, c->cfg.proba_tol, nullptr, (int32_t*)c->b_id.p));
-        mark(c, "k8_lda");
-        // a survivor becomes a record when the classifier says "sign" (label != 0); no score in this flavour
-        CU(cudaMemsetAsync(c->b_hund.p, 0, cap * 4, c->stream));
-        label_emit_kernel<<<cdiv(cap, 256), 256, 0, c->stream>>>((int32_t*)c->b_id.p, d_nsurv, nb, (uint8_t*)c->b_emit.p);
-        TRY(check_launch(c, "label_emit"));
+    {   // the pair-class bit rows are sized here (not inside dev_fold) so that no chunk can trigger a reallocation
+        const int RW = ((max_boxes_per_frame > 1 ? max_boxes_per_frame : 1) + 31) / 32;
+        if (max_boxes_per_frame <= 1024) TRY(ensure(c, c->b_pairs, cap * 2 * RW * sizeof(uint32_t)));
     }
-    det_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_emit.p, survoff, nframes, detcnt);
-    TRY(check_launch(c, "det_count"));
-    TRY(dev_scan(c, detcnt, nframes, detoff));
-    det_write_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->stream>>>((uint8_t*)c->b_emit.p, (int32_t*)c->b_id.p, (int32_t*)c->b_hund.p, (int4*)coords,
-                                                                               (int32_t*)c->b_slots.p, survoff, detoff, nframes, (int)cap, (DetRec*)c->b_det.p);
-    TRY(check_launch(c, "det_write"));
-    mark(c, "detections");
+    int rc = TSD_OK;
+    if (nchunks == 1) {
+        c->cur = c->stream;
+        rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, c->chunks[0].nbcap, max_boxes_per_frame, 0, 0, 0);
+    } else {
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(c->cs[i], c->ev_fork, 0));
+        for (int k = 0; k < nchunks && rc == TSD_OK; k++) {
+            const tsd_ctx::ChunkInfo& ci = c->chunks[k];
+            c->cur = c->cs[k & 1];
+            // offsets stay absolute (the kernels index `d_boxes` with them), so the box base pointer is not advanced
+            rc = enqueue_chain(c, mode, d_frames + (size_t)ci.f0 * frame_stride, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0,
+                               ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k);
+        }
+        c->cur = c->stream;
+        for (int i = 0; i < 2; i++) { CU(cudaEventRecord(c->ev_join[i], c->cs[i])); CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0)); }
+    }
+    c->cur = c->stream;
+    if (rc != TSD_OK) return rc;
     c->last_nframes = nframes; c->last_mode = mode; c->last_nboxes = nb; c->last_detcap = (int)cap;
     return TSD_OK;
 }
@@ -933,7 +1031,8 @@ int tsd_stat_hist_entries(tsd_ctx* c, int64_t* total) {
     unsigned long long* d = nullptr;
     CU(cudaMallocAsync((void**)&d, 8, c->stream));
     CU(cudaMemsetAsync(d, 0, 8, c->stream));
-    sum_nnz_kernel<<<64, 256, 0, c->stream>>>((const WinMeta*)c->b_meta.p, (const int32_t*)c->b_winoff.p + c->last_nframes, d);
+    for (const tsd_ctx::ChunkInfo& ci : c->chunks)
+        sum_nnz_kernel<<<64, 256, 0, c->stream>>>((const WinMeta*)c->b_meta.p + ci.wo, (const int32_t*)c->b_winoff.p + ci.fo + ci.cf, d);
     unsigned long long h = 0;
     CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaFreeAsync(d, c->stream));
@@ -946,20 +1045,31 @@ int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* n
     if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
     if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
     CU(cudaSetDevice(c->device));
-    const int F = c->last_nframes;
-    int32_t h[3];
-    CU(cudaMemcpyAsync(&h[0], (int32_t*)c->b_winoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&h[1], (int32_t*)c->b_survoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&h[2], (int32_t*)c->b_detoff.p + F, 4, cudaMemcpyDeviceToHost, c->stream));
+    static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
+    const int nchunks = (int)c->chunks.size();
+    std::vector<int32_t> h((size_t)nchunks * 4);
+    CU(cudaMemcpyAsync(h.data(), c->b_summary.p, (size_t)nchunks * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (counts) { counts[0] = c->last_nboxes; counts[1] = h[0]; counts[2] = h[1]; counts[3] = h[2]; }
-    *ndet = h[2];
-    if (h[2] > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, h[2]);
-    if (h[2]) {
+    int64_t tw = 0, ts = 0, td = 0;
+    for (int k = 0; k < nchunks; k++) { tw += h[4 * k]; ts += h[4 * k + 1]; td += h[4 * k + 2]; }
+    if (counts) { counts[0] = c->last_nboxes; counts[1] = (int32_t)tw; counts[2] = (int32_t)ts; counts[3] = (int32_t)td; }
+    *ndet = (int32_t)td;
+    if (td > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, (int)td);
+    if (td) {
         if (!det) return fail(TSD_E_INVALID, "det is NULL");
-        static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
-        CU(cudaMemcpyAsync(det, c->b_det.p, (size_t)h[2] * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
+        int o = 0;
+        for (int k = 0; k < nchunks; k++) {
+            const int n = h[4 * k + 2];
+            if (n) CU(cudaMemcpyAsync(det + o, (DetRec*)c->b_det.p + c->chunks[k].wo, (size_t)n * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
+            o += n;
+        }
         CU(cudaStreamSynchronize(c->stream));
+        o = 0;
+        for (int k = 0; k < nchunks; k++) {                  // records carry chunk-local frame indices
+            const int n = h[4 * k + 2], f0 = c->chunks[k].f0;
+            if (f0) for (int i = 0; i < n; i++) det[o + i].frame += f0;
+            o += n;
+        }
     }
     return TSD_OK;
 }

@@ -221,7 +221,8 @@ __device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_
 __global__ void __launch_bounds__(kPairWarps * 32) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
                                                                    const float* __restrict__ E_T, int64_t e_stride,
                                                                    const int32_t* __restrict__ offsets, int nframes, int es, int RW,
-                                                                   int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M) {
+                                                                   int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M,
+                                                                   int32_t* __restrict__ frame_cost) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x / tiles_per_frame, tile = blockIdx.x - f * tiles_per_frame;
     if (f >= nframes) return;
@@ -300,7 +301,35 @@ __global__ void __launch_bounds__(kPairWarps * 32) k5_pairs_kernel(const uint32_
             if (lane == k) c = classify(correl_from(s12, mj.s1, mj.A, mi.s1, mi.A), tol, lo);
         }
         const unsigned bd = __ballot_sync(0xffffffffu, valid && c == 1), bm = __ballot_sync(0xffffffffu, valid && c == 2);
-        if (lane == 0) { Mrow[i0 >> 5] = bd; Mrow[RW + (i0 >> 5)] = bm; }
+        if (lane == 0) {
+            Mrow[i0 >> 5] = bd; Mrow[RW + (i0 >> 5)] = bm;
+            if (bm && frame_cost) atomicAdd(frame_cost + f, __popc(bm));     // merge-band pairs: the fold's cost predictor
+        }
+    }
+}
+
+// Longest-processing-time-first order of the frames for the fold: key = 32 * (merge-band pairs) + windows, counting sort,
+// descending.  One CTA.  Also resets the fold's work counter.
+__global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restrict__ frame_cost, const int32_t* __restrict__ offsets, int nframes,
+                                                        int32_t* __restrict__ order, int32_t* __restrict__ counter) {
+    constexpr int NB = 2048;
+    __shared__ int32_t hist[NB];
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+        const int key = min(NB - 1, 32 * (frame_cost ? frame_cost[f] : 0) + (offsets[f + 1] - offsets[f]));
+        atomicAdd(&hist[NB - 1 - key], 1);                   // bucket 0 = heaviest
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                  // exclusive prefix over 2048 buckets (tiny)
+        int run = 0;
+        for (int i = 0; i < NB; i++) { const int c = hist[i]; hist[i] = run; run += c; }
+        *counter = 0;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+        const int key = min(NB - 1, 32 * (frame_cost ? frame_cost[f] : 0) + (offsets[f + 1] - offsets[f]));
+        order[atomicAdd(&hist[NB - 1 - key], 1)] = f;
     }
 }
 
@@ -314,6 +343,9 @@ struct FoldWarpSmem {
     int4 coords[RMAX];           // current coords of every item (merged coords are written here and to global)
     uint32_t hash[RMAX];         // current pixel hash of every item
     uint16_t dense[kDenseLen];   // dense counts of the item being merged
+    float eg[32];                // its group energies (Cauchy-Schwarz pruning, as in k5_pairs)
+    uint32_t rowd[32], rowm[32]; // class bits of the merged item against up to 1024 others (delete / merge), by word
+    uint16_t cand[RMAX];         // compacted list of the others that survive the pruning
     HistScratch<CAP> hs;
 };
 
@@ -348,6 +380,7 @@ __device__ __forceinline__ uint32_t avg_rne4(uint32_t a, uint32_t b) {
 }
 
 // item[slot_i] = avg(item[slot_i], item[slot_k]) in place, whole padded window (pad bytes stay 0); returns the new pixel hash
+template <bool HASH>
 __device__ __forceinline__ uint32_t merge_pixels_warp(uint8_t* ipx, const uint8_t* kpx, int ws, int npx) {
     const int lane = threadIdx.x & 31;
     uint4* a4 = reinterpret_cast<uint4*>(ipx);
@@ -359,9 +392,56 @@ __device__ __forceinline__ uint32_t merge_pixels_warp(uint8_t* ipx, const uint8_
         a4[i] = a;
     }
     __syncwarp();
+    if (!HASH) return 0;                                     // pass 1 gets the hash from the histogram rebuild
     uint32_t hsh = 0;
     for (int p = lane; p < npx; p += 32) hsh += pix_hash32(p, (uint32_t)(ipx[3 * p] | (ipx[3 * p + 1] << 8) | (ipx[3 * p + 2] << 16)));
     return warp_sum_u(hsh);
+}
+
+// Classes of the merged item (dense histogram in sm.dense, meta mj, energies sm.eg) against the items whose bits are set in
+// cmask (lane w = items 32w..32w+31), words [w0, w1].  Three steps: (1) lane-parallel Cauchy-Schwarz pruning, 32 items at a
+// time (class 0 without touching their histograms), survivors are compacted into sm.cand; (2) lane-parallel exact
+// classification of the compact list; (3) results as bit words in sm.rowd / sm.rowm.
+template <int RMAX, int CAP>
+__device__ __forceinline__ void fold_classify_against(FoldWarpSmem<RMAX, CAP>& sm, const FoldParams& P, const WinMeta& mj, int base, unsigned cmask,
+                                                      int w0, int w1) {
+    const int lane = threadIdx.x & 31;
+    sm.rowd[lane] = 0; sm.rowm[lane] = 0;
+    __syncwarp();
+    int ncand = 0;
+    for (int t = w0; t <= w1; t++) {
+        const unsigned aw = __shfl_sync(0xffffffffu, cmask, t);
+        if (!aw) continue;
+        const bool mine = (aw >> lane) & 1u;
+        const int q = base + 32 * t + lane;
+        int c = 0;
+        bool need = false;
+        if (mine) {
+            float ub = 0.f;
+#pragma unroll
+            for (int g = 0; g < kHistGroups; g++) ub += sm.eg[g] * P.E_T[(int64_t)g * P.e_stride + q];
+            const WinMeta mq = load_meta_cg(P.meta + q);
+            const double den2 = mj.A * mq.A;
+            if (!(fabs(den2) > DBL_EPSILON)) c = classify(1.0, P.hist_tol, P.hist_lo);      // compareHist's degenerate branch
+            else need = !prunable(ub, mj, mq.s1, mq.A, mq.rA, P.hist_lo);
+        }
+        const unsigned nb = __ballot_sync(0xffffffffu, need);
+        if (need) sm.cand[ncand + __popc(nb & ((1u << lane) - 1))] = (uint16_t)(32 * t + lane);
+        ncand += __popc(nb);
+        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bm = __ballot_sync(0xffffffffu, c == 2);
+        if (lane == 0) { sm.rowd[t] = bd; sm.rowm[t] = bm; }
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < ncand; r0 += 32) {
+        if (r0 + lane < ncand) {
+            const int ql = sm.cand[r0 + lane], q = base + ql;
+            const WinMeta mq = load_meta_cg(P.meta + q);
+            const int c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)q * P.es, mq, P.hist_tol, P.hist_lo);
+            if (c == 1) atomicOr(&sm.rowd[ql >> 5], 1u << (ql & 31));
+            else if (c == 2) atomicOr(&sm.rowm[ql >> 5], 1u << (ql & 31));
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ bool pixels_equal_warp(const uint8_t* a, const uint8_t* b, int ws) {
@@ -411,8 +491,8 @@ __device__ __forceinline__ unsigned fold_apply_deletions(unsigned A, unsigned D,
 }
 
 template <int RMAX, int CAP>
-__global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut) {
-    const int nwarp = blockDim.x >> 5;
+__global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
+                                                                       const int32_t* __restrict__ order, int32_t* counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HsvLut& lut = *reinterpret_cast<HsvLut*>(smem_raw);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -421,7 +501,14 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
     for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.dense)[b] = 0;
     __syncthreads();
     const int ws = P.ws, es = P.es;
-    for (int f = blockIdx.x * nwarp + wid; f < nframes; f += gridDim.x * nwarp) {
+    // persistent warps pull frames from a shared counter in longest-first order (k5_order_kernel): the heavy frames (many
+    // merges) start first and the light ones fill in behind them
+    while (true) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= nframes) break;
+        const int f = order[idx];
         const int base = P.offsets[f], n = P.offsets[f + 1] - base;
         if (n > RMAX || n > RW * 32) { if (lane == 0) P.out_count[f] = -1; continue; }    // host picks RMAX / RW large enough
         for (int p = lane; p < n; p += 32) { sm.coords[p] = P.coords[base + p]; sm.hash[p] = P.meta[base + p].hash; }
@@ -459,45 +546,42 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
                         for (int r = lane; r < mj.nnz; r += 32) sm.dense[sm.hs.binof[r]] = 0;
                         __syncwarp();
                     }
-                    const uint32_t hsh = merge_pixels_warp(ipx, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                    merge_pixels_warp<false>(ipx, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
                     const int4 kc = sm.coords[fm];
                     ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);   // Python // (coords >= 0)
                     __syncwarp();
-                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, lut, sm.hs, ient, P.meta + slot, nullptr, 0);
+                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, lut, sm.hs, ient, P.meta + slot, sm.eg, 1);
                     for (int r = lane; r < nnz; r += 32) sm.dense[sm.hs.binof[r]] = (uint16_t)sm.hs.cnt[r];
-                    if (lane == 0) sm.hash[j] = hsh;
                     __syncwarp();
                     mj = load_meta_cg(P.meta + slot);
+                    if (lane == 0) sm.hash[j] = mj.hash;     // the rebuild hashes the new pixels
+                    if (lane < kHistGroups) P.E_T[(int64_t)lane * P.e_stride + slot] = sm.eg[lane];   // later merges prune against the NEW histogram
                     // re-classify the updated item against the survivors after the merge position
                     scan = lane < L ? 0u : (lane == L ? (bit == 31 ? 0u : ~((2u << bit) - 1)) : 0xffffffffu);
-                    const unsigned arem = A & scan;
-                    for (int t = L; t <= ((j - 1) >> 5); t++) {
-                        const unsigned aw = __shfl_sync(0xffffffffu, arem, t);
-                        if (!aw) continue;
-                        int c = 0;
-                        if ((aw >> lane) & 1u) {
-                            const int q = base + 32 * t + lane;
-                            const WinMeta mq = load_meta_cg(P.meta + q);
-                            c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)q * es, mq, P.hist_tol, P.hist_lo);
-                        }
-                        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
-                        if (lane == t) { vd = bd; vm = bmm; }
-                    }
+                    fold_classify_against<RMAX, CAP>(sm, P, mj, base, A & scan, L, (j - 1) >> 5);
+                    if (lane >= L && lane <= ((j - 1) >> 5)) { vd = sm.rowd[lane]; vm = sm.rowm[lane]; }
+                    __syncwarp();
                     dirty = true;
                 }
                 if (dirty) {
                     if (lane == 0) { sm.coords[j] = ic; P.coords[slot] = ic; }
                     // the item is final: its class against every LATER item (their bit rows described the un-merged histogram)
                     const unsigned bitj = 1u << (j & 31);
-                    for (int t = j >> 5; t < nwords; t++) {
-                        const int q2 = 32 * t + lane;
-                        if (q2 > j && q2 < n) {
-                            const WinMeta mq = load_meta_cg(P.meta + base + q2);
-                            const int c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)(base + q2) * es, mq, P.hist_tol, P.hist_lo);
-                            uint32_t* r = M + (int64_t)(base + q2) * 2 * RW + (j >> 5);
-                            const uint32_t od = __ldcg(r), om = __ldcg(r + RW);
-                            r[0] = (od & ~bitj) | (c == 1 ? bitj : 0u);
-                            r[RW] = (om & ~bitj) | (c == 2 ? bitj : 0u);
+                    {
+                        unsigned later = 0;                  // items after j: lane w covers 32w..32w+31
+                        if (lane >= (j >> 5) && lane < nwords) {
+                            later = 0xffffffffu;
+                            if (lane == (j >> 5)) later = (j & 31) == 31 ? 0u : ~((2u << (j & 31)) - 1);
+                            if (lane == nwords - 1 && (n & 31)) later &= (1u << (n & 31)) - 1;
+                        }
+                        fold_classify_against<RMAX, CAP>(sm, P, mj, base, later, j >> 5, nwords - 1);
+                        for (int t = j >> 5; t < nwords; t++) {
+                            const int q2 = 32 * t + lane;
+                            if (q2 > j && q2 < n) {
+                                uint32_t* r = M + (int64_t)(base + q2) * 2 * RW + (j >> 5);
+                                r[0] = (r[0] & ~bitj) | (((sm.rowd[t] >> lane) & 1u) ? bitj : 0u);      // (this warp is the only writer of the frame's rows)
+                                r[RW] = (r[RW] & ~bitj) | (((sm.rowm[t] >> lane) & 1u) ? bitj : 0u);
+                            }
                         }
                     }
                     __syncwarp();
@@ -536,7 +620,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
                         // ---- merge (DET:217-221): pixels, coords; later comparisons use the updated item ----
                         const int bit = __ffs(bmm) - 1, fm = 32 * t + bit;
                         if (lane == t) D |= (bd & ((1u << bit) - 1)) | (1u << bit);
-                        const uint32_t hsh = merge_pixels_warp(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                        const uint32_t hsh = merge_pixels_warp<true>(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
                         const int4 kc = sm.coords[fm];
                         ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);
                         if (lane == 0) sm.hash[j] = hsh;

@@ -883,6 +883,8 @@ struct FoldParams {
     int simtab_n;
     const Tables* tab;
     int npx, ws, es;             // pixels per window; window stride (bytes); entry stride (words)
+    float* E_T;                  // group energies [25][e_stride] of the windows (pruning bound; rewritten for merged items), NULL when !do_hist
+    int64_t e_stride;
     int do_hist, do_coords;      // which passes to run (DET:127 then DET:129)
     double hist_tol, hist_lo, coord_tol, coord_lo;   // lo = tol * 0.8823 (DET:217), computed on the host in f64
 };
@@ -1381,8 +1383,12 @@ __global__ void det_count_kernel(const uint8_t* __restrict__ emit, const int32_t
 __global__ void det_write_kernel(const uint8_t* __restrict__ emit, const int32_t* __restrict__ id, const int32_t* __restrict__ hundredths,
                                  const int4* __restrict__ coords, const int32_t* __restrict__ slots,
                                  const int32_t* __restrict__ surv_offsets, const int32_t* __restrict__ det_offsets, int nframes,
-                                 int det_cap, DetRec* __restrict__ out) {
+                                 int det_cap, DetRec* __restrict__ out, const int32_t* __restrict__ nwin_ptr, const int32_t* __restrict__ nsurv_ptr,
+                                 int32_t* __restrict__ summary) {
     int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f == 0 && lane == 0 && summary) {                   // {windows, survivors, detections, 0} of this chunk, fetched in one copy
+        summary[0] = *nwin_ptr; summary[1] = *nsurv_ptr; summary[2] = det_offsets[nframes]; summary[3] = 0;
+    }
     if (f >= nframes) return;
     int o = det_offsets[f];
     for (int base = surv_offsets[f]; base < surv_offsets[f + 1]; base += 32) {

@@ -218,9 +218,9 @@ def test_chain_golden_frames(ctx_det, det_frames, frames3):
 
 
 def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
-    """BASELINE config 3 shape (1360x800, 200 candidates/frame) on 12 frames, plus a 4K frame with 500 candidates."""
+    """BASELINE config 3 shape (1360x800, 200 candidates/frame) on 64 frames, plus a 4K frame with 500 candidates."""
     red6, blue6 = templates
-    for (H, W, F, N) in ((800, 1360, 12, 200), (2160, 3840, 1, 500)):
+    for (H, W, F, N) in ((800, 1360, 64, 200), (2160, 3840, 1, 500)):
         frames = tsd.synth.make_frames(F, H, W)
         boxes, off = tsd.synth.make_boxes(F, N, H, W)
         det, counts = ctx_det.detect_frames(frames, boxes, off)
@@ -231,6 +231,29 @@ def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
             exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
         assert counts.tolist() == tot.tolist()
         assert _records(det) == exp
+
+
+def test_chain_256_frames_vs_oracle(ctx_det, oracle, templates, tsd):
+    """A full-sized batch (256 frames x 200 candidates = 51 200 windows) through the device-resident asynchronous chain, record
+    by record against the oracle: rare paths of the fold (merges of already merged items, pruning against rewritten
+    histograms, twins) only show up at this scale."""
+    import torch
+    red6, blue6 = templates
+    F = 256
+    uniq = tsd.synth.make_frames(16)
+    boxes, off = tsd.synth.make_boxes(F, 200, seed=tsd.synth.BOX_SEED + 7)
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(F, device=dev) % 16].contiguous()
+    d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+    ctx_det.enqueue_frames(d_frames.data_ptr(), F, 800, 1360, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=200)
+    det, counts = ctx_det.fetch_detections(int(off[-1]))
+    exp, tot = [], np.zeros(4, np.int64)
+    for f in range(F):
+        o = oracle.detect_frame(uniq[f % 16], boxes[off[f]:off[f + 1]], red6, blue6)
+        tot += o["stage_counts"]
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    assert counts.tolist() == tot.tolist()
+    assert _records(det) == exp
 
 
 def test_chain_properties_full_size(ctx_det, tsd):
