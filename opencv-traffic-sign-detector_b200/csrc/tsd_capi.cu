@@ -82,6 +82,7 @@ struct tsd_ctx {
     // last enqueue
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
+    int pairs_variant = 24;
     int k2_variant = 2;          // TSD_K2=v2|v3|v4 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
@@ -191,6 +192,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
@@ -536,18 +538,28 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     uint32_t* M = nullptr;
     int32_t* cost = nullptr;
     if (do_hist) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            CU(cudaFuncSetAttribute(k5_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * kDenseLen * 2));
-            attr_done = true;
-        }
         TRY(ensure(c, c->b_pairs, (m_row0 + (ncap > 0 ? ncap : 1)) * 2 * RW * sizeof(uint32_t)));     // (already large enough inside a chunked enqueue)
         M = (uint32_t*)c->b_pairs.p + m_row0 * 2 * RW;
         cost = out_count;                                    // [nframes] scratch until the fold writes the survivor counts (order is built first)
         CU(cudaMemsetAsync(cost, 0, (size_t)nframes * 4, c->cur));
         const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
-        k5_pairs_kernel<<<nframes * tiles, kPairWarps * 32, kPairWarps * kDenseLen * 2, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles,
-                                                                                                     P.hist_tol, P.hist_lo, M, cost);
+        const size_t psm = kPairWarps * kDenseLen * 2;
+#define PAIRS_LAUNCH(G, MB)                                                                                                  \
+        do {                                                                                                                 \
+            static bool done_ = false;                                                                                       \
+            if (!done_) { CU(cudaFuncSetAttribute(k5_pairs_kernel<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); done_ = true; } \
+            k5_pairs_kernel<G, MB><<<nframes * tiles, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles, \
+                                                                                     P.hist_tol, P.hist_lo, M, cost);          \
+        } while (0)
+        switch (c->pairs_variant) {                          // TSD_PAIRS = <group><minblocks>: A/B of the software pipeline depth / register budget
+            case 41: PAIRS_LAUNCH(4, 1); break;
+            case 43: PAIRS_LAUNCH(4, 3); break;
+            case 44: PAIRS_LAUNCH(4, 4); break;
+            case 23: PAIRS_LAUNCH(2, 3); break;
+            case 24: PAIRS_LAUNCH(2, 4); break;
+            default: PAIRS_LAUNCH(2, 4); break;
+        }
+#undef PAIRS_LAUNCH
         TRY(check_launch(c, "k5_pairs"));
         mark(c, "k5_pairs");
     }

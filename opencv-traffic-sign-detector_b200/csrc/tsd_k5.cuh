@@ -218,7 +218,8 @@ __device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_
     return warp_sum(s12);
 }
 
-__global__ void __launch_bounds__(kPairWarps * 32) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+template <int G, int MINB>
+__global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
                                                                    const float* __restrict__ E_T, int64_t e_stride,
                                                                    const int32_t* __restrict__ offsets, int nframes, int es, int RW,
                                                                    int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M,
@@ -259,36 +260,59 @@ __global__ void __launch_bounds__(kPairWarps * 32) k5_pairs_kernel(const uint32_
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         int Ik = 0;
-        while (todo) {
-            // up to 4 pairs per round; every lane loads 4 consecutive entries (128-bit) of each, so one round has all the
-            // entry loads of 4 pairs (<= 128 entries per load instruction) in flight together
-            int kk[4], nn[4];
-            const uint4* ee[4];
+        // Groups of up to G pairs; every lane loads 4 consecutive entries (128-bit) of each pair, so one load instruction
+        // covers 128 entries per pair.  The first loads of group g+1 are issued BEFORE group g is reduced (software
+        // pipelining across groups): the kernel is bound by the latency of these loads, not by their bandwidth.
+        int kc[G], nc[G], kn[G], nn[G];
+        const uint4 *ec[G], *en[G];
+        uint4 vc[G], vn[G];
+        bool have = todo != 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                kk[u] = todo ? __ffs(todo) - 1 : -1;
-                todo &= todo - 1;                           // (0 & anything stays 0)
-                nn[u] = kk[u] >= 0 ? (__shfl_sync(0xffffffffu, mi.nnz, kk[u] & 31) + 3) >> 2 : 0;      // uint4 count (zero padded)
-                ee[u] = reinterpret_cast<const uint4*>(entries + (int64_t)(base + i0 + (kk[u] & 31)) * es);
+        for (int u = 0; u < G; u++) {
+            kc[u] = todo ? __ffs(todo) - 1 : -1;
+            todo &= todo - 1;                               // (0 & anything stays 0)
+            nc[u] = kc[u] >= 0 ? (__shfl_sync(0xffffffffu, mi.nnz, kc[u] & 31) + 3) >> 2 : 0;          // uint4 count (zero padded)
+            ec[u] = reinterpret_cast<const uint4*>(entries + (int64_t)(base + i0 + (kc[u] & 31)) * es);
+            vc[u] = lane < nc[u] ? __ldg(ec[u] + lane) : make_uint4(0, 0, 0, 0);
+        }
+        while (have) {
+            const bool have_next = todo != 0;
+#pragma unroll
+            for (int u = 0; u < G; u++) {                    // next group: pop + first loads (harmless when the group is empty)
+                kn[u] = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - 1;
+                nn[u] = kn[u] >= 0 ? (__shfl_sync(0xffffffffu, mi.nnz, kn[u] & 31) + 3) >> 2 : 0;
+                en[u] = reinterpret_cast<const uint4*>(entries + (int64_t)(base + i0 + (kn[u] & 31)) * es);
+                vn[u] = lane < nn[u] ? __ldg(en[u] + lane) : make_uint4(0, 0, 0, 0);
             }
-            int acc[4] = {0, 0, 0, 0};
-            const int nmax = max(max(nn[0], nn[1]), max(nn[2], nn[3]));
-            for (int e = lane; e < nmax; e += 32) {
-                uint4 v[4];
+            int acc[G];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = e < nn[u] ? __ldg(ee[u] + e) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < G; u++)
+                acc[u] = (int)dense[vc[u].x >> 16] * (int)(vc[u].x & 0xffffu) + (int)dense[vc[u].y >> 16] * (int)(vc[u].y & 0xffffu) +
+                         (int)dense[vc[u].z >> 16] * (int)(vc[u].z & 0xffffu) + (int)dense[vc[u].w >> 16] * (int)(vc[u].w & 0xffffu);
+            int nmax = nc[0];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+            for (int u = 1; u < G; u++) nmax = max(nmax, nc[u]);
+            for (int e = lane + 32; e < nmax; e += 32) {     // windows with more than 128 occupied bins
+                uint4 v[G];
+#pragma unroll
+                for (int u = 0; u < G; u++) v[u] = e < nc[u] ? __ldg(ec[u] + e) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < G; u++)
                     acc[u] += (int)dense[v[u].x >> 16] * (int)(v[u].x & 0xffffu) + (int)dense[v[u].y >> 16] * (int)(v[u].y & 0xffffu) +
                               (int)dense[v[u].z >> 16] * (int)(v[u].z & 0xffffu) + (int)dense[v[u].w >> 16] * (int)(v[u].w & 0xffffu);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                for (int u = 0; u < G; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) if (lane == kk[u]) Ik = acc[u];
+            for (int u = 0; u < G; u++) {
+                if (lane == kc[u]) Ik = acc[u];
+                kc[u] = kn[u]; nc[u] = nn[u]; ec[u] = en[u]; vc[u] = vn[u];
+            }
+            have = have_next;
         }
         if (need) c = classify_from_int(Ik, mj, mi, tol, lo);
         unsigned unsure = __ballot_sync(0xffffffffu, need && c == kClsUnsure);
