@@ -67,6 +67,7 @@ struct tsd_ctx {
     // constant state
     Tables* d_tab = nullptr;
     ScoreTemplates* d_tmpl = nullptr;
+    MaskLut* d_mlut = nullptr;               // inRange bounds of tsd_config as per-channel flag tables (K3)
     bool have_templates = false;
     int tmpl_D = 0;
     double* d_simtab = nullptr;
@@ -210,6 +211,21 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     CU(cudaMalloc(&c->d_tab, sizeof(Tables)));
     CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tmpl, sizeof(ScoreTemplates)));
+    {   // K3 flag tables: bit 0 / 1 = red band 0 / 1, bit 2 = blue (DET:70-86 bounds from the config)
+        MaskLut ml;
+        const tsd_config& g = c->cfg;
+        for (int v = 0; v < 256; v++) {
+            uint8_t f[3] = {0, 0, 0};
+            for (int ch3 = 0; ch3 < 3; ch3++) {
+                if (v >= g.red_lo[0][ch3] && v <= g.red_hi[0][ch3]) f[ch3] |= 1;
+                if (v >= g.red_lo[1][ch3] && v <= g.red_hi[1][ch3]) f[ch3] |= 2;
+                if (v >= g.blue_lo[ch3] && v <= g.blue_hi[ch3]) f[ch3] |= 4;
+            }
+            ml.hf[v] = f[0]; ml.sf[v] = f[1]; ml.vf[v] = f[2];
+        }
+        CU(cudaMalloc(&c->d_mlut, sizeof(MaskLut)));
+        CU(cudaMemcpy(c->d_mlut, &ml, sizeof ml, cudaMemcpyHostToDevice));
+    }
     // default corner-similarity table
     const int n = 1 << 16;
     std::vector<double> f(n);
@@ -240,7 +256,7 @@ int tsd_destroy(tsd_ctx* c) {
     for (DevBuf* b : more) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_mlut, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -476,12 +492,15 @@ static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* bo
 static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, int ws, uint32_t* entries, WinMeta* meta,
                     float* E_T, int64_t e_stride) {
     if (n_max == 0) return TSD_OK;
-    int grid = cdiv(n_max, kHistWarps);
-    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-    if (npx <= 640)
-        k5_hist_kernel<640><<<grid, kHistWarps * 32, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
-    else
-        k5_hist_kernel<1024><<<grid, kHistWarps * 32, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+    if (npx <= 640) {
+        int grid = cdiv(n_max, 4);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        k5_hist_kernel<640, 4><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+    } else {
+        int grid = cdiv(n_max, 3);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        k5_hist_kernel<1024, 3><<<grid, 96, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+    }
     return check_launch(c, "k5_hist");
 }
 
@@ -894,7 +913,10 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
         uint32_t* bits = (uint32_t*)c->b_bits.p + wo * 2 * NW;
         int grid = cdiv((int64_t)cap * 32, 256);
         if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-        k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
+        if (ws <= 4 * 32 * 16)
+            k3_masks_v3_kernel<4><<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, c->d_mlut, red, blue, ms, bits);
+        else
+            k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
         TRY(check_launch(c, "k3_masks"));
         mark(c, "k3_masks");
         if (NW == 20)

@@ -179,23 +179,49 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     return nnz;
 }
 
-constexpr int kHistWarps = 4;
-
-template <int CAP>
+template <int CAP, int kHistWarps>      // warps per CTA: 4 for D=25, 3 for D=32 (static shared memory <= 48 KB)
 __global__ void __launch_bounds__(kHistWarps * 32) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
                                                                   int n_max, int npx, int ws, int es, const Tables* __restrict__ tab,
                                                                   uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
                                                                   float* __restrict__ E_T, int64_t e_stride) {
+    constexpr int NCH = (CAP * 3 / 16 + 31) / 32;            // 128-bit chunks per lane covering one window
     __shared__ HsvLut lut;
     __shared__ HistScratch<CAP> s_w[kHistWarps];
+    __shared__ uint4 s_px[kHistWarps][NCH * 32];
     load_hsv_lut(lut, tab);
     __syncthreads();
-    const int wid = threadIdx.x >> 5;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = gridDim.x * kHistWarps;
-    for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps)
-        hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
+    const bool staged = (ws & 15) == 0 && ((uintptr_t)windows & 15) == 0 && ws <= NCH * 32 * 16;
+    if (!staged) {                                           // packed public layout: pixels straight from global memory
+        for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps)
+            hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
+                                 E_T ? E_T + w : nullptr, e_stride);
+        return;
+    }
+    // internal layout: the NEXT window travels into registers (128-bit loads, all in flight together) while the current
+    // one is processed from shared memory -- the kernel was bound by the latency of its byte loads
+    const int nch = ws >> 4;
+    uint4 r[NCH];
+    int w = blockIdx.x * kHistWarps + wid;
+    if (w < n) {
+        const uint4* g = reinterpret_cast<const uint4*>(windows + (int64_t)w * ws);
+#pragma unroll
+        for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
+    }
+    for (; w < n; w += nwarps) {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) s_px[wid][lane + 32 * k] = r[k];
+        __syncwarp();
+        if (w + nwarps < n) {
+            const uint4* g = reinterpret_cast<const uint4*>(windows + (int64_t)(w + nwarps) * ws);
+#pragma unroll
+            for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
+        }
+        hist_build_warp<CAP>(reinterpret_cast<const uint8_t*>(s_px[wid]), npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
                              E_T ? E_T + w : nullptr, e_stride);
+    }
 }
 
 // =====================================================================================================================

@@ -632,6 +632,70 @@ __global__ void __launch_bounds__(256) k3_masks_v2_kernel(const uint8_t* __restr
     }
 }
 
+// K3 v3 (internal layout only): v2 + (1) the inRange tests become three byte-table lookups AND-ed together (bit 0/1 = the two
+// red bands, bit 2 = blue; tables built on the host from tsd_config, so any bounds work), (2) the next window travels into
+// registers with 128-bit loads while the current one is processed from shared memory (v2 stalled on its byte loads).
+struct MaskLut { uint8_t hf[256], sf[256], vf[256]; };
+
+template <int NCH>
+__global__ void __launch_bounds__(256) k3_masks_v3_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
+                                                          const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws,
+                                                          const Tables* __restrict__ tab, const MaskLut* __restrict__ mlut,
+                                                          uint8_t* __restrict__ red, uint8_t* __restrict__ blue, int ms, uint32_t* __restrict__ bits) {
+    __shared__ int32_t s_sdiv[256], s_hdiv[256];
+    __shared__ uint8_t s_hf[256], s_sf[256], s_vf[256];
+    __shared__ uint4 s_px[8][NCH * 32];
+    s_sdiv[threadIdx.x & 255] = tab->sdiv[threadIdx.x & 255];
+    s_hdiv[threadIdx.x & 255] = tab->hdiv[threadIdx.x & 255];
+    s_hf[threadIdx.x & 255] = mlut->hf[threadIdx.x & 255];
+    s_sf[threadIdx.x & 255] = mlut->sf[threadIdx.x & 255];
+    s_vf[threadIdx.x & 255] = mlut->vf[threadIdx.x & 255];
+    __syncthreads();
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int NW = (npx + 31) >> 5, nch = ws >> 4;
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint4 r[NCH];
+    int slot_next = 0;                                       // slot of window w + nwarps (loaded one iteration ahead)
+    if (w < n) {
+        const int s0 = slots ? __ldg(slots + w) : w;
+        const uint4* g = reinterpret_cast<const uint4*>(windows + (int64_t)s0 * ws);
+#pragma unroll
+        for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
+        if (w + nwarps < n) slot_next = slots ? __ldg(slots + w + nwarps) : w + nwarps;
+    }
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(s_px[wid]);
+    for (; w < n; w += nwarps) {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) s_px[wid][lane + 32 * k] = r[k];
+        __syncwarp();
+        if (w + nwarps < n) {
+            const uint4* g = reinterpret_cast<const uint4*>(windows + (int64_t)slot_next * ws);
+#pragma unroll
+            for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
+            if (w + 2 * nwarps < n) slot_next = slots ? __ldg(slots + w + 2 * nwarps) : w + 2 * nwarps;
+        }
+        uint8_t* __restrict__ ro = red + (int64_t)w * ms;
+        uint8_t* __restrict__ bo = blue + (int64_t)w * ms;
+        uint32_t myr = 0, myb = 0;
+#pragma unroll 4
+        for (int i = 0; i < NW; i++) {
+            const int p = i * 32 + lane;
+            const bool valid = p < npx;
+            const int pp = valid ? p : 0;
+            const int b = px[3 * pp], g = px[3 * pp + 1], rr = px[3 * pp + 2];
+            int H, S, V;
+            bgr2hsv(b, g, rr, s_sdiv, s_hdiv, H, S, V);
+            const unsigned fl = valid ? (unsigned)(s_hf[H] & s_sf[S] & s_vf[V]) : 0u;
+            if (valid) { ro[p] = (fl & 3u) ? 255 : 0; bo[p] = (fl & 4u) ? 255 : 0; }     // cv2.add of the two red bands saturates at 255
+            const unsigned wr = __ballot_sync(0xffffffffu, (fl & 3u) != 0), wb = __ballot_sync(0xffffffffu, (fl & 4u) != 0);
+            if (lane == i) { myr = wr; myb = wb; }
+        }
+        if (bits && lane < NW) { bits[(int64_t)w * 2 * NW + lane] = myr; bits[(int64_t)w * 2 * NW + NW + lane] = myb; }
+        __syncwarp();                                        // all taps read before the staging buffer is overwritten
+    }
+}
+
 __global__ void bgr2hsv_kernel(const uint8_t* __restrict__ bgr, int64_t npx, const Tables* __restrict__ tab,
                                uint8_t* __restrict__ hsv) {
     __shared__ int32_t s_sdiv[256], s_hdiv[256];
