@@ -60,6 +60,7 @@ struct tsd_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf b_stage[2], b_hboxes, b_hoff;
     int zero_copy = 1;                       // K2 reads page-locked host frames in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
+    int zc_chunk = 0, zc_grid = 0;           // zero-copy host path: frames per stream chunk / K2 CTAs per SM (0 = off: measured no gain)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
     tsd_config cfg;
     int64_t launches = 0;
@@ -84,6 +85,7 @@ struct tsd_ctx {
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
     int pairs_variant = 24;
+    int k2_grid_limit = 0;                   // > 0: persistent K2 with at most this many CTAs (host-memory frames, PCIe-bound)
     int k2_variant = 2;          // TSD_K2=v2|v3|v4 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
@@ -182,6 +184,8 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
         CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
     { const char* e = getenv("TSD_ZEROCOPY"); if (e) c->zero_copy = e[0] != '0'; }
+    { const char* e = getenv("TSD_ZC_CHUNK"); if (e) c->zc_chunk = atoi(e); }
+    { const char* e = getenv("TSD_ZC_GRID"); if (e) c->zc_grid = atoi(e); }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
@@ -447,13 +451,14 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
                            const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride) {
     if (n_max == 0) return TSD_OK;
-    const int g4 = cdiv(n_max, 4);
+    int g4 = cdiv(n_max, 4);
+    if (c->k2_grid_limit > 0 && g4 > c->k2_grid_limit) g4 = c->k2_grid_limit;     // only the v2 kernels loop over windows
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
     // TSD_K2 = v2 | v3 | v4 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all three are bit-identical.
     // v3 (staged through shared memory with cp.async) needs 16-byte aligned rows: its 128-bit chunks never leave the frame buffer.
-    const bool fast = c->k2_variant == 3 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
+    const bool fast = c->k2_variant == 3 && c->k2_grid_limit == 0 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
     const int gk = cdiv(n_max, kK2Warps);
-    const bool v4 = c->k2_variant == 4 && ((uintptr_t)windows % 16 == 0);
+    const bool v4 = c->k2_variant == 4 && c->k2_grid_limit == 0 && ((uintptr_t)windows % 16 == 0);
     if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
@@ -1154,8 +1159,19 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         // (~0.5 MB of a 3.26 MB frame at 200 candidates), measured 3.3x faster than copying whole frames (profiles/).
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            TRY(run_chunk((const uint8_t*)at.devicePointer, 0, nframes));
-            int rc = fetch_chunk(0);
+            // K2 is PCIe-bound here: a persistent grid of 2 CTAs per SM keeps the bus busy and leaves the SMs to the other
+            // kernels; the batch is split into chunks on two streams so that the chain of chunk k runs under the PCIe
+            // reads of chunk k+1 (TSD_ZC_CHUNK frames per chunk, 0 = one chunk; TSD_ZC_GRID CTAs per SM, 0 = full grid)
+            const int save_chunk = c->stream_chunk, save_limit = c->k2_grid_limit;
+            const bool save_prof = c->profiling;
+            if (!c->profiling) {
+                c->stream_chunk = c->zc_chunk > 0 ? c->zc_chunk : -1;
+                c->k2_grid_limit = c->zc_grid * c->sm_count;
+            }
+            int rc = run_chunk((const uint8_t*)at.devicePointer, 0, nframes);
+            c->stream_chunk = save_chunk; c->k2_grid_limit = save_limit; c->profiling = save_prof;
+            TRY(rc);
+            rc = fetch_chunk(0);
             *ndet = nd_total;
             if (counts) for (int i = 0; i < 4; i++) counts[i] = tot[i];
             return rc;

@@ -77,6 +77,7 @@ __device__ __forceinline__ WinMeta load_meta_cg(const WinMeta* p) {      // 3 x 
 // =====================================================================================================================
 template <int CAP>
 struct HistScratch {
+    uint32_t gsum[32];           // sum of count^2 per bin group (exact integers -> deterministic energies)
     uint32_t bitmap[96];
     uint32_t cnt[CAP];
     uint16_t prefix[96];
@@ -101,6 +102,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
                                                uint32_t* __restrict__ e, WinMeta* meta, float* Eg, int64_t e_stride) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
+    sw.gsum[lane] = 0;
     __syncwarp();
     // pass A: bin of every pixel + occupancy bitmap + pixel hash
     uint32_t hsh = 0;
@@ -149,25 +151,21 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     for (int r = lane; r < nnz4; r += 32) {
         uint32_t v = 0;
         if (r < nnz) {
-            const uint32_t c = sw.cnt[r];
-            v = ((uint32_t)sw.binof[r] << 16) | c;
+            const uint32_t c = sw.cnt[r], bin = sw.binof[r];
+            v = (bin << 16) | c;
             const double h = (double)((float)c * a);
             s1 += h; s11 += h * h;
+            if (Eg) atomicAdd(&sw.gsum[(bin * 2185u) >> 18], c * c);     // bin / 120, exact for bin < 3000 (checked exhaustively)
         }
         e[r] = v;
     }
     s1 = warp_sum(s1); s11 = warp_sum(s11);
     hsh = warp_sum_u(hsh);
     if (Eg) {
-        // group g = bins [120 g, 120 g + 120): contiguous rank range; lane g sums its range (deterministic, no atomics)
-        float eg = 0.f;
-        if (lane < kHistGroups) {
-            const int bs = 120 * lane, be = 120 * lane + 120;
-            const int rs = (int)sw.prefix[bs >> 5] + __popc(sw.bitmap[bs >> 5] & ((1u << (bs & 31)) - 1));
-            const int re = lane == kHistGroups - 1 ? nnz : (int)sw.prefix[be >> 5] + __popc(sw.bitmap[be >> 5] & ((1u << (be & 31)) - 1));
-            for (int r = rs; r < re; r++) { const float hf = (float)sw.cnt[r] * a; eg += hf * hf; }
-            Eg[(int64_t)lane * e_stride] = sqrtf(eg) * 1.00001f;       // inflated: only ever used as an upper bound
-        }
+        // E_g = sqrt(sum h^2) over the group, h = fl32(count * a) <= count * a * (1 + 2^-23): a * sqrt(sum count^2), inflated by
+        // 1e-5, is an upper bound of it (only ever used as a bound: Cauchy-Schwarz pruning in k5_pairs / the fold)
+        __syncwarp();
+        if (lane < kHistGroups) Eg[(int64_t)lane * e_stride] = a * sqrtf((float)sw.gsum[lane]) * 1.00001f;
     }
     if (lane == 0) {
         const double A = s11 - s1 * s1 * (1.0 / (double)kHistBins);

@@ -237,13 +237,15 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
     uint8_t* __restrict__ windows, int out_stride) {
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    if (w >= n) return;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // one window per warp; the grid normally covers all windows (one trip), a smaller grid makes the warps persistent
+    // (host-memory frames: the kernel is PCIe-bound and should leave the SMs to the other stream's kernels)
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
     const int4 c = coords[w];
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
-    if (cw <= 0 || ch <= 0) return;
+    if (cw <= 0 || ch <= 0) continue;
     const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
     uint8_t* __restrict__ dst = windows + (int64_t)w * out_stride + lane * C;
     if (D * D * C + lane < out_stride) windows[(int64_t)w * out_stride + D * D * C + lane] = 0;    // zero pad (< 16 bytes)
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
                 for (int k = 0; k < C; k++) dst[dy * D * C + k] = v[k];
             }
         }
-        return;
+        continue;
     }
     if (cw == 2 * D && ch == 2 * D) {                       // INTER_AREA 2x2 fast path
         const uint8_t* p = src + 2 * li * C;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
                 for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
             }
         }
-        return;
+        continue;
     }
     // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
     int xs0, xd1, xa0, xa1, yr0, yr1, yb0, yb1;
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
 #pragma unroll
             for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
         }
+    }
     }
 }
 
