@@ -240,7 +240,17 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     c->h_simtab = f;
     {   // HOG Gaussian window, sigma = (16+16)/8 = 4  (OpenCV HOGCache::init)
         float sigma = 4.f, sc = 1.f / (sigma * sigma * 2);
-        for (int i = 0; i < 16; i++) { float di = i - 16 * 0.5f; c->hog.gauss[i] = expf(-di * di * sc); }
+        for (int i = 0; i < 16; i++) {
+            const float di = i - 16 * 0.5f, g = expf(-di * di * sc);
+            const float cell = (i + 0.5f) / 8 - 0.5f;
+            const int i0 = (int)floorf(cell);
+            const float f = cell - i0;
+            for (int cc = 0; cc < 2; cc++) {
+                float wgt = 0.f;                             // bilinear weight of cell cc at position i (out-of-range neighbours dropped)
+                if (cc == i0) wgt = 1.f - f; else if (cc == i0 + 1) wgt = f;
+                c->hog.wsep[i][cc] = g * wgt;
+            }
+        }
     }
     *out = c;
     return TSD_OK;
@@ -816,7 +826,11 @@ int tsd_hog(tsd_ctx* c, const uint8_t* gray, int n, float* desc, int mem) {
     Stage s(c);
     void *dg = (void*)gray, *dd = desc;
     if (mem == TSD_MEM_HOST) { TRY(s.in(gray, (size_t)n * 1024, &dg)); TRY(s.alloc(&dd, (size_t)n * TSD_HOG_LEN * 4)); }
-    k7_hog_kernel<<<cdiv(n, kHogWarps), kHogWarps * 32, 0, c->cur>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dd);
+    {
+        int grid = cdiv(n, kHogWarps);
+        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        k7_hog_kernel<<<grid, kHogWarps * 32, 0, c->cur>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dd);
+    }
     TRY(check_launch(c, "k7_hog"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(desc, dd, (size_t)n * TSD_HOG_LEN * 4)); CU(cudaStreamSynchronize(c->stream)); }
     return TSD_OK;
@@ -940,7 +954,11 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
         k6_gray_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, gray);
         TRY(check_launch(c, "k6_gray"));
         mark(c, "k6_gray");
-        k7_hog_kernel<<<cdiv(cap, kHogWarps), kHogWarps * 32, 0, c->cur>>>(gray, d_nsurv, nb, c->hog, hog);
+        {
+            int hgrid = cdiv(cap, kHogWarps);
+            if (hgrid > c->sm_count * 8) hgrid = c->sm_count * 8;
+            k7_hog_kernel<<<hgrid, kHogWarps * 32, 0, c->cur>>>(gray, d_nsurv, nb, c->hog, hog);
+        }
         TRY(check_launch(c, "k7_hog"));
         mark(c, "k7_hog");
         TRY(dev_lda(c, hog, d_nsurv, nb, c->cfg.proba_tol, nullptr, id));

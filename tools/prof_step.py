@@ -16,6 +16,7 @@ ap.add_argument("--boxes", type=int, default=200)
 ap.add_argument("--H", type=int, default=800)
 ap.add_argument("--W", type=int, default=1360)
 ap.add_argument("--times", action="store_true")
+ap.add_argument("--mode", default="det", choices=["det", "rec"], help="det: K1 K2 K5 K3 K4 (x1.30, 25x25); rec: K1 K2 K5 K6 K7 K8 (x1.15, 32x32)")
 a = ap.parse_args()
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "det_templates.npz"))
 U = min(16, a.frames)
@@ -24,17 +25,22 @@ boxes, off = tsd_b200.synth.make_boxes(a.frames, a.boxes, a.H, a.W)
 dev = torch.device("cuda", 0)
 d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(a.frames, device=dev) % U].contiguous()
 d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
-ctx = tsd_b200.Context(0, "det")
-ctx.set_templates(g["red6"], g["blue6"])
+mode = tsd_b200.RUN_DETECT if a.mode == "det" else tsd_b200.RUN_RECOGNIZE
+ctx = tsd_b200.Context(0, a.mode)
+if a.mode == "det":
+    ctx.set_templates(g["red6"], g["blue6"])
+else:
+    r = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "rec_golden.npz"))
+    ctx.set_lda(r["lda_W"], r["lda_b"])
 def one():
-    ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=a.boxes)
+    ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), mode=mode, max_boxes_per_frame=a.boxes)
 if a.times:
     for _ in range(3):
         one()
     ctx.synchronize()
     ctx.set_profiling(True)
 for _ in range(a.steps):
-    ctx.enqueue_frames(d_frames.data_ptr(), a.frames, a.H, a.W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=a.boxes)
+    one()
 ctx.synchronize()
 if a.times:
     print({k: round(v / a.steps, 4) for k, v in ctx.stage_times()})
