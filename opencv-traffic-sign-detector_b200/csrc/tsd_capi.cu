@@ -555,10 +555,10 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
     P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
     if (nframes == 0) return TSD_OK;
-    if (max_n > 1024) {
-        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes);
-        return check_launch(c, "k5_fold");
-    }
+    // max_n is only an upper bound (raw boxes per frame); frames with more than 1024 aspect-passing windows are flagged by
+    // the warp-per-frame fold (out_count = -1) and redone by the general block-synchronous fold below
+    const bool may_exceed = max_n > 1024;
+    if (may_exceed) max_n = 1024;
     const int RW = ((max_n > 1 ? max_n : 1) + 31) / 32;
     // Corner similarity can only act when sqrt(f1 f2) >= coord_lo, i.e. both f >= coord_lo^2: squared distances at or
     // beyond `cut` are class 0 without a table lookup (f is non-increasing in d2).
@@ -598,7 +598,15 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         mark(c, "k5_pairs");
     }
     if (max_n <= 256) return npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
-    return npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
+    {
+        const int rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
+        if (rc != TSD_OK) return rc;
+    }
+    if (may_exceed) {
+        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
+        TRY(check_launch(c, "k5_fold"));
+    }
+    return TSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1045,8 +1053,9 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
     }
     {   // the pair-class bit rows are sized here (not inside dev_fold) so that no chunk can trigger a reallocation
-        const int RW = ((max_boxes_per_frame > 1 ? max_boxes_per_frame : 1) + 31) / 32;
-        if (max_boxes_per_frame <= 1024) TRY(ensure(c, c->b_pairs, cap * 2 * RW * sizeof(uint32_t)));
+        const int mb = max_boxes_per_frame > 1024 ? 1024 : max_boxes_per_frame;
+        const int RW = ((mb > 1 ? mb : 1) + 31) / 32;
+        TRY(ensure(c, c->b_pairs, cap * 2 * RW * sizeof(uint32_t)));
     }
     int rc = TSD_OK;
     if (nchunks == 1) {

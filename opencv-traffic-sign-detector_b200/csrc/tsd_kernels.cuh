@@ -1034,7 +1034,7 @@ __device__ void apply_deletions_block(FoldSmem& sm, const FoldParams& P, int32_t
 // One CTA per frame.  Sequential over the frame's items (the fold order is the semantics); each item is compared
 // with ALL current survivors in parallel, the classes are scanned in list order up to the first merge, the merge is
 // applied and only the survivors after it are re-evaluated with the updated item (speculate-then-scan).
-__global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int nframes) {
+__global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int nframes, int only_flagged) {
     __shared__ FoldSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = kFoldThreads >> 5;
     const int nbytes = P.npx * 3;
@@ -1042,6 +1042,7 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
     if (tid == 0) sm.any_del = 0;
     __syncthreads();
     for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        if (only_flagged && P.out_count[f] != -1) continue;  // the warp-per-frame fold already did this frame (block-uniform)
         const int base = P.offsets[f], n = P.offsets[f + 1] - base;
         int32_t* list = P.list + base;
         uint8_t* flags = P.flags + base;

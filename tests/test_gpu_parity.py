@@ -198,6 +198,29 @@ def test_k5_dedup_adversarial(ctx_det, oracle):
             assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (by_coords, tol, f)
 
 
+def test_k5_dedup_large_frames(ctx_det, oracle):
+    """Frames with 300 / 700 / 1300 windows in one call: the 1024-window warp-per-frame fold, and the frame that exceeds it
+    (flagged and redone by the general block-synchronous fold)."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (40, 25, 25, 3), dtype=np.uint8)
+    wins, coords, off = [], [], [0]
+    for n in (300, 1300, 700):
+        for i in range(n):
+            b = base[int(rng.integers(0, 40))].astype(np.int16)
+            w = b + rng.integers(-10, 11, b.shape) if rng.random() < 0.7 else rng.integers(0, 256, b.shape)
+            wins.append(np.clip(w, 0, 255).astype(np.uint8))
+            x, y, s = int(rng.integers(0, 1300)), int(rng.integers(0, 760)), int(rng.integers(20, 80))
+            coords.append((x, y, x + s, y + s))
+        off.append(len(coords))
+    wins = np.stack(wins); coords = np.array(coords, np.int32); off = np.array(off, np.int32)
+    for by_coords, tol in ((False, 0.85), (True, 0.95)):
+        gw, gc, go = ctx_det.dedup(wins, coords, off, by_coords, tol)
+        for f in range(len(off) - 1):
+            ow, oc = oracle.dedup(wins[off[f]:off[f + 1]], coords[off[f]:off[f + 1]], by_coords, tol)
+            assert go[f + 1] - go[f] == len(oc), (by_coords, f)
+            assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (by_coords, f)
+
+
 # ---- whole chain ------------------------------------------------------------------------------------------------------
 def _records(det):
     return [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
