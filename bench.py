@@ -207,11 +207,40 @@ def cpu_baseline_sample(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and so the first-touch placement of its page-locked host frames) to the CPUs of the NUMA node
+    the GPU hangs off: the e2e leg reads host memory from the GPU, a remote node costs PCIe/UPI bandwidth.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.replace(",", "").isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def run_b200(args, rank, world, local_rank):
     # The CPU baseline forks worker processes: run it BEFORE this process touches CUDA (rank 0, N=1 only)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_sample(args)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import tsd_b200
     if not torch.cuda.is_available():
@@ -355,7 +384,7 @@ def run_b200(args, rank, world, local_rank):
             "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in per_stage.items() if v > 0},
             "chain": {"algorithmic_bytes_per_step": fused_bytes, "gbs": fused_bytes / (ms / args.steps * 1e-3) / 1e9,
                       "frac_of_peak": fused_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "numa_node_rank0": numa_node,
         }
         if cpu_base is not None:
             out["cpu_baseline"] = cpu_base
