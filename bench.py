@@ -336,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
     Fe = min(args.e2e_frames, F) if not args.no_e2e else 1
     h_frames = torch.empty((Fe, H, W, 3), dtype=torch.uint8).pin_memory()
     for f0 in range(0, Fe, 256):
-        h_frames[f0:f0 + 256].copy_(d_frames[f0:f0 + 256])
+        h_frames[f0:min(f0 + 256, Fe)].copy_(d_frames[f0:min(f0 + 256, Fe)])
     hf = h_frames.numpy()
     hb, ho = boxes[:off[Fe]], off[:Fe + 1]
     for _ in range(2):

@@ -54,12 +54,15 @@ struct tsd_ctx {
                                              // the fold's shared memory footprint keeps other kernels from co-residing)
     struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; };
     std::vector<ChunkInfo> chunks;           // of the last enqueue
+    std::vector<cudaEvent_t> ev_chunk;
+    int pipe_mode = 0;                       // chunked enqueue as a producer (K1+K2) / consumer (rest) pipeline instead of alternating streams
     DevBuf b_summary, b_order;
     size_t order_off = 0;                   // offset (ints) of the current chunk inside b_order
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf b_stage[2], b_hboxes, b_hoff;
     int zero_copy = 1;                       // K2 reads page-locked host frames in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
+    int zc_pipe = 0;                         // (producer/consumer chunk pipeline for the zero-copy path: measured slower, off)
     int zc_chunk = 0, zc_grid = 0;           // zero-copy host path: frames per stream chunk / K2 CTAs per SM (0 = off: measured no gain)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
     tsd_config cfg;
@@ -173,9 +176,12 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->cur = c->stream;
-    for (int i = 0; i < 2; i++) {
-        CU(cudaStreamCreateWithFlags(&c->cs[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    {
+        int lo_p = 0, hi_p = 0;                              // numerically lower = higher priority
+        CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CU(cudaStreamCreateWithPriority(&c->cs[0], cudaStreamNonBlocking, lo_p));
+        CU(cudaStreamCreateWithPriority(&c->cs[1], cudaStreamNonBlocking, hi_p));
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     { const char* e = getenv("TSD_STREAM_CHUNK"); if (e) c->stream_chunk = atoi(e); }
@@ -186,6 +192,8 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     { const char* e = getenv("TSD_ZEROCOPY"); if (e) c->zero_copy = e[0] != '0'; }
     { const char* e = getenv("TSD_ZC_CHUNK"); if (e) c->zc_chunk = atoi(e); }
     { const char* e = getenv("TSD_ZC_GRID"); if (e) c->zc_grid = atoi(e); }
+    { const char* e = getenv("TSD_ZC_PIPE"); if (e) c->zc_pipe = atoi(e); }
+    { const char* e = getenv("TSD_PIPE"); if (e) c->pipe_mode = atoi(e); }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
@@ -267,6 +275,7 @@ int tsd_destroy(tsd_ctx* c) {
     DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order};
     for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
     for (DevBuf* b : more) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -899,7 +908,8 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 // One chunk of frames through the whole chain on c->cur.  wo = first window slot of the chunk in the per-window scratch,
 // fo = first entry of the chunk in the per-frame scratch arrays (cf + 1 entries), nbcap = upper bound of the chunk's boxes.
 static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, int H, int W, int64_t row_stride, int64_t frame_stride,
-                         const int32_t* d_boxes, const int32_t* d_box_offsets, int nbcap, int maxb, size_t wo, int fo, int chunk_index) {
+                         const int32_t* d_boxes, const int32_t* d_box_offsets, int nbcap, int maxb, size_t wo, int fo, int chunk_index,
+                         int phase = 3 /* bit 0: K1+K2 (the part that reads the frames), bit 1: everything after */) {
     const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
     const int nb = nbcap;
@@ -916,14 +926,17 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
     uint8_t *flags = (uint8_t*)c->b_flags.p + wo, *emit = (uint8_t*)c->b_emit.p + wo;
     DetRec* det = (DetRec*)c->b_det.p + wo;
     c->order_off = (size_t)fo;
-    mark(c, "start");
-    // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
-    TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
-    mark(c, "k1_expand_filter");
     const int32_t* d_nwin = winoff + cf;
-    // K2 (DET:123-124)
-    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
-    mark(c, "k2_crop_resize");
+    if (phase & 1) {
+        mark(c, "start");
+        // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
+        TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
+        mark(c, "k1_expand_filter");
+        // K2 (DET:123-124)
+        TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
+        mark(c, "k2_crop_resize");
+    }
+    if (!(phase & 2)) return TSD_OK;
     // K5 (DET:127-129)
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
@@ -1064,12 +1077,29 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     } else {
         CU(cudaEventRecord(c->ev_fork, c->stream));
         for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(c->cs[i], c->ev_fork, 0));
+        while ((int)c->ev_chunk.size() < nchunks) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_chunk.push_back(e);
+        }
         for (int k = 0; k < nchunks && rc == TSD_OK; k++) {
             const tsd_ctx::ChunkInfo& ci = c->chunks[k];
-            c->cur = c->cs[k & 1];
             // offsets stay absolute (the kernels index `d_boxes` with them), so the box base pointer is not advanced
-            rc = enqueue_chain(c, mode, d_frames + (size_t)ci.f0 * frame_stride, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0,
-                               ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k);
+            const uint8_t* fr = d_frames + (size_t)ci.f0 * frame_stride;
+            if (c->pipe_mode) {
+                // producer / consumer: K1+K2 of every chunk on cs[0] (low priority; PCIe-bound when the frames are host memory),
+                // the rest of the chain of chunk k on cs[1] (high priority) as soon as its windows exist -> it runs under K2 of chunk k+1
+                c->cur = c->cs[0];
+                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k, 1);
+                if (rc != TSD_OK) break;
+                CU(cudaEventRecord(c->ev_chunk[k], c->cs[0]));
+                CU(cudaStreamWaitEvent(c->cs[1], c->ev_chunk[k], 0));
+                c->cur = c->cs[1];
+                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k, 2);
+            } else {
+                c->cur = c->cs[k & 1];
+                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k);
+            }
         }
         c->cur = c->stream;
         for (int i = 0; i < 2; i++) { CU(cudaEventRecord(c->ev_join[i], c->cs[i])); CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0)); }
@@ -1189,14 +1219,14 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
             // K2 is PCIe-bound here: a persistent grid of 2 CTAs per SM keeps the bus busy and leaves the SMs to the other
             // kernels; the batch is split into chunks on two streams so that the chain of chunk k runs under the PCIe
             // reads of chunk k+1 (TSD_ZC_CHUNK frames per chunk, 0 = one chunk; TSD_ZC_GRID CTAs per SM, 0 = full grid)
-            const int save_chunk = c->stream_chunk, save_limit = c->k2_grid_limit;
-            const bool save_prof = c->profiling;
+            const int save_chunk = c->stream_chunk, save_limit = c->k2_grid_limit, save_pipe = c->pipe_mode;
             if (!c->profiling) {
                 c->stream_chunk = c->zc_chunk > 0 ? c->zc_chunk : -1;
                 c->k2_grid_limit = c->zc_grid * c->sm_count;
+                c->pipe_mode = c->zc_pipe;
             }
             int rc = run_chunk((const uint8_t*)at.devicePointer, 0, nframes);
-            c->stream_chunk = save_chunk; c->k2_grid_limit = save_limit; c->profiling = save_prof;
+            c->stream_chunk = save_chunk; c->k2_grid_limit = save_limit; c->pipe_mode = save_pipe;
             TRY(rc);
             rc = fetch_chunk(0);
             *ndet = nd_total;
