@@ -88,6 +88,8 @@ struct tsd_ctx {
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
     int pairs_variant = 24;
+    int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
+                                             // consecutive windows: measured slower (0.45 vs 0.27 ms device, 19.1 vs 16.5 ms zero-copy e2e)
     int k2_grid_limit = 0;                   // > 0: persistent K2 with at most this many CTAs (host-memory frames, PCIe-bound)
     int k2_variant = 2;          // TSD_K2=v2|v3|v4 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
     std::vector<cudaEvent_t> ev;
@@ -205,6 +207,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("TSD_K2_BY_FRAME"); if (e) c->k2_by_frame = atoi(e); }
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
@@ -468,10 +471,13 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
 
 // out_stride = bytes between output windows: D*D*ch (public packed layout) or win_stride() (internal, zero padded)
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
-                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride) {
+                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride,
+                           const int32_t* frame_offsets = nullptr, int nframes = 0) {
     if (n_max == 0) return TSD_OK;
     int g4 = cdiv(n_max, 4);
     if (c->k2_grid_limit > 0 && g4 > c->k2_grid_limit) g4 = c->k2_grid_limit;     // only the v2 kernels loop over windows
+    if (!c->k2_by_frame || c->k2_variant != 2) frame_offsets = nullptr;
+    if (frame_offsets) g4 = nframes;                         // one CTA per frame (v2 only)
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
     // TSD_K2 = v2 | v3 | v4 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all three are bit-identical.
     // v3 (staged through shared memory with cp.async) needs 16-byte aligned rows: its 128-bit chunks never leave the frame buffer.
@@ -486,10 +492,10 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
     else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
     else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
@@ -933,7 +939,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
         TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
         mark(c, "k1_expand_filter");
         // K2 (DET:123-124)
-        TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
+        TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws, winoff, cf));
         mark(c, "k2_crop_resize");
     }
     if (!(phase & 2)) return TSD_OK;

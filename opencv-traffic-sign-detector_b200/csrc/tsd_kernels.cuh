@@ -235,13 +235,27 @@ template <int C, int D>
 __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride) {
+    uint8_t* __restrict__ windows, int out_stride, const int32_t* __restrict__ frame_offsets, int nframes) {
     const int lane = threadIdx.x & 31;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     // one window per warp; the grid normally covers all windows (one trip), a smaller grid makes the warps persistent
     // (host-memory frames: the kernel is PCIe-bound and should leave the SMs to the other stream's kernels)
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+    // With frame_offsets (CSR of the windows per frame) a CTA takes whole FRAMES: the windows of one frame overlap heavily
+    // (nested / jittered MSER boxes), so their source bytes are fetched once into this SM's L1 instead of once per SM.
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, w_end = n, w_step = nwarps, f = blockIdx.x;
+    if (frame_offsets) {
+        if (f >= nframes) return;
+        w = frame_offsets[f] + (threadIdx.x >> 5); w_end = min(frame_offsets[f + 1], n); w_step = blockDim.x >> 5;
+    }
+    for (;; w += w_step) {
+    if (w >= w_end) {
+        if (!frame_offsets) break;
+        f += gridDim.x;
+        if (f >= nframes) break;
+        w = frame_offsets[f] + (threadIdx.x >> 5) - w_step; w_end = min(frame_offsets[f + 1], n);
+        continue;
+    }
     const int4 c = coords[w];
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
