@@ -23,9 +23,8 @@ __host__ __device__ inline int ent_stride(int npx) { return (npx + 3) & ~3; }
 // order-independent pixel-content hash: sum over pixels of mix(position, bgr).  Equal windows -> equal hash; used only as a
 // pre-filter of the pop-by-pixel-equality rule (DET:471-477), candidates are always verified byte by byte.
 __device__ __forceinline__ uint32_t pix_hash32(int p, uint32_t bgr) {
-    uint32_t x = (bgr ^ ((uint32_t)p * 0x9E3779B1u)) * 0x85EBCA6Bu;
-    x ^= x >> 15;
-    return x * 0xC2B2AE35u;
+    const uint32_t x = bgr * 0x9E3779B1u + (uint32_t)p * 0x85EBCA6Bu;       // two IMADs; p * K strength-reduces to an add in the pixel loops
+    return x ^ (x >> 15);
 }
 
 // ---- small tables (global memory, L2-resident; staged to shared memory by the kernels that index them per lane)
@@ -329,7 +328,7 @@ __global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
         for (int k = 0; k < C; k++) {
             const int t0 = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
             const int t1 = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
-            v[k] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+            v[k] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;       // (IMAD.HI variant measured slower)
         }
         if (act) {
 #pragma unroll
