@@ -132,6 +132,13 @@ TSD_API int tsd_dedup(tsd_ctx *ctx, const uint8_t *windows, const int32_t *coord
 /* calculateHistAndNormalize (DET/source.py:575-586): float32 [n][50][60] min-max normalised H-S histograms. */
 TSD_API int tsd_hist(tsd_ctx *ctx, const uint8_t *windows, int n, int D, float *hist, int mem);
 
+/* Template builder: the running average of calculateMeanMasks (DET/source.py:44-52).  windows uint8
+ * [n][D][D][3] (class crops already resized with tsd_crop_resize), group_offsets int32 [ngroups+1] (CSR, one group per sign
+ * type, windows in the caller's os.listdir order -- the result depends on it): mean_out [ngroups][D][D][3] = first window,
+ * then cv2.addWeighted(window, .5, mean, .5, 0) for every further one.  Host pointers only. */
+TSD_API int tsd_mean_windows(tsd_ctx *ctx, const uint8_t *windows, const int32_t *group_offsets, int ngroups, int D,
+                             uint8_t *mean_out, int mem);
+
 /* K3  getColorMaskRedOrBlue(img, 'r') and (img, 'b') (DET/source.py:63-89): uint8 [n][D*D] in {0,255} each. */
 TSD_API int tsd_color_masks(tsd_ctx *ctx, const uint8_t *windows, int n, int D, uint8_t *red, uint8_t *blue, int mem);
 /* cv2.cvtColor(BGR2HSV) (DET/source.py:65,576) for npx pixels. */

@@ -12,6 +12,7 @@ Layout
 from . import _capi, synth  # noqa: F401
 from ._capi import DET_DTYPE, HOG_LEN, MEM_DEVICE, MEM_HOST, RUN_DETECT, RUN_RECOGNIZE, TsdError, build  # noqa: F401
 from .engine import Context, default_config, similarity_table  # noqa: F401
+from . import sharding, source_det, source_rec  # noqa: F401,E402
 
 __all__ = ["Context", "default_config", "similarity_table", "TsdError", "build", "DET_DTYPE", "HOG_LEN",
            "RUN_DETECT", "RUN_RECOGNIZE", "MEM_HOST", "MEM_DEVICE", "synth"]

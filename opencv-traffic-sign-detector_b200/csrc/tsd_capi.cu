@@ -786,6 +786,27 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
     return TSD_OK;
 }
 
+int tsd_mean_windows(tsd_ctx* c, const uint8_t* windows, const int32_t* group_offsets, int ngroups, int D, uint8_t* mean_out, int mem) {
+    if (!c || !group_offsets || ngroups < 0 || D < 1 || (ngroups && !mean_out)) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_mean_windows takes host pointers (one-off template building)");
+    CU(cudaSetDevice(c->device));
+    if (ngroups == 0) return TSD_OK;
+    const int n = group_offsets[ngroups], nbytes = D * D * 3;
+    if (n && !windows) return fail(TSD_E_INVALID, "NULL argument");
+    for (int g = 0; g < ngroups; g++)
+        if (group_offsets[g + 1] <= group_offsets[g]) return fail(TSD_E_INVALID, "group %d is empty (the reference would return an all-zero mask; pass at least one window)", g);
+    Stage s(c);
+    void *dw, *dg, *dm;
+    TRY(s.in(windows, (size_t)n * nbytes, &dw));
+    TRY(s.in(group_offsets, (size_t)(ngroups + 1) * 4, &dg));
+    TRY(s.alloc(&dm, (size_t)ngroups * nbytes));
+    mean_windows_kernel<<<ngroups, 32, 0, c->cur>>>((uint8_t*)dw, (int32_t*)dg, ngroups, nbytes, (uint8_t*)dm);
+    TRY(check_launch(c, "mean_windows"));
+    TRY(s.out(mean_out, dm, (size_t)ngroups * nbytes));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
 int tsd_bgr2hsv(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* hsv, int mem) {
     if (!c || npx < 0 || (npx && (!bgr || !hsv))) return fail(TSD_E_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));

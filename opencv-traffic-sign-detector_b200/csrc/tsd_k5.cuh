@@ -504,6 +504,27 @@ __device__ __forceinline__ bool pixels_equal_warp(const uint8_t* a, const uint8_
     return __all_sync(0xffffffffu, eq);
 }
 
+// calculateMeanMasks' running average (DET:44-52): per sign type, mask = first window, then mask = addWeighted(window, .5, mask, .5)
+// for every further window IN ORDER (the result depends on the order: it is the caller's os.listdir order).  One warp per
+// group; the bytes are independent, so each lane folds its own 16-byte chunks through the whole list.  Packed layout.
+__global__ void __launch_bounds__(32) mean_windows_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ group_offsets,
+                                                          int ngroups, int nbytes, uint8_t* __restrict__ mean_out) {
+    const int g = blockIdx.x, lane = threadIdx.x;
+    if (g >= ngroups) return;
+    const int w0 = group_offsets[g], w1 = group_offsets[g + 1];
+    for (int i = lane * 4; i < nbytes; i += 128) {           // 4 bytes per lane per step (packed windows are only 1-byte aligned)
+        const int nb = min(4, nbytes - i);
+        uint32_t m = 0;
+        for (int w = w0; w < w1; w++) {
+            const uint8_t* p = windows + (int64_t)w * nbytes + i;
+            uint32_t v = 0;
+            for (int k = 0; k < nb; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
+            m = (w == w0) ? v : avg_rne4(v, m);
+        }
+        for (int k = 0; k < nb; k++) mean_out[(int64_t)g * nbytes + i + k] = (uint8_t)(m >> (8 * k));
+    }
+}
+
 // pop-by-pixel-equality (DET:183-185,471-477) on the alive bit set A (lane w = items 32w..32w+31, list order = index order):
 // for every marked position p, in increasing order, remove the FIRST alive entry whose pixels equal p's.  Returns new A.
 template <int RMAX, int CAP>

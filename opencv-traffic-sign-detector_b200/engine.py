@@ -275,6 +275,16 @@ class Context:
         check(self._L.tsd_stat_hist_entries(self._h, C.byref(t)))
         return int(t.value)
 
+    def mean_windows(self, windows, group_offsets):
+        """calculateMeanMasks' running average (DET:44-52) per group of windows (CSR offsets, caller's order).
+        -> uint8 [ngroups, D, D, 3]."""
+        windows = _u8(windows); group_offsets = _i32(group_offsets)
+        ng = len(group_offsets) - 1
+        D = windows.shape[1]
+        out = np.zeros((ng, D, D, 3), np.uint8)
+        check(self._L.tsd_mean_windows(self._h, ptr(windows), ptr(group_offsets), ng, D, ptr(out), MEM_HOST))
+        return out
+
     def set_profiling(self, on=True):
         check(self._L.tsd_set_profiling(self._h, int(bool(on))))
 

@@ -54,6 +54,51 @@ def proposals(image, mser):
     return np.asarray(boxes, np.int32).reshape(-1, 4)
 
 
+# ---- template masks -----------------------------------------------------------------------------
+SIGN_GROUPS = (['00', '01', '02', '03', '04', '05', '07', '08', '09', '10', '15', '16'],                       # DET/constants.py:2-7
+               ['11', '18', '19', '20', '21', '22', '23', '24', '25', '26', '27', '28', '29', '30', '31'],
+               ['14'], ['17'], ['13'], ['38'])
+
+
+def meanMasksFromCrops(crops_per_type):
+    """The arithmetic of calculateMeanMasks (DET:24-59) on the GPU: every class crop resized to 25x25 (K2), the
+    order-dependent running average per sign type (tsd_mean_windows), then the red / blue masks of the six mean images
+    (K3).  crops_per_type: 6 lists of BGR uint8 images in the reference's iteration order.
+    -> (signalsMasksRed, signalsMasksBlue, mean6) with the reference's [(mask, name)] * 6 convention."""
+    ctx = context()
+    crops = [np.asarray(c, np.uint8) for t in crops_per_type for c in t]
+    off = np.concatenate([[0], np.cumsum([len(t) for t in crops_per_type])]).astype(np.int32)
+    Hm, Wm = max(c.shape[0] for c in crops), max(c.shape[1] for c in crops)
+    Wm = (Wm + 15) // 16 * 16
+    atlas = np.zeros((len(crops), Hm, Wm, 3), np.uint8)       # one "frame" per crop; the crop is the ROI (0, 0, w, h)
+    coords = np.zeros((len(crops), 4), np.int32)
+    for i, c in enumerate(crops):
+        atlas[i, :c.shape[0], :c.shape[1]] = c
+        coords[i] = (0, 0, c.shape[1], c.shape[0])
+    wins = ctx.crop_resize(atlas, coords, np.arange(len(crops), dtype=np.int32))
+    mean6 = ctx.mean_windows(wins, off)
+    red, blue = ctx.color_masks(mean6)
+    return [(red[k], SIGNALLIST[k]) for k in range(6)], [(blue[k], SIGNALLIST[k]) for k in range(6)], mean6
+
+
+def calculateMeanMasks(train_path=None):
+    """DET:24-59 drop-in: same directory walk (os.listdir order, DET:42-43) and image decode (cv2.imread) as the reference;
+    resize, running average and masks on the GPU."""
+    import cv2
+    if train_path is None:
+        import constants                                       # the reference's module (DET/constants.py), when patched in
+        train_path = constants.TRAIN_PATH
+    crops = []
+    for dirs in SIGN_GROUPS:
+        t = []
+        for d in dirs:
+            for f in os.listdir(train_path + '/' + d):
+                t.append(cv2.imread(train_path + '/' + d + '/' + f))
+        crops.append(t)
+    red, blue, _ = meanMasksFromCrops(crops)
+    return red, blue
+
+
 # ---- K1 -----------------------------------------------------------------------------------------------------------
 def makeWindowBiggerOrDiscardFakeDetections(window, percentage):
     """DET:155-174 -> (x1, y1, x2, y2) Python ints, or None."""
@@ -205,7 +250,7 @@ def createDetectionsStrings(detections):
     return [";".join([d[0]] + [str(v) for v in d[1:]]) for d in detections]
 
 
-_PATCHED = ("makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
+_PATCHED = ("calculateMeanMasks", "makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
             "detectSignsOnDirectory", "calculateHistAndNormalize", "getColorMaskRedOrBlue", "getSimilarSignalType",
             "calculateScoreBetweenMatrixs", "detectionsMaskCorrelation")
 

@@ -192,6 +192,25 @@ def dedup(windows, coords, by_coords, tol, merge_factor=0.8823, stats=None):
     return windows[:m], coords[:m]
 
 
+def mean_masks(crops_per_type, D=25):
+    """calculateMeanMasks (DET/source.py:24-59): per sign type, every crop resized to DxD (cv2.resize INTER_LINEAR, A.2),
+    mask = first crop (addWeighted(img, 1, zeros, 0)), then mask = addWeighted(img, .5, mask, .5) = round-half-even of the mean
+    (A.5 avg_rne) in list order; then the red / blue masks of the mean image (A.3).  -> (red6, blue6, mean6)."""
+    red6, blue6, mean6 = [], [], []
+    for crops in crops_per_type:
+        mask = np.zeros((D, D, 3), np.uint8)
+        for k, c in enumerate(crops):
+            r = resize_linear(np.ascontiguousarray(c, np.uint8), D).astype(np.int32)
+            if k == 0:
+                mask = r.astype(np.uint8)
+            else:
+                s_ = r + mask.astype(np.int32)
+                mask = ((s_ >> 1) + ((s_ & 1) & ((s_ >> 1) & 1))).astype(np.uint8)
+        rm, bm = color_masks(mask)
+        red6.append(rm); blue6.append(bm); mean6.append(mask)
+    return np.stack(red6), np.stack(blue6), np.stack(mean6)
+
+
 # ---- A.6 / A.7 / A.8  REC:388, 519, 565-641, 592-596 -------------------------------------------------------------
 def bgr2gray(bgr):
     bgr = np.ascontiguousarray(bgr, np.uint8)

@@ -30,6 +30,17 @@ def templates():
 
 
 @pytest.fixture(scope="session")
+def det_crops():
+    """The class crops calculateMeanMasks reads, in the reference's iteration order -> 6 lists of BGR images."""
+    g = np.load(os.path.join(GOLDEN, "det_crops.npz"))
+    pix, shapes, off = g["pixels"], g["shapes"], g["type_offsets"]
+    crops, pos = [], 0
+    for h, w in shapes:
+        crops.append(pix[pos:pos + h * w * 3].reshape(h, w, 3)); pos += h * w * 3
+    return [crops[off[t]:off[t + 1]] for t in range(6)]
+
+
+@pytest.fixture(scope="session")
 def det_frames():
     return np.load(os.path.join(GOLDEN, "det_frames.npz"))
 

@@ -5,6 +5,7 @@ consumes the committed fixtures.  Usage:
 
     python tests/golden/make_golden.py det      # detection goldens (about 1 min)
     python tests/golden/make_golden.py rec      # recognition goldens (needs MSERTrain.val: about 7 min first time)
+    python tests/golden/make_golden.py crops    # inputs of calculateMeanMasks (class crops, reference order)
 
 Everything stored here is an output of the reference's own functions (DET/source.py, REC/source.py)
 called through tests/golden/refload.py; the oracle (oracle/) is NOT involved in producing them.
@@ -18,6 +19,7 @@ Files written
                            survivors and final detection tuples (the resultado.txt content)
   det_resultado150.txt     the reference's resultado.txt lines for all 150 frames in sorted file order
   rec_golden.npz           LDA/KNN weights, grey 32x32 windows, HOG descriptors, logits, probabilities, labels
+  det_crops.npz            the 708 class crops calculateMeanMasks reads (decoded BGR), in the reference's iteration order
   rec_frames.npz           recognition-flavour (x1.15, 32x32) window extraction for the stored frames
 """
 import hashlib
@@ -185,8 +187,36 @@ def make_rec(workdir="/tmp/o_rec"):
         os.chdir(cwd)
 
 
+def make_crops():
+    """Inputs of calculateMeanMasks (DET/source.py:24-59): every class crop the reference reads, decoded by cv2.imread, in the
+    reference's own iteration order (constants.* directory lists, os.listdir inside each).  The expected output is
+    det_templates.npz (written by make_det from the reference's calculateMeanMasks in the same container / listdir order);
+    this function re-runs the reference and asserts that it still gives those templates before writing the inputs."""
+    src, const = refload.load_det()
+    _silence_tqdm(src)
+    const.TRAIN_PATH = os.path.join(refload.DET_DIR, "train_jpg")
+    red, blue = src.calculateMeanMasks()
+    g = np.load(os.path.join(HERE, "det_templates.npz"))
+    assert np.array_equal(np.stack([m for m, _ in red]), g["red6"]) and np.array_equal(np.stack([m for m, _ in blue]), g["blue6"])
+    groups = [const.PROHIBICION, const.PELIGRO, const.STOP, const.DIRECCIONPROHIBIDA, const.CEDAPASO, const.DIRECCIONOBLIGATORIA]
+    pix, shapes, off = [], [], [0]
+    for dirs in groups:
+        n = 0
+        for d in dirs:
+            for f in os.listdir(const.TRAIN_PATH + '/' + d):      # same call, same process-independent order as DET:42-43
+                im = cv2.imread(const.TRAIN_PATH + '/' + d + '/' + f)
+                pix.append(im.reshape(-1)); shapes.append(im.shape[:2]); n += 1
+        off.append(off[-1] + n)
+    np.savez_compressed(os.path.join(HERE, "det_crops.npz"), pixels=np.concatenate(pix), shapes=np.array(shapes, np.int32),
+                        type_offsets=np.array(off, np.int32))
+    print("det_crops.npz:", off[-1], "crops", sum(p.size for p in pix), "bytes raw")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "det"
+    if what == "crops":
+        make_crops()
+        sys.exit(0)
     if what in ("det", "all"):
         make_det()
     if what in ("rec", "all"):

@@ -1,0 +1,119 @@
+"""GPU (-m gpu): the drop-in mirrors of the reference's own functions (source_det / source_rec), called the way the
+reference's drivers call them (DET/source.py:611-853 test(), REC/source.py:646-809 testValidation()), against outputs of
+the unmodified reference stored under tests/golden/."""
+import types
+
+import numpy as np
+import pytest
+
+from conftest import STORED
+
+pytestmark = pytest.mark.gpu
+
+
+def _templates_as_reference(templates, names):
+    red6, blue6 = templates
+    return [(red6[k], names[k]) for k in range(6)], [(blue6[k], names[k]) for k in range(6)]
+
+
+def test_detection_functions_like_the_reference_driver(tsd, templates, det_frames, frames3):
+    """detectSignsOnDirectory's per-frame body + the mask-correlation filter of test() (DET:101,708-716) + createDetectionsStrings
+    (DET:501-508) on the three stored real frames: lists of tuples with the reference's exact conventions (Python ints, float
+    score rounded to 2 dp, insertion order), and the resultado.txt lines of those files byte for byte."""
+    import cv2
+    S = tsd.source_det
+    red, blue = _templates_as_reference(templates, S.SIGNALLIST)
+    mser = cv2.MSER_create(delta=7, min_area=200, max_area=2000, max_variation=0.15)     # DET/main.py:28 default detector
+    expected_lines = {}
+    import os
+    for ln in open(os.path.join(os.path.dirname(__file__), "golden", "det_resultado150.txt")).read().splitlines():
+        expected_lines.setdefault(ln.split(";")[0], []).append(ln)
+    for k in STORED:
+        img, file = frames3[k], k + ".jpg"
+        boxes = S.proposals(img, mser)
+        assert np.array_equal(boxes, det_frames[k + "_boxes"])                            # cv2 path unchanged
+        dets = S.MSERTrafficSignDetector(img, mser, file)
+        assert [d[1] for d in dets] == [tuple(int(v) for v in c) for c in det_frames[k + "_p2_coords"]]
+        assert all(isinstance(v, int) for d in dets for v in d[1]) and all(d[2] == file for d in dets)
+        assert np.array_equal(np.stack([d[0] for d in dets]), det_frames[k + "_p2_windows"])
+        out = [S.detectionsMaskCorrelation(d, red, blue, 0.55) for d in dets]
+        out = [o for o in out if o is not None]
+        assert [o[1:5] for o in out] == [tuple(int(v) for v in c) for c in det_frames[k + "_det_coords"]]
+        assert [o[5] for o in out] == [int(v) for v in det_frames[k + "_det_ids"]]
+        assert [o[6] for o in out] == [float(v) for v in det_frames[k + "_det_scores"]]
+        assert S.createDetectionsStrings(out) == expected_lines.get(file, [])
+        # the batched entry point gives the same tuples in one library call
+        b_out, _ = S.detectBatch(img[None], boxes, np.array([0, len(boxes)], np.int32), [file], red, blue)
+        assert b_out == out
+
+
+def test_detection_helpers_like_the_reference(tsd, templates, det_frames, oracle):
+    """makeWindowBiggerOrDiscardFakeDetections, cleanDuplicatedDetections, calculateHistAndNormalize, getColorMaskRedOrBlue,
+    getSimilarSignalType, calculateScoreBetweenMatrixs with the reference's argument and return conventions."""
+    S = tsd.source_det
+    red, blue = _templates_as_reference(templates, S.SIGNALLIST)
+    k = STORED[0]
+    boxes, coords, valid = det_frames[k + "_boxes"], det_frames[k + "_coords"], det_frames[k + "_valid"]
+    for i in range(0, len(boxes), 7):
+        r = S.makeWindowBiggerOrDiscardFakeDetections(boxes[i], 1.30)
+        assert (r is None) == (not valid[i])
+        if r is not None:
+            assert r == tuple(int(v) for v in coords[i]) and all(isinstance(v, int) for v in r)
+    items = [(w, tuple(int(v) for v in c), "f.jpg") for w, c in zip(det_frames[k + "_windows"], coords[valid])]
+    p1 = S.cleanDuplicatedDetections(items, False, 0.85)
+    assert [d[1] for d in p1] == [tuple(int(v) for v in c) for c in det_frames[k + "_p1_coords"]]
+    p2 = S.cleanDuplicatedDetections(p1, True, 0.95)
+    assert [d[1] for d in p2] == [tuple(int(v) for v in c) for c in det_frames[k + "_p2_coords"]]
+    assert S.cleanDuplicatedDetections([], False, 0.85) == []
+    for i, w in enumerate(det_frames[k + "_windows"]):
+        assert np.array_equal(S.calculateHistAndNormalize(w), det_frames[k + "_hists"][i])
+    for i, w in enumerate(det_frames[k + "_p2_windows"]):
+        mr, mb = S.getColorMaskRedOrBlue(w, 'r'), S.getColorMaskRedOrBlue(w, 'b')
+        assert np.array_equal(mr, det_frames[k + "_red"][i]) and np.array_equal(mb, det_frames[k + "_blue"][i])
+        assert S.getColorMaskRedOrBlue(w, 'x') is None                                    # DET:63-89 falls through
+        sc_r, id_r = S.getSimilarSignalType(mr, red)
+        sc_b, id_b = S.getSimilarSignalType(mb, blue)
+        exp = det_frames[k + "_scores"][i]                                                # [2][6] per-template scores of the reference
+        assert sc_r == float(max(exp[0])) and id_r == int(np.argmax(exp[0])) + 1
+        assert sc_b == float(max(exp[1])) and id_b == int(np.argmax(exp[1])) + 1
+        for t in range(6):
+            m1 = mr * red[t][0]                                                           # uint8 wrap-around product, DET:254
+            got = S.calculateScoreBetweenMatrixs(m1, red[t][0])
+            assert got == (0 if int((red[t][0] == 255).sum()) <= 6 else float(exp[0][t]))
+    assert S.calculateScoreBetweenMatrixs(np.zeros((25, 25), np.uint8), np.zeros((24, 25), np.uint8)) is None
+
+
+def test_recognition_functions_like_the_reference_driver(tsd, rec_golden, rec_frames, frames3):
+    """computeDescriptors / calculateDescriptors / predictProbability (REC:507-521,619-624) with stand-ins for the fitted
+    scikit-learn objects that carry exactly the attributes the reference's code path reads."""
+    import cv2
+    R = tsd.source_rec
+    g = rec_golden
+    n = 200
+    hog_desc = (None, 'HOG')
+    d0 = R.computeDescriptors(g["gray"][0], hog_desc)
+    assert d0.dtype == np.float32 and d0.shape == (324,)
+    assert np.max(np.abs(d0 - g["hog"][0]) / np.maximum(np.abs(g["hog"][0]), 1e-2)) < 1e-4
+    assert np.array_equal(R.computeDescriptors(g["gray"][0], (None, 'GRAY')), g["gray"][0].ravel())
+    data = {t: [] for t in range(7)}
+    for i in range(n):
+        data[int(g["true"][i])].append((g["gray"][i], (0, 0, 32, 32), "f.jpg", int(g["true"][i])))
+    desc = R.calculateDescriptors(data, hog_desc)
+    flat = [d for t in range(7) for d in desc[t]]
+    order = [i for t in range(7) for i in range(n) if int(g["true"][i]) == t]
+    lda = [types.SimpleNamespace(coef_=g["lda_W"][:, c][None, :], intercept_=np.array([g["lda_b"][c]])) for c in range(6)]
+    pred, true = R.predictProbability((lda, 'LDABAYES'), None, flat, 0.5)
+    assert pred == [int(g["pred_lda"][i]) for i in order] and true == [int(g["true"][i]) for i in order]
+    knn = types.SimpleNamespace(_fit_X=g["knn_Ztrain"], classes_=np.arange(7), _y=g["knn_ytrain"].astype(np.int64), n_neighbors=4)
+    reducer = (types.SimpleNamespace(xbar_=g["knn_xbar"], scalings_=g["knn_scalings"]),)
+    pred_k, true_k = R.predictProbability((knn, 'KNN'), reducer, flat, 0.5)
+    assert [int(v) for v in pred_k] == [int(g["pred_knn"][i]) for i in order]
+    # window extraction of the recognition flavour (x1.15, 32x32, 4-tuples with the label slot) on a real frame
+    k = STORED[0]
+    mser = cv2.MSER_create(delta=7, min_area=200, max_area=2000, max_variation=1.0)      # REC/main.py:44 default detector
+    dets = R.MSERTrafficSignDetector(frames3[k], mser, k + ".jpg")
+    assert all(len(d) == 4 and d[3] == 0 and d[0].shape == (32, 32, 3) for d in dets)
+    assert [d[1] for d in dets] == [tuple(int(v) for v in c) for c in rec_frames[k + "_coords"]]
+    assert np.array_equal(np.stack([d[0] for d in dets]), rec_frames[k + "_windows"])
+    gray = R.windowsToGray(dets)
+    assert np.array_equal(np.stack([d[0] for d in gray]), rec_frames[k + "_gray"])

@@ -245,6 +245,16 @@ def test_k5_dedup_large_frames(ctx_det, oracle):
             assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (by_coords, f)
 
 
+def test_template_builder_golden(tsd, det_crops, templates, oracle):
+    """calculateMeanMasks on the GPU (K2 on every class crop, order-dependent running average, K3) gives the
+    reference's 6 + 6 template masks bit for bit; the mean images equal the oracle's."""
+    red6, blue6 = templates
+    red, blue, mean6 = tsd.source_det.meanMasksFromCrops(det_crops)
+    assert np.array_equal(np.stack([m for m, _ in red]), red6) and np.array_equal(np.stack([m for m, _ in blue]), blue6)
+    assert [n for _, n in red] == tsd.source_det.SIGNALLIST
+    assert np.array_equal(mean6, oracle.mean_masks(det_crops)[2])
+
+
 # ---- whole chain ------------------------------------------------------------------------------------------------------
 def _records(det):
     return [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
