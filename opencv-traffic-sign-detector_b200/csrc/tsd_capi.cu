@@ -88,6 +88,8 @@ struct tsd_ctx {
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
     int pairs_variant = 24;
+    int hist_minb = 1;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
+    int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
     int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
                                              // consecutive windows: measured slower (0.45 vs 0.27 ms device, 19.1 vs 16.5 ms zero-copy e2e)
     int k2_grid_limit = 0;                   // > 0: persistent K2 with at most this many CTAs (host-memory frames, PCIe-bound)
@@ -207,6 +209,8 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("TSD_HIST_MINB"); if (e) c->hist_minb = atoi(e); }
+    { const char* e = getenv("TSD_K2_MINB"); if (e) c->k2_minb = atoi(e); }
     { const char* e = getenv("TSD_K2_BY_FRAME"); if (e) c->k2_by_frame = atoi(e); }
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
@@ -492,10 +496,10 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
+    else if (ch == 3 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
+    else if (ch == 3 && D == 32) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 32, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 32, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 32, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
+    else if (ch == 1 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<1, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<1, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<1, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
+    else if (ch == 1 && D == 32) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<1, 32, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<1, 32, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<1, 32, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
     else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
     else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
@@ -525,11 +529,13 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
     if (npx <= 640) {
         int grid = cdiv(n_max, 4);
         if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k5_hist_kernel<640, 4><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        if (c->hist_minb == 8) k5_hist_kernel<640, 4, 8><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        else if (c->hist_minb == 10) k5_hist_kernel<640, 4, 10><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        else k5_hist_kernel<640, 4, 1><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     } else {
         int grid = cdiv(n_max, 3);
         if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        k5_hist_kernel<1024, 3><<<grid, 96, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<1024, 3, 1><<<grid, 96, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     }
     return check_launch(c, "k5_hist");
 }

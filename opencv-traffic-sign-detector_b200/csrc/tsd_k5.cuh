@@ -177,8 +177,8 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     return nnz;
 }
 
-template <int CAP, int kHistWarps>      // warps per CTA: 4 for D=25, 3 for D=32 (static shared memory <= 48 KB)
-__global__ void __launch_bounds__(kHistWarps * 32) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
+template <int CAP, int kHistWarps, int MINB>      // warps per CTA: 4 for D=25, 3 for D=32 (static shared memory <= 48 KB)
+__global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
                                                                   int n_max, int npx, int ws, int es, const Tables* __restrict__ tab,
                                                                   uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
                                                                   float* __restrict__ E_T, int64_t e_stride) {

@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 // byte-iteration).  One warp per window, lane = destination column; the x coefficients live in registers, the y
 // coefficients are computed by lane dy and broadcast by shuffle; each lane walks the D destination rows and reads its
 // 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
-template <int C, int D>
-__global__ void __launch_bounds__(128) k2_crop_resize_v2_kernel(
+template <int C, int D, int MINB>
+__global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
     uint8_t* __restrict__ windows, int out_stride, const int32_t* __restrict__ frame_offsets, int nframes) {
