@@ -207,6 +207,66 @@ def cpu_baseline_sample(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def _time_steps(torch, stream, ctx, fn, steps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    ctx.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_runs(torch, tsd_b200, dev, local_rank, ctx_det, stream_det):
+    """Two more device-resident measurements, reported beside the headline (not bench lines of their own):
+    (1) the recognition flavour of the chain (K1 K2 K5 K6 K7 K8, x1.15 / 32x32, BASELINE configs[3]) on 1024 synthetic
+        frames with the LDA weights fitted by the reference (tests/golden/rec_golden.npz);
+    (2) the detection chain on REAL frames with REAL cv2.MSER boxes: the three stored test frames and the
+        boxes the reference's MSER produced for them, tiled to 1024 frames."""
+    out = {}
+    F = 1024
+    try:
+        uniq = tsd_b200.synth.make_frames(16)
+        boxes, off = tsd_b200.synth.make_boxes(F, NBOX)
+        d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(F, device=dev) % 16].contiguous()
+        d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+        r = np.load(os.path.join(ROOT, "tests", "golden", "rec_golden.npz"))
+        with tsd_b200.Context(device=local_rank, flavour="rec") as rc:
+            rc.set_lda(r["lda_W"], r["lda_b"])
+            st = torch.cuda.ExternalStream(rc.stream, device=dev)
+            ms = _time_steps(torch, st, rc, lambda: rc.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]),
+                                                                      mode=tsd_b200.RUN_RECOGNIZE, max_boxes_per_frame=NBOX))
+            _, cnt = rc.fetch_detections(int(off[-1]))
+        out["recognize_chain"] = {"windows_per_s": F * NBOX / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms, "frames": F,
+                                  "stage_counts": [int(v) for v in cnt], "config": "synthetic 1360x800, 200 candidates/frame, x1.15 / 32x32, HOG + 6 LDA (f64)"}
+        del d_frames
+    except Exception as e:                                   # secondary numbers never break the bench line
+        out["recognize_chain"] = {"error": str(e)[:200]}
+    try:
+        import cv2
+        g = np.load(os.path.join(ROOT, "tests", "golden", "det_frames.npz"))
+        names = ["00604", "00639", "00719"]
+        imgs = np.stack([cv2.imread(os.path.join(ROOT, "tests", "golden", "det_frame_%s.png" % k)) for k in names])
+        bl = [g[k + "_boxes"].astype(np.int32) for k in names]
+        boxes = np.concatenate([bl[f % 3] for f in range(F)])
+        off = np.concatenate([[0], np.cumsum([len(bl[f % 3]) for f in range(F)])]).astype(np.int32)
+        d_frames = torch.from_numpy(imgs).to(dev)[torch.arange(F, device=dev) % 3].contiguous()
+        d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+        mb = int(max(len(b) for b in bl))
+        ms = _time_steps(torch, stream_det, ctx_det, lambda: ctx_det.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]),
+                                                                                    max_boxes_per_frame=mb))
+        _, cnt = ctx_det.fetch_detections(int(off[-1]))
+        out["real_mser_frames"] = {"windows_per_s": int(off[-1]) / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms, "frames": F,
+                                   "boxes_per_frame_mean": float(off[-1]) / F, "stage_counts": [int(v) for v in cnt],
+                                   "config": "3 real GTSDB test frames + the boxes cv2.MSER(7,200,2000,0.15) gives for them, tiled to 1024 frames"}
+    except Exception as e:
+        out["real_mser_frames"] = {"error": str(e)[:200]}
+    return out
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Pin this process (and so the first-touch placement of its page-locked host frames) to the CPUs of the NUMA node
     the GPU hangs off: the e2e leg reads host memory from the GPU, a remote node costs PCIe/UPI bandwidth.  Best effort."""
@@ -358,6 +418,9 @@ def run_b200(args, rank, world, local_rank):
                   "(only candidate ROIs cross the bus), boxes H2D, detection records D2H; h2d_bytes_per_step counts the whole "
                   "host input (frames + boxes) the call consumes"}
 
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = secondary_runs(torch, tsd_b200, dev, local_rank, ctx, stream)
     if rank == 0:
         peak, peak_src = load_peaks()
         alg, npass = algorithmic_bytes(boxes, off, counts, hist_entries, (NBOX + 31) // 32)
@@ -388,6 +451,8 @@ def run_b200(args, rank, world, local_rank):
         }
         if cpu_base is not None:
             out["cpu_baseline"] = cpu_base
+        if secondary is not None:
+            out["secondary"] = secondary
         print(json.dumps(out))
     ctx.close()
     if dist is not None:
@@ -406,6 +471,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (recognition chain, real-MSER frames) measurements")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used for the ncu launch list of the device-resident step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
