@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(128) k4_score_bits_kernel(const uint32_t* __re
 // Per-window sparse H-S histogram record (calculateHistAndNormalize DET:575-586):
 //   entries (bin << 16 | count), sorted by bin; a = (float)(1/max) ; h[bin] = (float)count * a  (min is always 0
 //   because npx <= 1024 < 3000 bins, so the MINMAX shift is +0);  s1 = sum h, s11 = sum h^2 in f64;
-//   hash = 64-bit hash of the pixels (used only to pre-filter the pop-by-pixel-equality rule DET:471-477).
+//   hash = 32-bit order-independent hash of the pixels (pix_hash32 sum; only pre-filters the pop-by-pixel-equality rule DET:471-477).
 // =====================================================================================================
 struct __align__(16) WinMeta {
     double s1, s11;              // sum h, sum h^2 over the 3000 bins (f64)

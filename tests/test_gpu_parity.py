@@ -275,9 +275,10 @@ def test_chain_golden_frames(ctx_det, det_frames, frames3):
 
 
 def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
-    """BASELINE config 3 shape (1360x800, 200 candidates/frame) on 64 frames, plus a 4K frame with 500 candidates."""
+    """BASELINE config 3 shape (1360x800, 200 candidates/frame) on 64 frames, plus 4K frames with 500 and 2000 candidates
+    (BASELINE config 5 sweep ends: ~800 windows per frame after the aspect filter, the 1024-window fold variant)."""
     red6, blue6 = templates
-    for (H, W, F, N) in ((800, 1360, 64, 200), (2160, 3840, 1, 500)):
+    for (H, W, F, N) in ((800, 1360, 64, 200), (2160, 3840, 1, 500), (2160, 3840, 2, 2000)):
         frames = tsd.synth.make_frames(F, H, W)
         boxes, off = tsd.synth.make_boxes(F, N, H, W)
         det, counts = ctx_det.detect_frames(frames, boxes, off)
