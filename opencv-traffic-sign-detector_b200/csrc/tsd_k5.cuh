@@ -284,6 +284,45 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         int Ik = 0;
+        if (G == 1) {
+            // One pair per pipeline stage, two stages in flight (ping-pong registers, no copies): every lane loads 2 x 4
+            // consecutive entries (128-bit) of the pair, i.e. one stage covers 256 entries -- most windows -- with both
+            // loads issued a full stage before they are consumed.  The kernel is bound by the latency of these loads.
+            const uint4* ent4 = reinterpret_cast<const uint4*>(entries) + (int64_t)(base + i0) * (es >> 2);
+            const int es4 = es >> 2;
+            int kA, nA, kB, nB;
+            const uint4 *eA, *eB;
+            uint4 a0, a1, b0, b1;
+#define PAIR_FETCH(K, N, E, V0, V1)                                                                          \
+            do {                                                                                             \
+                K = todo ? __ffs(todo) - 1 : -1;                                                             \
+                todo &= todo - 1;                                                                            \
+                N = K >= 0 ? (__shfl_sync(0xffffffffu, mi.nnz, K & 31) + 3) >> 2 : 0;                        \
+                E = ent4 + (int64_t)(K & 31) * es4;                                                          \
+                V0 = lane < N ? __ldg(E + lane) : make_uint4(0, 0, 0, 0);                                    \
+                V1 = lane + 32 < N ? __ldg(E + lane + 32) : make_uint4(0, 0, 0, 0);                          \
+            } while (0)
+#define PAIR_DOT(V) ((int)dense[(V).x >> 16] * (int)((V).x & 0xffffu) + (int)dense[(V).y >> 16] * (int)((V).y & 0xffffu) + \
+                     (int)dense[(V).z >> 16] * (int)((V).z & 0xffffu) + (int)dense[(V).w >> 16] * (int)((V).w & 0xffffu))
+#define PAIR_COMPUTE(K, N, E, V0, V1)                                                                        \
+            do {                                                                                             \
+                int acc = PAIR_DOT(V0) + PAIR_DOT(V1);                                                       \
+                for (int e = lane + 64; e < N; e += 32) { const uint4 v = __ldg(E + e); acc += PAIR_DOT(v); } \
+                acc = warp_sum_i(acc);                                                                       \
+                if (lane == K) Ik = acc;                                                                     \
+            } while (0)
+            PAIR_FETCH(kA, nA, eA, a0, a1);
+            while (kA >= 0) {
+                PAIR_FETCH(kB, nB, eB, b0, b1);
+                PAIR_COMPUTE(kA, nA, eA, a0, a1);
+                if (kB < 0) break;
+                PAIR_FETCH(kA, nA, eA, a0, a1);
+                PAIR_COMPUTE(kB, nB, eB, b0, b1);
+            }
+#undef PAIR_FETCH
+#undef PAIR_DOT
+#undef PAIR_COMPUTE
+        } else {
         // Groups of up to G pairs; every lane loads 4 consecutive entries (128-bit) of each pair, so one load instruction
         // covers 128 entries per pair.  The first loads of group g+1 are issued BEFORE group g is reduced (software
         // pipelining across groups): the kernel is bound by the latency of these loads, not by their bandwidth.
@@ -337,6 +376,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
                 kc[u] = kn[u]; nc[u] = nn[u]; ec[u] = en[u]; vc[u] = vn[u];
             }
             have = have_next;
+        }
         }
         if (need) c = classify_from_int(Ik, mj, mi, tol, lo);
         unsigned unsure = __ballot_sync(0xffffffffu, need && c == kClsUnsure);
