@@ -132,6 +132,15 @@ TSD_API int tsd_dedup(tsd_ctx *ctx, const uint8_t *windows, const int32_t *coord
 /* calculateHistAndNormalize (DET/source.py:575-586): float32 [n][50][60] min-max normalised H-S histograms. */
 TSD_API int tsd_hist(tsd_ctx *ctx, const uint8_t *windows, int n, int D, float *hist, int mem);
 
+/* Proposal pre-processing: grayAndEnhanceContrast (DET/source.py:135-152 = REC/source.py:67-84) for a
+ * batch of frames: cv2.cvtColor(BGR2GRAY) -> cv2.createCLAHE(clipLimit, (tiles_x, tiles_y)).apply -> cv2.GaussianBlur((3,3), 0) ->
+ * cv2.LUT(gamma table).  out uint8 [nframes][H][W] is what the reference hands to cv2.MSER.detectRegions (which stays on cv2).
+ * The reference uses clip_limit = 2, tiles 8 x 8.  tsd_set_gamma_table replaces the default gammaCorrection(src, 2) table
+ * (DET/source.py:599-605) with the caller's 256 bytes. */
+TSD_API int tsd_set_gamma_table(tsd_ctx *ctx, const uint8_t *table256);
+TSD_API int tsd_preprocess(tsd_ctx *ctx, const uint8_t *frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                           double clip_limit, int tiles_x, int tiles_y, uint8_t *out, int mem);
+
 /* Template builder: the running average of calculateMeanMasks (DET/source.py:44-52).  windows uint8
  * [n][D][D][3] (class crops already resized with tsd_crop_resize), group_offsets int32 [ngroups+1] (CSR, one group per sign
  * type, windows in the caller's os.listdir order -- the result depends on it): mean_out [ngroups][D][D][3] = first window,

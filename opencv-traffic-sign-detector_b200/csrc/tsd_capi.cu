@@ -71,6 +71,8 @@ struct tsd_ctx {
     // constant state
     Tables* d_tab = nullptr;
     ScoreTemplates* d_tmpl = nullptr;
+    uint8_t* d_gamma = nullptr;              // gammaCorrection table (DET:599-605), 256 bytes
+    DevBuf b_pgray, b_pluts, b_pin, b_pout;  // pre-processing scratch
     MaskLut* d_mlut = nullptr;               // inRange bounds of tsd_config as per-channel flag tables (K3)
     bool have_templates = false;
     int tmpl_D = 0;
@@ -230,6 +232,13 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     CU(cudaMalloc(&c->d_tab, sizeof(Tables)));
     CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tmpl, sizeof(ScoreTemplates)));
+    {   // default gamma table: ((i / 255) ** (1 / 2)) * 255 truncated to uint8 (DET:602-603); the Python wrapper overrides it with the
+        // table the reference's own expression gives in-process
+        uint8_t gt[256];
+        for (int i = 0; i < 256; i++) gt[i] = (uint8_t)(pow(i / 255.0, 1.0 / 2.0) * 255.0);
+        CU(cudaMalloc(&c->d_gamma, 256));
+        CU(cudaMemcpy(c->d_gamma, gt, 256, cudaMemcpyHostToDevice));
+    }
     {   // K3 flag tables: bit 0 / 1 = red band 0 / 1, bit 2 = blue (DET:70-86 bounds from the config)
         MaskLut ml;
         const tsd_config& g = c->cfg;
@@ -279,14 +288,14 @@ int tsd_destroy(tsd_ctx* c) {
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order};
+    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
     for (DevBuf* b : more) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_mlut, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -791,6 +800,52 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
                                                     npx, nullptr);       // public layout: packed windows and masks
     TRY(check_launch(c, "k3_masks"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
+    return TSD_OK;
+}
+
+int tsd_set_gamma_table(tsd_ctx* c, const uint8_t* table256) {
+    if (!c || !table256) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_gamma, table256, 256, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int tsd_preprocess(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride, double clip_limit,
+                   int tiles_x, int tiles_y, uint8_t* out, int mem) {
+    if (!c || !frames || !out || nframes < 1 || H < 1 || W < 1 || tiles_x < 1 || tiles_y < 1 || tiles_x * tiles_y > 65535)
+        return fail(TSD_E_INVALID, "bad argument");
+    if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
+    CU(cudaSetDevice(c->device));
+    // OpenCV clahe.cpp: if EITHER size is not a multiple of the grid both are extended (BORDER_REFLECT_101) by tiles - size % tiles
+    const bool divisible = H % tiles_y == 0 && W % tiles_x == 0;
+    const int He = divisible ? H : H + tiles_y - H % tiles_y, We = divisible ? W : W + tiles_x - W % tiles_x;
+    const int tw = We / tiles_x, th = He / tiles_y, total = tw * th;
+    const float lut_scale = 255.0f / (float)total;
+    int clip = 0;
+    if (clip_limit > 0.0) { clip = (int)(clip_limit * total / 256); if (clip < 1) clip = 1; }
+    const size_t npix = (size_t)nframes * H * W;
+    TRY(ensure(c, c->b_pgray, npix));
+    TRY(ensure(c, c->b_pluts, (size_t)nframes * tiles_x * tiles_y * 256));
+    const uint8_t* d_in = frames;
+    uint8_t* d_out = out;
+    if (mem == TSD_MEM_HOST) {
+        const size_t in_bytes = (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3;
+        TRY(ensure(c, c->b_pin, in_bytes));
+        TRY(ensure(c, c->b_pout, npix));
+        CU(cudaMemcpyAsync(c->b_pin.p, frames, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_in = (const uint8_t*)c->b_pin.p; d_out = (uint8_t*)c->b_pout.p;
+    }
+    pre_gray_lut_kernel<<<dim3(tiles_x * tiles_y, nframes), 256, 0, c->cur>>>(d_in, H, W, row_stride, frame_stride, tiles_x, tiles_y, tw, th, clip, lut_scale,
+                                                                               (uint8_t*)c->b_pgray.p, (uint8_t*)c->b_pluts.p);
+    TRY(check_launch(c, "pre_gray_lut"));
+    pre_clahe_blur_kernel<<<dim3(cdiv(W, kPreTW), cdiv(H, kPreTH), nframes), 256, 0, c->cur>>>((uint8_t*)c->b_pgray.p, (uint8_t*)c->b_pluts.p, H, W, tiles_x, tiles_y,
+                                                                                                  1.0f / (float)tw, 1.0f / (float)th, c->d_gamma, d_out);
+    TRY(check_launch(c, "pre_clahe_blur"));
+    if (mem == TSD_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, npix, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
     return TSD_OK;
 }
 

@@ -1229,6 +1229,114 @@ __global__ void k6_gray_kernel(const uint8_t* __restrict__ windows, const int32_
 }
 
 // =====================================================================================================
+// N1  grayAndEnhanceContrast (DET:135-152 = REC:67-84): BGR2GRAY -> CLAHE(clip 2, 8x8 tiles) -> GaussianBlur 3x3 -> gamma LUT.
+// The proposal pre-processing that feeds cv2.MSER.  Two kernels:
+//   pre_gray_lut   : one CTA per (tile, frame): grey conversion of the tile (written out), its 256-bin histogram in shared
+//                    memory, clip + redistribution + cumulative sum -> the tile's 256-entry LUT (OpenCV clahe.cpp, including
+//                    the BORDER_REFLECT_101 extension of images that are not a multiple of the grid).
+//   pre_clahe_blur : one CTA per 64x16 output pixels: the CLAHE value (float bilinear blend of 4 tile LUTs, OpenCV's exact
+//                    operation order, no FMA) of the tile + 1-pixel halo into shared memory, then the exact (1 2 1)x(1 2 1)/16
+//                    blur with round-half-up and the gamma table.
+// =====================================================================================================
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) pre_gray_lut_kernel(const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+                                                           int tiles_x, int tiles_y, int tw, int th, int clip, float lut_scale,
+                                                           uint8_t* __restrict__ gray, uint8_t* __restrict__ luts) {
+    __shared__ int s_hist[256];
+    __shared__ int s_part[8];
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const uint8_t* __restrict__ fr = frames + (int64_t)f * frame_stride;
+    uint8_t* __restrict__ go = gray + (int64_t)f * H * W;
+    s_hist[tid] = 0;
+    __syncthreads();
+    for (int r = wid; r < th; r += 8) {
+        const int ye = ty * th + r, y = reflect101(ye, H);
+        const uint8_t* __restrict__ row = fr + (int64_t)y * row_stride;
+        for (int cidx = lane; cidx < tw; cidx += 32) {
+            const int xe = tx * tw + cidx, x = reflect101(xe, W);
+            const int g = (3735 * __ldg(row + 3 * x) + 19235 * __ldg(row + 3 * x + 1) + 9798 * __ldg(row + 3 * x + 2) + 16384) >> 15;   // A.6
+            atomicAdd(&s_hist[g], 1);
+            if (ye < H && xe < W) go[(int64_t)ye * W + xe] = (uint8_t)g;
+        }
+    }
+    __syncthreads();
+    int h = s_hist[tid];
+    if (clip > 0) {
+        int excess = h > clip ? h - clip : 0;
+        h = h > clip ? clip : h;
+        int e = warp_sum_i(excess);
+        if (lane == 0) s_part[wid] = e;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) clipped += s_part[k];
+        const int batch = clipped >> 8, residual = clipped - (batch << 8);
+        h += batch;
+        if (residual != 0) {
+            int step = 256 / residual; if (step < 1) step = 1;
+            if (tid % step == 0 && tid / step < residual) h++;       // bins 0, step, 2 step, ... get one more each
+        }
+        __syncthreads();
+    }
+    // inclusive scan over the 256 bins
+    int x = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y2 = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y2; }
+    if (lane == 31) s_part[wid] = x;
+    __syncthreads();
+    int pre = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < wid) pre += s_part[k];
+    const int sum = pre + x;
+    int v = __float2int_rn(__fmul_rn((float)sum, lut_scale));
+    v = v < 0 ? 0 : v > 255 ? 255 : v;
+    luts[((int64_t)f * tiles_x * tiles_y + tile) * 256 + tid] = (uint8_t)v;
+}
+
+constexpr int kPreTW = 64, kPreTH = 16;
+__global__ void __launch_bounds__(256) pre_clahe_blur_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ luts, int H, int W,
+                                                             int tiles_x, int tiles_y, float inv_tw, float inv_th,
+                                                             const uint8_t* __restrict__ gamma, uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_c[(kPreTH + 2) * (kPreTW + 2)];
+    __shared__ uint8_t s_gamma[256];
+    const int f = blockIdx.z, x0 = blockIdx.x * kPreTW, y0 = blockIdx.y * kPreTH, tid = threadIdx.x;
+    s_gamma[tid] = gamma[tid];
+    const uint8_t* __restrict__ g = gray + (int64_t)f * H * W;
+    const uint8_t* __restrict__ L = luts + (int64_t)f * tiles_x * tiles_y * 256;
+    for (int i = tid; i < (kPreTH + 2) * (kPreTW + 2); i += 256) {
+        const int yy = i / (kPreTW + 2), xx = i - yy * (kPreTW + 2);
+        const int y = reflect101(min(y0 - 1 + yy, H), H), x = reflect101(min(x0 - 1 + xx, W), W);   // (min: keeps out-of-range halo of edge tiles cheap)
+        const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f), txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+        int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
+        const float ya = __fsub_rn(tyf, (float)ty1), xa = __fsub_rn(txf, (float)tx1);
+        const float ya1 = __fsub_rn(1.0f, ya), xa1 = __fsub_rn(1.0f, xa);
+        int ty2 = min(ty1 + 1, tiles_y - 1), tx2 = min(tx1 + 1, tiles_x - 1);
+        ty1 = max(ty1, 0); tx1 = max(tx1, 0);
+        const int v = __ldg(g + (int64_t)y * W + x);
+        const float l11 = (float)__ldg(L + (ty1 * tiles_x + tx1) * 256 + v), l12 = (float)__ldg(L + (ty1 * tiles_x + tx2) * 256 + v);
+        const float l21 = (float)__ldg(L + (ty2 * tiles_x + tx1) * 256 + v), l22 = (float)__ldg(L + (ty2 * tiles_x + tx2) * 256 + v);
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        int r = __float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya)));
+        s_c[i] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+    }
+    __syncthreads();
+    for (int i = tid; i < kPreTH * kPreTW; i += 256) {
+        const int yy = i / kPreTW, xx = i - yy * kPreTW, y = y0 + yy, x = x0 + xx;
+        if (y >= H || x >= W) continue;
+        const uint8_t* c = s_c + yy * (kPreTW + 2) + xx;     // top-left of the 3x3 neighbourhood
+        const int s = c[0] + 2 * c[1] + c[2] + 2 * c[kPreTW + 2] + 4 * c[kPreTW + 3] + 2 * c[kPreTW + 4] +
+                      c[2 * (kPreTW + 2)] + 2 * c[2 * (kPreTW + 2) + 1] + c[2 * (kPreTW + 2) + 2];
+        out[(int64_t)f * H * W + (int64_t)y * W + x] = s_gamma[(s + 8) >> 4];
+    }
+}
+
+// =====================================================================================================
 // K7  cv2.HOGDescriptor((32,32),(16,16),(8,8),(8,8),9,signed).compute  (REC:487-494,519), SURVEY A.7.
 // One warp per window.  Gradient votes are staged in shared memory; each (block, cell, bin) accumulator has a
 // FIXED owner lane that walks the block's pixels in raster order -> no float atomics, bit-reproducible runs.

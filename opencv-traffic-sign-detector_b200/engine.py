@@ -275,6 +275,23 @@ class Context:
         check(self._L.tsd_stat_hist_entries(self._h, C.byref(t)))
         return int(t.value)
 
+    def preprocess(self, frames, clip_limit=2.0, tiles=(8, 8), gamma=2):
+        """grayAndEnhanceContrast (DET:135-152) for a batch: BGR2GRAY -> CLAHE -> GaussianBlur 3x3 -> gamma LUT.
+        frames uint8 [F,H,W,3] or [H,W,3] -> uint8 [F,H,W] (or [H,W])."""
+        frames = _u8(frames)
+        single = frames.ndim == 3
+        if single:
+            frames = frames[None]
+        F, H, W = frames.shape[:3]
+        if getattr(self, "_gamma", None) != gamma:
+            inv = 1 / gamma
+            table = np.array([((i / 255) ** inv) * 255 for i in range(256)], np.uint8)      # the reference's own expression (DET:602-603)
+            check(self._L.tsd_set_gamma_table(self._h, ptr(table)))
+            self._gamma = gamma
+        out = np.empty((F, H, W), np.uint8)
+        check(self._L.tsd_preprocess(self._h, ptr(frames), F, H, W, W * 3, H * W * 3, float(clip_limit), int(tiles[0]), int(tiles[1]), ptr(out), MEM_HOST))
+        return out[0] if single else out
+
     def mean_windows(self, windows, group_offsets):
         """calculateMeanMasks' running average (DET:44-52) per group of windows (CSR offsets, caller's order).
         -> uint8 [ngroups, D, D, 3]."""

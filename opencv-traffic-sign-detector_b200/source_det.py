@@ -37,19 +37,22 @@ def _use_templates(signalsMasksRed, signalsMasksBlue):
         _templates_key = key
 
 
-# ---- proposal stage (stays on the reference's cv2 path by north_star) ---------------------------------------------
+# ---- proposal stage ---------------------------------------------------------------------------------------------------
 def grayAndEnhanceContrast(image):
-    """DET:135-152 -- cv2 CPU pre-processing feeding MSER (out of scope for the kernels)."""
-    import cv2
-    gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
-    eq = cv2.createCLAHE(clipLimit=2).apply(gray)
-    blur = cv2.GaussianBlur(eq, (3, 3), 0)
-    table = np.array([((i / 255) ** (1 / 2)) * 255 for i in range(256)], np.uint8)   # gammaCorrection(src, 2), DET:599-605
-    return cv2.LUT(blur, table)
+    """DET:135-152 -- the pre-processing that feeds MSER, on the GPU: BGR2GRAY, CLAHE(clip 2, 8x8), Gaussian
+    3x3 and the gamma-2 table, bit-identical to the four cv2 calls of the reference."""
+    return context().preprocess(np.asarray(image, np.uint8))
+
+
+def gammaCorrection(src, gamma):
+    """DET:599-605 (a 256-entry table lookup; host-side numpy, kept for callers that use it on its own)."""
+    table = np.array([((i / 255) ** (1 / gamma)) * 255 for i in range(256)], np.uint8)
+    return table[np.asarray(src, np.uint8)]
 
 
 def proposals(image, mser):
-    """int32 [n,4] (x,y,w,h) MSER boxes exactly as DET:112-114 produces them."""
+    """int32 [n,4] (x,y,w,h) MSER boxes exactly as DET:112-114 produces them: GPU pre-processing, then cv2's MSER (which stays
+    on the reference's cv2 path by north_star)."""
     boxes = mser.detectRegions(grayAndEnhanceContrast(image))[1]
     return np.asarray(boxes, np.int32).reshape(-1, 4)
 
@@ -250,7 +253,7 @@ def createDetectionsStrings(detections):
     return [";".join([d[0]] + [str(v) for v in d[1:]]) for d in detections]
 
 
-_PATCHED = ("calculateMeanMasks", "makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
+_PATCHED = ("calculateMeanMasks", "grayAndEnhanceContrast", "makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
             "detectSignsOnDirectory", "calculateHistAndNormalize", "getColorMaskRedOrBlue", "getSimilarSignalType",
             "calculateScoreBetweenMatrixs", "detectionsMaskCorrelation")
 

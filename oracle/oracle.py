@@ -62,6 +62,9 @@ def lib():
         L.orc_dedup.argtypes = [_u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.orc_dedup.restype = C.c_int
         L.orc_bgr2gray.argtypes = [_u8p, C.c_int, _u8p]
+        L.orc_clahe.argtypes = [_u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _u8p]
+        L.orc_gauss3.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        L.orc_preprocess.argtypes = [_u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _u8p, _u8p]
         L.orc_hog_32.argtypes = [_u8p, _f32p]
         L.orc_lda_predict.argtypes = [_f32p, C.c_int, C.c_int, _f64p, _f64p, C.c_double, _f64p, _i32p]
         L.orc_knn_predict.argtypes = [_f32p, C.c_int, C.c_int, _f64p, _f64p, _f64p, _i32p, C.c_int, C.c_int, _f64p, _i32p]
@@ -216,6 +219,35 @@ def bgr2gray(bgr):
     bgr = np.ascontiguousarray(bgr, np.uint8)
     out = np.empty(bgr.shape[:-1], np.uint8)
     lib().orc_bgr2gray(bgr.reshape(-1), bgr.size // 3, out.reshape(-1))
+    return out
+
+
+def gamma_table(gamma=2):
+    """gammaCorrection's table exactly as the reference builds it (DET/source.py:599-603)."""
+    inv = 1 / gamma
+    return np.array([((i / 255) ** inv) * 255 for i in range(256)], np.uint8)
+
+
+def clahe(gray, clip_limit=2.0, tiles=(8, 8)):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty_like(gray)
+    lib().orc_clahe(gray.reshape(-1), gray.shape[0], gray.shape[1], float(clip_limit), int(tiles[0]), int(tiles[1]), out.reshape(-1))
+    return out
+
+
+def gauss3(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty_like(gray)
+    lib().orc_gauss3(gray.reshape(-1), gray.shape[0], gray.shape[1], out.reshape(-1))
+    return out
+
+
+def preprocess(bgr, clip_limit=2.0, tiles=(8, 8), gamma=2):
+    """grayAndEnhanceContrast (DET/source.py:135-152): BGR2GRAY -> CLAHE(clip 2, 8x8) -> GaussianBlur 3x3 -> gamma LUT."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    out = np.empty(bgr.shape[:2], np.uint8)
+    lib().orc_preprocess(bgr.reshape(-1), bgr.shape[0], bgr.shape[1], float(clip_limit), int(tiles[0]), int(tiles[1]),
+                         gamma_table(gamma), out.reshape(-1))
     return out
 
 

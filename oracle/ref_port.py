@@ -16,6 +16,15 @@ import numpy as np
 SIGNALLIST = ['prohibicion', 'peligro', 'stop', 'direccionProhibida', 'cedaPaso', 'direccionObligatoria']
 
 
+def gray_and_enhance_contrast(image):
+    """DET/source.py:135-152 + gammaCorrection :599-605: the four cv2 calls of the reference, in its order."""
+    gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
+    eq = cv2.createCLAHE(clipLimit=2).apply(gray)
+    blur = cv2.GaussianBlur(eq, (3, 3), 0)
+    table = np.array([((i / 255) ** (1 / 2)) * 255 for i in range(256)], np.uint8)
+    return cv2.LUT(blur, table)
+
+
 def expand_or_reject(box, percentage):
     """DET/source.py:155-174."""
     x, y, w, h = box

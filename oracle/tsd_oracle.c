@@ -13,7 +13,7 @@
  *
  * Pinning: the reference holds no tests / golden vectors for this path, so this
  * oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF run in the build container
- * (tests/golden/make_golden.py -> tests/golden/*.npz) and, where cv2 is importable, against live cv2.
+ * (tests/golden/make_golden.py -> tests/golden/ *.npz) and, where cv2 is importable, against live cv2.
  *
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off; no FMA contraction so f64/f32 steps round
  * exactly as the reference's numpy / OpenCV scalar code does).
@@ -395,6 +395,102 @@ ORC_API void orc_bgr2gray(const uint8_t *bgr, int npx, uint8_t *gray)
 {
     for (int i = 0; i < npx; i++)
         gray[i] = (uint8_t)((3735 * bgr[3 * i] + 19235 * bgr[3 * i + 1] + 9798 * bgr[3 * i + 2] + 16384) >> 15);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * N1  grayAndEnhanceContrast -- DET/source.py:135-152 (= REC/source.py:67-84), gammaCorrection :599-605.
+ *     cv2.cvtColor(BGR2GRAY) (A.6) -> cv2.createCLAHE(clipLimit=2).apply -> cv2.GaussianBlur((3,3), 0) -> cv2.LUT(gamma).
+ *     OpenCV imgproc/clahe.cpp: 8x8 tiles (the image is extended to a multiple of the grid with BORDER_REFLECT_101 for
+ *     the tile histograms only), clip = max(int(clipLimit * tileArea / 256), 1), excess redistributed (batch + stride),
+ *     LUT = cvRound(cumsum * (255f / tileArea)), per pixel float bilinear blend of the 4 neighbouring tile LUTs in the
+ *     order (l11*xa1 + l12*xa)*ya1 + (l21*xa1 + l22*xa)*ya, cvRound.  GaussianBlur 3x3 sigma 0 on 8U = exact
+ *     (1 2 1)x(1 2 1)/16 with round-half-up, BORDER_REFLECT_101.  0 mismatches against cv2 4.13.0 on real frames, noise,
+ *     4K and sizes that are not multiples of 8.
+ * ---------------------------------------------------------------------------------------------- */
+static int reflect101(int i, int n) { if (n == 1) return 0; while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i; return i; }
+
+ORC_API void orc_clahe(const uint8_t *src, int H, int W, double clip_limit, int tiles_x, int tiles_y, uint8_t *dst)
+{
+    /* clahe.cpp: when EITHER size is not a multiple of the grid, copyMakeBorder pads bottom by tilesY - rows % tilesY and right
+     * by tilesX - cols % tilesX -- i.e. a whole extra grid step on the axis that WAS a multiple */
+    int divisible = H % tiles_y == 0 && W % tiles_x == 0;
+    int He = divisible ? H : H + tiles_y - H % tiles_y, We = divisible ? W : W + tiles_x - W % tiles_x;
+    int tw = We / tiles_x, th = He / tiles_y, total = tw * th;
+    float lut_scale = 255.0f / (float)total;
+    int clip = 0;
+    if (clip_limit > 0.0) { clip = (int)(clip_limit * total / 256); if (clip < 1) clip = 1; }
+    uint8_t *lut = (uint8_t *)malloc((size_t)tiles_x * tiles_y * 256);
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++) {
+            int hist[256];
+            memset(hist, 0, sizeof hist);
+            for (int y = ty * th; y < (ty + 1) * th; y++)
+                for (int x = tx * tw; x < (tx + 1) * tw; x++) hist[src[(size_t)reflect101(y, H) * W + reflect101(x, W)]]++;
+            if (clip > 0) {
+                int clipped = 0;
+                for (int i = 0; i < 256; i++) if (hist[i] > clip) { clipped += hist[i] - clip; hist[i] = clip; }
+                int batch = clipped / 256, residual = clipped - batch * 256;
+                for (int i = 0; i < 256; i++) hist[i] += batch;
+                if (residual != 0) {
+                    int step = 256 / residual; if (step < 1) step = 1;
+                    for (int i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++;
+                }
+            }
+            int sum = 0;
+            uint8_t *l = lut + ((size_t)ty * tiles_x + tx) * 256;
+            for (int i = 0; i < 256; i++) {
+                sum += hist[i];
+                long v = lrintf((float)sum * lut_scale);
+                l[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
+        }
+    float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    for (int y = 0; y < H; y++) {
+        float tyf = (float)y * inv_th - 0.5f;
+        int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
+        float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+        if (ty1 < 0) ty1 = 0;
+        if (ty2 > tiles_y - 1) ty2 = tiles_y - 1;
+        for (int x = 0; x < W; x++) {
+            float txf = (float)x * inv_tw - 0.5f;
+            int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
+            float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+            if (tx1 < 0) tx1 = 0;
+            if (tx2 > tiles_x - 1) tx2 = tiles_x - 1;
+            int v = src[(size_t)y * W + x];
+            float l11 = lut[((size_t)ty1 * tiles_x + tx1) * 256 + v], l12 = lut[((size_t)ty1 * tiles_x + tx2) * 256 + v];
+            float l21 = lut[((size_t)ty2 * tiles_x + tx1) * 256 + v], l22 = lut[((size_t)ty2 * tiles_x + tx2) * 256 + v];
+            float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+            long r = lrintf(res);
+            dst[(size_t)y * W + x] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+        }
+    }
+    free(lut);
+}
+
+ORC_API void orc_gauss3(const uint8_t *src, int H, int W, uint8_t *dst)
+{
+    for (int y = 0; y < H; y++) {
+        const uint8_t *r0 = src + (size_t)reflect101(y - 1, H) * W, *r1 = src + (size_t)y * W, *r2 = src + (size_t)reflect101(y + 1, H) * W;
+        for (int x = 0; x < W; x++) {
+            int xl = reflect101(x - 1, W), xr = reflect101(x + 1, W);
+            int s = r0[xl] + 2 * r0[x] + r0[xr] + 2 * r1[xl] + 4 * r1[x] + 2 * r1[xr] + r2[xl] + 2 * r2[x] + r2[xr];
+            dst[(size_t)y * W + x] = (uint8_t)((s + 8) >> 4);
+        }
+    }
+}
+
+/* the whole grayAndEnhanceContrast: gamma_table = the reference's own 256-entry table (DET/source.py:602-603) */
+ORC_API void orc_preprocess(const uint8_t *bgr, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                            const uint8_t *gamma_table, uint8_t *out)
+{
+    size_t n = (size_t)H * W;
+    uint8_t *g = (uint8_t *)malloc(n), *c = (uint8_t *)malloc(n);
+    orc_bgr2gray(bgr, (int)n, g);
+    orc_clahe(g, H, W, clip_limit, tiles_x, tiles_y, c);
+    orc_gauss3(c, H, W, g);
+    for (size_t i = 0; i < n; i++) out[i] = gamma_table[g[i]];
+    free(g); free(c);
 }
 
 /* ------------------------------------------------------------------------------------------------

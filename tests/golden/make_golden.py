@@ -19,6 +19,7 @@ Files written
                            survivors and final detection tuples (the resultado.txt content)
   det_resultado150.txt     the reference's resultado.txt lines for all 150 frames in sorted file order
   rec_golden.npz           LDA/KNN weights, grey 32x32 windows, HOG descriptors, logits, probabilities, labels
+  det_pre.npz              sha1 + a 64x128 crop of grayAndEnhanceContrast's output for the three stored frames
   det_crops.npz            the 708 class crops calculateMeanMasks reads (decoded BGR), in the reference's iteration order
   rec_frames.npz           recognition-flavour (x1.15, 32x32) window extraction for the stored frames
 """
@@ -212,8 +213,26 @@ def make_crops():
     print("det_crops.npz:", off[-1], "crops", sum(p.size for p in pix), "bytes raw")
 
 
+def make_pre():
+    """Outputs of the reference's grayAndEnhanceContrast (DET/source.py:135-152) for the three stored frames: sha1 of the whole
+    uint8 [800,1360] result plus rows 300..363 x cols 600..727 verbatim (so a mismatch can be localised)."""
+    src, _ = refload.load_det()
+    out = {}
+    for f in STORED_FRAMES:
+        k = f[:-4]
+        img = cv2.imread(os.path.join(HERE, "det_frame_%s.png" % k))
+        r = src.grayAndEnhanceContrast(img)
+        out[k + "_sha1"] = np.frombuffer(hashlib.sha1(np.ascontiguousarray(r).tobytes()).digest(), np.uint8)
+        out[k + "_crop"] = r[300:364, 600:728].copy()
+    np.savez_compressed(os.path.join(HERE, "det_pre.npz"), **out)
+    print("det_pre.npz written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "det"
+    if what == "pre":
+        make_pre()
+        sys.exit(0)
     if what == "crops":
         make_crops()
         sys.exit(0)

@@ -117,3 +117,26 @@ def test_recognition_functions_like_the_reference_driver(tsd, rec_golden, rec_fr
     assert np.array_equal(np.stack([d[0] for d in dets]), rec_frames[k + "_windows"])
     gray = R.windowsToGray(dets)
     assert np.array_equal(np.stack([d[0] for d in gray]), rec_frames[k + "_gray"])
+
+
+def test_preprocessing_like_the_reference(tsd, oracle, frames3):
+    """grayAndEnhanceContrast on the GPU = the reference's stored outputs on the real frames (sha1 + crop), the
+    oracle on odd sizes / 4K / batches, and therefore the same cv2.MSER boxes (checked in the driver test above)."""
+    import hashlib
+    import os
+    S = tsd.source_det
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "det_pre.npz"))
+    for k in STORED:
+        r = S.grayAndEnhanceContrast(frames3[k])
+        assert r.dtype == np.uint8 and r.shape == (800, 1360)
+        assert hashlib.sha1(np.ascontiguousarray(r).tobytes()).digest() == g[k + "_sha1"].tobytes()
+        assert np.array_equal(r[300:364, 600:728], g[k + "_crop"])
+    rng = np.random.default_rng(4)
+    ctx = S.context()
+    for (H, W, F) in ((97, 131, 3), (480, 641, 2), (481, 640, 1), (64, 64, 5), (9, 17, 1), (100, 7, 2), (2160, 3840, 1)):
+        imgs = np.clip(rng.normal(120, 40, (F, H, W, 3)), 0, 255).astype(np.uint8)
+        got = ctx.preprocess(imgs)
+        for f in range(F):
+            assert np.array_equal(got[f], oracle.preprocess(imgs[f])), (H, W, f)
+    assert np.array_equal(S.gammaCorrection(np.arange(256, dtype=np.uint8), 2), oracle.gamma_table(2))
+
