@@ -67,6 +67,84 @@ def windowsToGray(detections):
     return [(g[i],) + tuple(d[1:]) for i, d in enumerate(detections)]
 
 
+# ---- training-set window extraction ------------------------------------------------------------------
+def orderCroppedImagesByImageFile(trainImages, trainResults):
+    """REC:247-258: positives = ground-truth boxes cropped from the GREY frame and resized to 32x32 (1-channel K6 + K2),
+    -> {file: [(uint8[32,32], (x1,y1,x2,y2), file, signType)]}.  One grey conversion per frame that has ground truth, one
+    batched crop+resize call for all boxes."""
+    ctx = context()
+    out = dict((name, []) for name in trainImages.keys())
+    files = sorted(set(r[0] for r in trainResults))
+    if not files:
+        return out
+    index = {f: i for i, f in enumerate(files)}
+    grey = np.stack([ctx.bgr2gray(np.asarray(trainImages[f], np.uint8)) for f in files])
+    coords = np.array([r[1:5] for r in trainResults], np.int32)
+    wf = np.array([index[r[0]] for r in trainResults], np.int32)
+    wins = ctx.crop_resize(grey, coords, wf)
+    for i, r in enumerate(trainResults):
+        out[r[0]].append((wins[i], (r[1], r[2], r[3], r[4]), r[0], r[5]))
+    return out
+
+
+def intersectionOverUnion(imageACoords, imageBCoords):
+    """REC:263-280 (inclusive-pixel IoU; a handful of Python ints per call, host side like the reference)."""
+    xA, yA = max(imageACoords[0], imageBCoords[0]), max(imageACoords[1], imageBCoords[1])
+    xB, yB = min(imageACoords[2], imageBCoords[2]), min(imageACoords[3], imageBCoords[3])
+    inter = max(0, xB - xA + 1) * max(0, yB - yA + 1)
+    areaA = (imageACoords[2] - imageACoords[0] + 1) * (imageACoords[3] - imageACoords[1] + 1)
+    areaB = (imageBCoords[2] - imageBCoords[0] + 1) * (imageBCoords[3] - imageBCoords[1] + 1)
+    return inter / float(areaA + areaB - inter)
+
+
+def computeNegativeTrainResults(trainImages, positiveTrainResults, allImagesMSERDetections):
+    """REC:365-377: MSER windows whose best IoU with the frame's ground truth is <= 0.5 are negatives."""
+    negatives = dict((name, []) for name in trainImages.keys())
+    for name in trainImages.keys():
+        for det in allImagesMSERDetections[name]:
+            best = -float("inf")
+            for pos in positiveTrainResults[name]:
+                best = max(best, intersectionOverUnion(det[1], pos[1]))
+            if best <= 0.5:
+                negatives[name].append(det)
+    return negatives
+
+
+def extractMSERDetectionsGray(trainImages, mser, frames_per_call=64):
+    """The body of REC:383-389 for ALL frames: MSERTrafficSignDetector (x1.15, 32x32, both de-duplication passes) followed by the
+    per-window BGR2GRAY, batched: cv2.MSER per frame on the host (north_star), then K1+K2, K5 x2 and K6 in four library calls
+    per `frames_per_call` frames.  -> {file: [(uint8[32,32] grey, (x1,y1,x2,y2), file, 0)]} -- the content of MSERTrain.val."""
+    ctx = context()
+    names = list(trainImages.keys())
+    out = dict((name, []) for name in names)
+    for c0 in range(0, len(names), frames_per_call):
+        chunk = names[c0:c0 + frames_per_call]
+        imgs = np.stack([np.asarray(trainImages[n], np.uint8) for n in chunk])
+        boxes = [proposals(trainImages[n], mser) for n in chunk]
+        off = np.concatenate([[0], np.cumsum([len(b) for b in boxes])]).astype(np.int32)
+        allb = np.concatenate(boxes) if off[-1] else np.zeros((0, 4), np.int32)
+        wins, coords, woff = ctx.windows(imgs, allb, off)
+        w1, c1, o1 = ctx.dedup(wins, coords, woff, False, 0.85)      # REC:59
+        w2, c2, o2 = ctx.dedup(w1, c1, o1, True, 0.95)               # REC:61
+        grey = ctx.bgr2gray(w2) if len(w2) else np.zeros((0, 32, 32), np.uint8)
+        for f, n in enumerate(chunk):
+            out[n] = [(grey[i], tuple(int(v) for v in c2[i]), n, 0) for i in range(int(o2[f]), int(o2[f + 1]))]
+    return out
+
+
+def calculateNegativeTrainResults(trainImages, positiveTrainResults, mser):
+    """REC:380-398 drop-in, same cwd-relative pickle cache `MSERTrain.val` with the same layout."""
+    import pickle
+    if not os.path.exists('MSERTrain.val'):
+        allImagesMSERDetections = extractMSERDetectionsGray(trainImages, mser)
+        with open("MSERTrain.val", "wb") as outfile:
+            pickle.dump(allImagesMSERDetections, outfile)
+    else:
+        with open("MSERTrain.val", "rb") as infile:
+            allImagesMSERDetections = pickle.load(infile)
+    return computeNegativeTrainResults(trainImages, positiveTrainResults, allImagesMSERDetections)
+
+
 # ---- descriptors ---------------------------------------------------------------------------------------------------
 def computeDescriptors(image, featureDescriptor):
     """REC:517-521: 'HOG' -> float32[324] (cv2.HOGDescriptor.compute), 'GRAY' -> image.ravel()."""
@@ -145,8 +223,8 @@ def predictProbability(classifiers, reducer, testDataDescriptors, tolerance):
         return predictProbabilityKNNClassifiers(classifiers[0], reducer, testDataDescriptors)
 
 
-_PATCHED = ("makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
-            "computeDescriptors", "calculateDescriptors", "predictProbabilityLDAClassifiers",
+_PATCHED = ("grayAndEnhanceContrast", "makeWindowBiggerOrDiscardFakeDetections", "cleanDuplicatedDetections", "MSERTrafficSignDetector",
+            "orderCroppedImagesByImageFile", "calculateNegativeTrainResults", "computeDescriptors", "calculateDescriptors", "predictProbabilityLDAClassifiers",
             "predictProbabilityKNNClassifiers", "predictProbability")
 
 

@@ -140,3 +140,42 @@ def test_preprocessing_like_the_reference(tsd, oracle, frames3):
             assert np.array_equal(got[f], oracle.preprocess(imgs[f])), (H, W, f)
     assert np.array_equal(S.gammaCorrection(np.arange(256, dtype=np.uint8), 2), oracle.gamma_table(2))
 
+
+def test_training_window_extraction_like_the_reference(tsd, rec_frames, frames3, oracle, tmp_path, monkeypatch):
+    """the producer of MSERTrain.val (REC:380-398) through the GPU path.  The three stored frames stand in for the
+    train frames: every cache entry (grey 32x32 pixels, coords, file, label slot 0, in order) equals what the reference's
+    MSERTrafficSignDetector + BGR2GRAY gave for that frame (rec_frames.npz); the pickle has the reference's layout; negatives
+    follow the IoU <= 0.5 rule; positives (REC:247-258) equal cv2 on the grey frame."""
+    import pickle
+    import cv2
+    R = tsd.source_rec
+    mser = cv2.MSER_create(delta=7, min_area=200, max_area=2000, max_variation=1.0)
+    train = {k + ".jpg": frames3[k] for k in STORED}
+    gt = []
+    for k in STORED:                                                  # "ground truth": two survivors of each frame + an odd box
+        c = rec_frames[k + "_coords"]
+        gt += [(k + ".jpg", int(c[0][0]), int(c[0][1]), int(c[0][2]), int(c[0][3]), 1),
+               (k + ".jpg", int(c[-1][0]), int(c[-1][1]), int(c[-1][2]), int(c[-1][3]), 3), (k + ".jpg", 100, 200, 163, 251, 2)]
+    pos = R.orderCroppedImagesByImageFile(train, gt)
+    for k in STORED:
+        g = cv2.cvtColor(frames3[k], cv2.COLOR_BGR2GRAY)
+        assert len(pos[k + ".jpg"]) == 3
+        for (win, coords, file, label), r in zip(pos[k + ".jpg"], [t for t in gt if t[0] == k + ".jpg"]):
+            assert coords == r[1:5] and file == r[0] and label == r[5]
+            x1, y1, x2, y2 = coords
+            assert np.array_equal(win, cv2.resize(g[y1:y2, x1:x2], (32, 32)))
+    monkeypatch.chdir(tmp_path)                                       # the cache is cwd-relative (REC:381)
+    neg = R.calculateNegativeTrainResults(train, pos, mser)
+    cache = pickle.load(open(tmp_path / "MSERTrain.val", "rb"))
+    assert list(cache.keys()) == list(train.keys())
+    for k in STORED:
+        ent = cache[k + ".jpg"]
+        assert [e[1] for e in ent] == [tuple(int(v) for v in c) for c in rec_frames[k + "_coords"]]
+        assert all(isinstance(v, int) for e in ent for v in e[1]) and all(e[2] == k + ".jpg" and e[3] == 0 for e in ent)
+        assert np.array_equal(np.stack([e[0] for e in ent]), rec_frames[k + "_gray"])
+        # the two ground-truth boxes that ARE survivors overlap themselves (IoU 1 > 0.5): not negatives
+        exp_neg = [e for e in ent if max(R.intersectionOverUnion(e[1], p[1]) for p in pos[k + ".jpg"]) <= 0.5]
+        assert [e[1] for e in neg[k + ".jpg"]] == [e[1] for e in exp_neg] and len(exp_neg) <= len(ent) - 2
+    neg2 = R.calculateNegativeTrainResults(train, pos, None)          # second call: served from the cache, no MSER needed
+    assert [[e[1] for e in neg2[n]] for n in train] == [[e[1] for e in neg[n]] for n in train]
+
