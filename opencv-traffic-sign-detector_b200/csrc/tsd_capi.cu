@@ -559,8 +559,10 @@ static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32
     static int per_sm = 0;
     if (!per_sm) {
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_fold_warp_kernel<RMAX, CAP>, warps * 32, smem));
         if (per_sm < 1) per_sm = 1;
+        if (getenv("TSD_DEBUG")) fprintf(stderr, "[tsd] k5_fold_warp<%d,%d>: %zu B shared memory per CTA, %d CTAs per SM\n", RMAX, CAP, smem, per_sm);
     }
     // longest-first frame order + work counter (context scratch: [nframes] order, [1] counter)
     TRY(ensure(c, c->b_order, (c->order_off + nframes + 1) * 4));

@@ -427,14 +427,22 @@ __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restric
 constexpr int kFoldWarps = 4;                          // default warps (= frames in flight) per CTA; the kernel reads blockDim
 
 template <int RMAX, int CAP>
-struct FoldWarpSmem {
-    int4 coords[RMAX];           // current coords of every item (merged coords are written here and to global)
-    uint32_t hash[RMAX];         // current pixel hash of every item
+struct FoldPass1Smem {           // merge workspace of the histogram pass
     uint16_t dense[kDenseLen];   // dense counts of the item being merged
     float eg[32];                // its group energies (Cauchy-Schwarz pruning, as in k5_pairs)
     uint32_t rowd[32], rowm[32]; // class bits of the merged item against up to 1024 others (delete / merge), by word
-    uint16_t cand[RMAX];         // compacted list of the others that survive the pruning
-    HistScratch<CAP> hs;
+    uint32_t cand_big[RMAX <= CAP ? 1 : RMAX];   // compacted list (item | nnz << 16) of the others that survive the pruning; when it
+    HistScratch<CAP> hs;                         // fits it lives in hs.cnt instead (dead once the dense copy is filled)
+    __device__ __forceinline__ uint32_t* cand() { return RMAX <= CAP ? hs.cnt : cand_big; }
+};
+
+template <int RMAX, int CAP>
+struct FoldWarpSmem {
+    uint32_t hash[RMAX];         // current pixel hash of every item (both passes: pop-by-pixel-equality pre-filter)
+    union {                      // the two passes never overlap: the coordinate pass reuses the merge workspace for the coordinates
+        FoldPass1Smem<RMAX, CAP> p1;
+        int4 coords[RMAX];       // pass 2: current coords of every survivor candidate (merged coords also go to global)
+    };
 };
 
 // per-lane class of (dense item d) vs (sparse item o): integer dot, exact f64 fallback
@@ -486,15 +494,16 @@ __device__ __forceinline__ uint32_t merge_pixels_warp(uint8_t* ipx, const uint8_
     return warp_sum_u(hsh);
 }
 
-// Classes of the merged item (dense histogram in sm.dense, meta mj, energies sm.eg) against the items whose bits are set in
+// Classes of the merged item (dense histogram in sm.p1.dense, meta mj, energies sm.p1.eg) against the items whose bits are set in
 // cmask (lane w = items 32w..32w+31), words [w0, w1].  Three steps: (1) lane-parallel Cauchy-Schwarz pruning, 32 items at a
-// time (class 0 without touching their histograms), survivors are compacted into sm.cand; (2) lane-parallel exact
-// classification of the compact list; (3) results as bit words in sm.rowd / sm.rowm.
+// time (class 0 without touching their histograms), survivors are compacted into sm.p1.cand; (2) lane-parallel exact
+// classification of the compact list; (3) results as bit words in sm.p1.rowd / sm.p1.rowm.
 template <int RMAX, int CAP>
 __device__ __forceinline__ void fold_classify_against(FoldWarpSmem<RMAX, CAP>& sm, const FoldParams& P, const WinMeta& mj, int base, unsigned cmask,
                                                       int w0, int w1) {
     const int lane = threadIdx.x & 31;
-    sm.rowd[lane] = 0; sm.rowm[lane] = 0;
+    sm.p1.rowd[lane] = 0; sm.p1.rowm[lane] = 0;
+    uint32_t* cand = sm.p1.cand();
     __syncwarp();
     int ncand = 0;
     for (int t = w0; t <= w1; t++) {
@@ -502,32 +511,84 @@ __device__ __forceinline__ void fold_classify_against(FoldWarpSmem<RMAX, CAP>& s
         if (!aw) continue;
         const bool mine = (aw >> lane) & 1u;
         const int q = base + 32 * t + lane;
-        int c = 0;
+        int c = 0, nnz_q = 0;
         bool need = false;
         if (mine) {
             float ub = 0.f;
 #pragma unroll
-            for (int g = 0; g < kHistGroups; g++) ub += sm.eg[g] * P.E_T[(int64_t)g * P.e_stride + q];
+            for (int g = 0; g < kHistGroups; g++) ub += sm.p1.eg[g] * P.E_T[(int64_t)g * P.e_stride + q];
             const WinMeta mq = load_meta_cg(P.meta + q);
+            nnz_q = mq.nnz;
             const double den2 = mj.A * mq.A;
             if (!(fabs(den2) > DBL_EPSILON)) c = classify(1.0, P.hist_tol, P.hist_lo);      // compareHist's degenerate branch
             else need = !prunable(ub, mj, mq.s1, mq.A, mq.rA, P.hist_lo);
         }
         const unsigned nb = __ballot_sync(0xffffffffu, need);
-        if (need) sm.cand[ncand + __popc(nb & ((1u << lane) - 1))] = (uint16_t)(32 * t + lane);
+        if (need) cand[ncand + __popc(nb & ((1u << lane) - 1))] = (uint32_t)(32 * t + lane) | ((uint32_t)nnz_q << 16);
         ncand += __popc(nb);
         const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bm = __ballot_sync(0xffffffffu, c == 2);
-        if (lane == 0) { sm.rowd[t] = bd; sm.rowm[t] = bm; }
+        if (lane == 0) { sm.p1.rowd[t] = bd; sm.p1.rowm[t] = bm; }
     }
     __syncwarp();
+    // step 2: exact integer dots of the compact list, warp-wide and software-pipelined exactly like k5_pairs (one candidate per
+    // stage, two stages in flight, 128-bit entry loads): the fold is bound by the latency of these loads.  Plain loads: entries of
+    // items merged earlier in this frame were rewritten by this warp.
+    const uint16_t* dense = sm.p1.dense;
+    const uint4* ent4 = reinterpret_cast<const uint4*>(P.entries) + (int64_t)base * (P.es >> 2);
+    const int es4 = P.es >> 2;
     for (int r0 = 0; r0 < ncand; r0 += 32) {
-        if (r0 + lane < ncand) {
-            const int ql = sm.cand[r0 + lane], q = base + ql;
-            const WinMeta mq = load_meta_cg(P.meta + q);
-            const int c = pair_class_lane(sm.dense, mj, P.entries + (int64_t)q * P.es, mq, P.hist_tol, P.hist_lo);
-            if (c == 1) atomicOr(&sm.rowd[ql >> 5], 1u << (ql & 31));
-            else if (c == 2) atomicOr(&sm.rowm[ql >> 5], 1u << (ql & 31));
+        const int nr = min(32, ncand - r0);
+        int Ik = 0;
+        int cA = 0, cB = 0, nA = 0, nB = 0;
+        const uint4 *eA = ent4, *eB = ent4;
+        uint4 a0, a1, b0, b1;
+#define FOLD_FETCH(CI, N, E, V0, V1)                                                                         \
+        do {                                                                                                 \
+            const uint32_t info = cand[r0 + (CI)];                                                           \
+            N = (int)((info >> 16) + 3) >> 2;                                                                \
+            E = ent4 + (int64_t)(info & 0xffffu) * es4;                                                      \
+            V0 = lane < N ? E[lane] : make_uint4(0, 0, 0, 0);                                                \
+            V1 = lane + 32 < N ? E[lane + 32] : make_uint4(0, 0, 0, 0);                                      \
+        } while (0)
+#define FOLD_DOT(V) ((int)dense[(V).x >> 16] * (int)((V).x & 0xffffu) + (int)dense[(V).y >> 16] * (int)((V).y & 0xffffu) + \
+                     (int)dense[(V).z >> 16] * (int)((V).z & 0xffffu) + (int)dense[(V).w >> 16] * (int)((V).w & 0xffffu))
+#define FOLD_COMPUTE(CI, N, E, V0, V1)                                                                       \
+        do {                                                                                                 \
+            int acc = FOLD_DOT(V0) + FOLD_DOT(V1);                                                           \
+            for (int e = lane + 64; e < N; e += 32) { const uint4 v = E[e]; acc += FOLD_DOT(v); }            \
+            acc = warp_sum_i(acc);                                                                           \
+            if (lane == (CI)) Ik = acc;                                                                      \
+        } while (0)
+        FOLD_FETCH(cA, nA, eA, a0, a1);
+        while (cA < nr) {
+            cB = cA + 1;
+            if (cB < nr) FOLD_FETCH(cB, nB, eB, b0, b1);
+            FOLD_COMPUTE(cA, nA, eA, a0, a1);
+            if (cB >= nr) break;
+            cA = cB + 1;
+            if (cA < nr) FOLD_FETCH(cA, nA, eA, a0, a1);
+            FOLD_COMPUTE(cB, nB, eB, b0, b1);
         }
+#undef FOLD_FETCH
+#undef FOLD_DOT
+#undef FOLD_COMPUTE
+        if (lane < nr) {                                     // lane-parallel classification (exact f64 only within 2e-6 of a threshold)
+            const int ql = (int)(cand[r0 + lane] & 0xffffu), q = base + ql;
+            const WinMeta mq = load_meta_cg(P.meta + q);
+            int c = classify_from_int(Ik, mj, mq, P.hist_tol, P.hist_lo);
+            if (c == kClsUnsure) {
+                const uint32_t* eo = P.entries + (int64_t)q * P.es;
+                double s12 = 0;
+                for (int i = 0; i < mq.nnz; i++) {
+                    const uint32_t v = eo[i];
+                    s12 += (double)((float)dense[v >> 16] * mj.a) * (double)((float)(v & 0xffffu) * mq.a);
+                }
+                c = classify(correl_from(s12, mj.s1, mj.A, mq.s1, mq.A), P.hist_tol, P.hist_lo);
+            }
+            if (c == 1) atomicOr(&sm.p1.rowd[ql >> 5], 1u << (ql & 31));
+            else if (c == 2) atomicOr(&sm.p1.rowm[ql >> 5], 1u << (ql & 31));
+        }
+        __syncwarp();
     }
     __syncwarp();
 }
@@ -607,7 +668,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FoldWarpSmem<RMAX, CAP>& sm = reinterpret_cast<FoldWarpSmem<RMAX, CAP>*>(smem_raw + ((sizeof(HsvLut) + 15) & ~15))[wid];
     load_hsv_lut(lut, P.tab);
-    for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.dense)[b] = 0;
+    for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;
     __syncthreads();
     const int ws = P.ws, es = P.es;
     // persistent warps pull frames from a shared counter in longest-first order (k5_order_kernel): the heavy frames (many
@@ -620,7 +681,8 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
         const int f = order[idx];
         const int base = P.offsets[f], n = P.offsets[f + 1] - base;
         if (n > RMAX || n > RW * 32) { if (lane == 0) P.out_count[f] = -1; continue; }    // host picks RMAX / RW large enough
-        for (int p = lane; p < n; p += 32) { sm.coords[p] = P.coords[base + p]; sm.hash[p] = P.meta[base + p].hash; }
+        for (int p = lane; p < n; p += 32) sm.hash[p] = P.meta[base + p].hash;
+        for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;   // (the previous frame's pass 2 overlaid it)
         __syncwarp();
         const int nwords = (n + 31) >> 5;
         unsigned A = 0;                                      // survivors, list order = item order
@@ -650,30 +712,30 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
                     else if (lane == L) D |= (d & ((1u << bit) - 1)) | (1u << bit);
                     uint8_t* ipx = P.windows + (int64_t)slot * ws;
                     uint32_t* ient = P.entries + (int64_t)slot * es;
-                    if (!dirty) ic = sm.coords[j];
+                    if (!dirty) ic = P.coords[slot];          // (pass 1 keeps coordinates in global memory: only merges touch them)
                     else {                                   // clear the previous dense copy of this item (hs still holds its bins)
-                        for (int r = lane; r < mj.nnz; r += 32) sm.dense[sm.hs.binof[r]] = 0;
+                        for (int r = lane; r < mj.nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = 0;
                         __syncwarp();
                     }
                     merge_pixels_warp<false>(ipx, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
-                    const int4 kc = sm.coords[fm];
+                    const int4 kc = P.coords[base + fm];
                     ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);   // Python // (coords >= 0)
                     __syncwarp();
-                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, lut, sm.hs, ient, P.meta + slot, sm.eg, 1);
-                    for (int r = lane; r < nnz; r += 32) sm.dense[sm.hs.binof[r]] = (uint16_t)sm.hs.cnt[r];
+                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, lut, sm.p1.hs, ient, P.meta + slot, sm.p1.eg, 1);
+                    for (int r = lane; r < nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = (uint16_t)sm.p1.hs.cnt[r];
                     __syncwarp();
                     mj = load_meta_cg(P.meta + slot);
                     if (lane == 0) sm.hash[j] = mj.hash;     // the rebuild hashes the new pixels
-                    if (lane < kHistGroups) P.E_T[(int64_t)lane * P.e_stride + slot] = sm.eg[lane];   // later merges prune against the NEW histogram
+                    if (lane < kHistGroups) P.E_T[(int64_t)lane * P.e_stride + slot] = sm.p1.eg[lane];   // later merges prune against the NEW histogram
                     // re-classify the updated item against the survivors after the merge position
                     scan = lane < L ? 0u : (lane == L ? (bit == 31 ? 0u : ~((2u << bit) - 1)) : 0xffffffffu);
                     fold_classify_against<RMAX, CAP>(sm, P, mj, base, A & scan, L, (j - 1) >> 5);
-                    if (lane >= L && lane <= ((j - 1) >> 5)) { vd = sm.rowd[lane]; vm = sm.rowm[lane]; }
+                    if (lane >= L && lane <= ((j - 1) >> 5)) { vd = sm.p1.rowd[lane]; vm = sm.p1.rowm[lane]; }
                     __syncwarp();
                     dirty = true;
                 }
                 if (dirty) {
-                    if (lane == 0) { sm.coords[j] = ic; P.coords[slot] = ic; }
+                    if (lane == 0) P.coords[slot] = ic;
                     // the item is final: its class against every LATER item (their bit rows described the un-merged histogram)
                     const unsigned bitj = 1u << (j & 31);
                     {
@@ -688,13 +750,13 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
                             const int q2 = 32 * t + lane;
                             if (q2 > j && q2 < n) {
                                 uint32_t* r = M + (int64_t)(base + q2) * 2 * RW + (j >> 5);
-                                r[0] = (r[0] & ~bitj) | (((sm.rowd[t] >> lane) & 1u) ? bitj : 0u);      // (this warp is the only writer of the frame's rows)
-                                r[RW] = (r[RW] & ~bitj) | (((sm.rowm[t] >> lane) & 1u) ? bitj : 0u);
+                                r[0] = (r[0] & ~bitj) | (((sm.p1.rowd[t] >> lane) & 1u) ? bitj : 0u);      // (this warp is the only writer of the frame's rows)
+                                r[RW] = (r[RW] & ~bitj) | (((sm.p1.rowm[t] >> lane) & 1u) ? bitj : 0u);
                             }
                         }
                     }
                     __syncwarp();
-                    for (int r = lane; r < mj.nnz; r += 32) sm.dense[sm.hs.binof[r]] = 0;
+                    for (int r = lane; r < mj.nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = 0;
                     __syncwarp();
                     if (j + 1 < n && lane < RW) { nd = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + lane); nm = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + RW + lane); }
                 }
@@ -705,6 +767,9 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
             if (lane < nwords) A = (lane == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1) : 0xffffffffu;
         }
         if (P.do_coords) {
+            __syncwarp();
+            for (int p = lane; p < n; p += 32) sm.coords[p] = P.coords[base + p];      // overlays the pass-1 workspace
+            __syncwarp();
             const unsigned A1 = A;
             unsigned A2 = 0;
             const double tol = P.coord_tol, lo = P.coord_lo;
