@@ -118,8 +118,7 @@ def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7):
     """SURVEY.md section 8(d) per-unit figures x the units one launch processes (independent of the implementation).
     K2: in 3*min(w_c,2D)*min(h_c,2D) + out 3*D*D per aspect-passing window; k5_hist: 3*D*D + 16 per window; k5_pairs:
     the sparse histograms + moments + energies read once, bit rows written; k5_fold: in 3*D*D+16 per input window, out
-    3*D*D+16 per survivor; K3: 3*D*D in, 2*D*D out; K4: 2*D*D in, 8 out (the chain's K4 reads K3's bit-packed masks, which
-    is less; it is credited with the SURVEY figure)."""
+    3*D*D+16 per survivor; K3: 3*D*D in, bit-packed masks out (160 B); K4: 160 B in, 8 out."""
     b = boxes.astype(np.int64)
     w, h = b[:, 2].astype(np.float64), b[:, 3].astype(np.float64)
     pm1 = 1.30 - 1
@@ -139,8 +138,10 @@ def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7):
         # two bit rows written per window
         "k5_pairs": int(4 * hist_entries + npass * (48 + 100 + 8 * row_words)),
         "k5_fold": int(npass * (3 * px + 16) + nsurv * (3 * px + 16)),
-        "k3_masks": int(nsurv * 5 * px),
-        "k4_score": int(nsurv * (2 * px + 8)),
+        # inside the chain K3 hands K4 bit-packed masks (2 x 20 words per window); the byte masks of SURVEY's 2*D*D figure are
+        # written only by the tsd_color_masks entry point (TSD_KEEP_MASKS=1 restores them in the chain)
+        "k3_masks": int(nsurv * (3 * px + 8 * ((px + 31) // 32))),
+        "k4_score": int(nsurv * (8 * ((px + 31) // 32) + 8)),
         "detections": int(counts[3] * 32),
     }, npass
 

@@ -89,6 +89,7 @@ struct tsd_ctx {
     // last enqueue
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
+    int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int pairs_variant = 14;
     int hist_minb = 1;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
     int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
@@ -214,6 +215,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     { const char* e = getenv("TSD_HIST_MINB"); if (e) c->hist_minb = atoi(e); }
     { const char* e = getenv("TSD_K2_MINB"); if (e) c->k2_minb = atoi(e); }
     { const char* e = getenv("TSD_K2_BY_FRAME"); if (e) c->k2_by_frame = atoi(e); }
+    { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
@@ -1045,8 +1047,11 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
         uint32_t* bits = (uint32_t*)c->b_bits.p + wo * 2 * NW;
         int grid = cdiv((int64_t)cap * 32, 256);
         if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        // inside the chain only the bit-packed masks are consumed (K4); the byte masks (the bit-exact artefact tsd_color_masks returns)
+        // are written only when TSD_KEEP_MASKS=1 asks for them
         if (ws <= 4 * 32 * 16)
-            k3_masks_v3_kernel<4><<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, c->d_mlut, red, blue, ms, bits);
+            k3_masks_v3_kernel<4><<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, c->d_mlut, c->keep_masks ? red : nullptr,
+                                                            c->keep_masks ? blue : nullptr, ms, bits);
         else
             k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
         TRY(check_launch(c, "k3_masks"));

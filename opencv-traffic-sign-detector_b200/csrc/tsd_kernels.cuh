@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(256) k3_masks_v3_kernel(const uint8_t* __restr
             int H, S, V;
             bgr2hsv(b, g, rr, s_sdiv, s_hdiv, H, S, V);
             const unsigned fl = valid ? (unsigned)(s_hf[H] & s_sf[S] & s_vf[V]) : 0u;
-            if (valid) { ro[p] = (fl & 3u) ? 255 : 0; bo[p] = (fl & 4u) ? 255 : 0; }     // cv2.add of the two red bands saturates at 255
+            if (valid && red) { ro[p] = (fl & 3u) ? 255 : 0; bo[p] = (fl & 4u) ? 255 : 0; }     // cv2.add of the two red bands saturates at 255
             const unsigned wr = __ballot_sync(0xffffffffu, (fl & 3u) != 0), wb = __ballot_sync(0xffffffffu, (fl & 4u) != 0);
             if (lane == i) { myr = wr; myb = wb; }
         }
