@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
     uint8_t* __restrict__ windows, int out_stride, const int32_t* __restrict__ frame_offsets, int nframes) {
-    const int lane = threadIdx.x & 31;
+    __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     // one window per warp; the grid normally covers all windows (one trip), a smaller grid makes the warps persistent
@@ -317,10 +318,13 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
         yb1 = __float2int_rn(f * 2048.f);
     }
     const uint8_t* px = src + xs0;
+    __syncwarp();                                            // (the previous window's rows are consumed)
+    s_y[wl][lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
+    __syncwarp();
 #pragma unroll 5
     for (int dy = 0; dy < D; dy++) {
-        const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
-        const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
+        const int4 yc = s_y[wl][dy];
+        const int r0 = yc.x, r1 = yc.y, b0 = yc.z, b1 = yc.w;
         const uint8_t* p0 = px + (int64_t)r0 * row_stride;
         const uint8_t* p1 = px + (int64_t)r1 * row_stride;
         int v[C];
