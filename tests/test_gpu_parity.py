@@ -291,6 +291,29 @@ def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
         assert _records(det) == exp
 
 
+def test_chain_flat_frames_vs_oracle(ctx_det, oracle, templates, tsd):
+    """Frames made of large flat patches (windows whose histogram puts all 625 pixels into one or two bins, many exactly equal
+    windows -> the pop-by-pixel-equality rule, degenerate correlations), mixed with ordinary frames in one batch."""
+    red6, blue6 = templates
+    rng = np.random.default_rng(17)
+    F, H, W = 10, 800, 1360
+    frames = tsd.synth.make_frames(F)
+    for f in (1, 4, 7):                                               # flat / two-tone / coarse-block frames
+        frames[f] = np.array([30, 40, 200], np.uint8)
+    frames[4][:, W // 2:] = np.array([200, 60, 20], np.uint8)
+    blocks = rng.integers(0, 256, (H // 40, W // 40, 3), dtype=np.uint8)
+    frames[7] = np.repeat(np.repeat(blocks, 40, 0), 40, 1)
+    boxes, off = tsd.synth.make_boxes(F, 200, seed=tsd.synth.BOX_SEED + 3)
+    det, counts = ctx_det.detect_frames(frames, boxes, off)
+    exp, tot = [], np.zeros(4, np.int64)
+    for f in range(F):
+        o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+        tot += o["stage_counts"]
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    assert counts.tolist() == tot.tolist()
+    assert _records(det) == exp
+
+
 def test_chain_256_frames_vs_oracle(ctx_det, oracle, templates, tsd):
     """A full-sized batch (256 frames x 200 candidates = 51 200 windows) through the device-resident asynchronous chain, record
     by record against the oracle: rare paths of the fold (merges of already merged items, pruning against rewritten
