@@ -633,16 +633,17 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         TRY(check_launch(c, "k5_pairs"));
         mark(c, "k5_pairs");
     }
-    if (max_n <= 256) return npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
     {
-        const int rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
+        int rc;
+        if (max_n <= 256) rc = npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
+        else rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
         if (rc != TSD_OK) return rc;
     }
-    if (may_exceed) {
-        k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
-        TRY(check_launch(c, "k5_fold"));
-    }
-    return TSD_OK;
+    // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
+    // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
+    (void)may_exceed;
+    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
+    return check_launch(c, "k5_fold");
 }
 
 // ---------------------------------------------------------------------------------------------------------------

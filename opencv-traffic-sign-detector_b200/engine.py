@@ -250,7 +250,7 @@ class Context:
         F, H, W = frames.shape[:3]
         boxes = _i32(boxes).reshape(-1, 4); box_offsets = _i32(box_offsets)
         cap = max(int(box_offsets[-1]), 1)
-        det = np.zeros(cap, DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)
+        det = np.empty(cap, DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)      # (only det[:nd] is ever read)
         check(self._L.tsd_detect_frames(self._h, int(mode), ptr(frames), F, H, W, W * 3, H * W * 3, ptr(boxes), ptr(box_offsets),
                                         ptr(det), cap, C.byref(nd), ptr(counts), MEM_HOST))
         return det[:nd.value].copy(), counts
@@ -265,7 +265,7 @@ class Context:
                                          ptr(int(d_boxes)), ptr(int(d_box_offsets)), int(nboxes_total), int(max_boxes_per_frame)))
 
     def fetch_detections(self, cap):
-        det = np.zeros(max(int(cap), 1), DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)
+        det = np.empty(max(int(cap), 1), DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)
         check(self._L.tsd_fetch_detections(self._h, ptr(det), len(det), C.byref(nd), ptr(counts)))
         return det[:nd.value].copy(), counts
 

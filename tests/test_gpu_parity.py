@@ -337,6 +337,26 @@ def test_chain_256_frames_vs_oracle(ctx_det, oracle, templates, tsd):
     assert _records(det) == exp
 
 
+def test_too_small_box_bound_is_harmless(ctx_det, oracle, templates, tsd):
+    """tsd_enqueue_frames with a max_boxes_per_frame that is SMALLER than the truth (a caller bug): frames that do not fit the
+    bit rows sized from it are flagged by the warp fold and redone by the general fold -- same records as the oracle."""
+    import torch
+    red6, blue6 = templates
+    F = 6
+    frames = tsd.synth.make_frames(F)
+    boxes, off = tsd.synth.make_boxes(F, 200)
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(frames).to(dev)
+    d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+    ctx_det.enqueue_frames(d_frames.data_ptr(), F, 800, 1360, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=64)
+    det, counts = ctx_det.fetch_detections(int(off[-1]))
+    exp = []
+    for f in range(F):
+        o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    assert _records(det) == exp
+
+
 def test_chain_properties_full_size(ctx_det, tsd):
     """Size-independent properties at a larger batch: idempotence of the fold, determinism, frame independence."""
     F = 48
