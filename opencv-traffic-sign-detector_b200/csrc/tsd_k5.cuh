@@ -14,6 +14,10 @@
 //                    the item's histogram, re-classifies it against the survivors after the merge position and -- once the
 //                    item is final -- against every later item (their bit rows described the un-merged histogram).
 //                    Pass 2 (corner similarity, DET:209-213) runs in the same warp from coordinates in shared memory.
+//                    Persistent warps pull frames longest-first (k5_order); the merged item is re-classified with the same
+//                    Cauchy-Schwarz pruning and the same software-pipelined exact dots as k5_pairs.
+// The exact dots are bound by the latency of the entry loads (L2): one pair per pipeline stage, two stages in flight in
+// ping-pong registers, 128-bit loads (2 x 4 entries per lane cover 256 bins).
 #pragma once
 #include "tsd_kernels.cuh"
 
@@ -444,30 +448,6 @@ struct FoldWarpSmem {
         int4 coords[RMAX];       // pass 2: current coords of every survivor candidate (merged coords also go to global)
     };
 };
-
-// per-lane class of (dense item d) vs (sparse item o): integer dot, exact f64 fallback
-__device__ __forceinline__ int pair_class_lane(const uint16_t* dense, const WinMeta& md, const uint32_t* eo, const WinMeta& mo,
-                                               double tol, double lo) {
-    int acc = 0;
-    const int n4 = (mo.nnz + 3) >> 2;                       // entries are zero-padded to a multiple of 4
-    const uint4* e4 = reinterpret_cast<const uint4*>(eo);
-#pragma unroll 8
-    for (int i = 0; i < n4; i++) {
-        const uint4 v = e4[i];                              // plain (L1-coherent within the SM): only this warp touches the frame's data
-        acc += (int)dense[v.x >> 16] * (int)(v.x & 0xffffu) + (int)dense[v.y >> 16] * (int)(v.y & 0xffffu) +
-               (int)dense[v.z >> 16] * (int)(v.z & 0xffffu) + (int)dense[v.w >> 16] * (int)(v.w & 0xffffu);
-    }
-    int c = classify_from_int(acc, md, mo, tol, lo);
-    if (c == kClsUnsure) {
-        double s12 = 0;
-        for (int i = 0; i < mo.nnz; i++) {
-            const uint32_t v = eo[i];
-            s12 += (double)((float)dense[v >> 16] * md.a) * (double)((float)(v & 0xffffu) * mo.a);
-        }
-        c = classify(correl_from(s12, md.s1, md.A, mo.s1, mo.A), tol, lo);
-    }
-    return c;
-}
 
 // cv2.addWeighted(a, .5, b, .5, 0) on 4 packed bytes: round-half-even of (a+b)/2 (DET:219)
 __device__ __forceinline__ uint32_t avg_rne4(uint32_t a, uint32_t b) {
