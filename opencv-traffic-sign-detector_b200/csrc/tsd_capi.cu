@@ -558,7 +558,8 @@ template <int RMAX, int CAP>
 static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost) {
     const int warps = RMAX <= 256 ? kFoldWarps : 2;
     const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<RMAX, CAP>);
-    static int per_sm = 0;
+    static int per_sm_dev[64] = {0};                         // function attributes are per device: keyed by the context's device
+    int& per_sm = per_sm_dev[c->device & 63];
     if (!per_sm) {
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -614,8 +615,8 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         const size_t psm = kPairWarps * kDenseLen * 2;
 #define PAIRS_LAUNCH(G, MB)                                                                                                  \
         do {                                                                                                                 \
-            static bool done_ = false;                                                                                       \
-            if (!done_) { CU(cudaFuncSetAttribute(k5_pairs_kernel<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); done_ = true; } \
+            static bool done_[64] = {false};                                                                                 \
+            if (!done_[c->device & 63]) { CU(cudaFuncSetAttribute(k5_pairs_kernel<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); done_[c->device & 63] = true; } \
             k5_pairs_kernel<G, MB><<<nframes * tiles, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles, \
                                                                                      P.hist_tol, P.hist_lo, M, cost);          \
         } while (0)
