@@ -90,7 +90,7 @@ struct tsd_ctx {
     int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
-    int pairs_variant = 14;
+    int pairs_variant = 18;
     int hist_minb = 1;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
     int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
     int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
@@ -627,8 +627,11 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
             case 23: PAIRS_LAUNCH(2, 3); break;
             case 24: PAIRS_LAUNCH(2, 4); break;
             case 14: PAIRS_LAUNCH(1, 4); break;
+            case 18: PAIRS_LAUNCH(1, 8); break;
+            case 116: PAIRS_LAUNCH(1, 16); break;
+            case 16: PAIRS_LAUNCH(1, 6); break;
             case 13: PAIRS_LAUNCH(1, 3); break;
-            default: PAIRS_LAUNCH(1, 4); break;
+            default: PAIRS_LAUNCH(1, 8); break;
         }
 #undef PAIRS_LAUNCH
         TRY(check_launch(c, "k5_pairs"));

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const ui
 // pruned by the energy bound; surviving pairs are evaluated warp-wide (coalesced entry loads), two pairs in flight.
 // Output: M[(base + j)][0..RW) = delete bits over il, M[(base + j)][RW..2RW) = merge bits.
 // =====================================================================================================================
-constexpr int kPairWarps = 8;
+constexpr int kPairWarps = 4;                          // 4-warp CTAs: finer tail granularity than 8 (-6 %), same L1 sharing of the streamed entries
 constexpr int kDenseLen = kHistBins + 8;
 
 __device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_d, const uint32_t* eo, int nnz_o, float a_o) {
