@@ -91,7 +91,7 @@ struct tsd_ctx {
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int pairs_variant = 18;
-    int hist_minb = 1;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
+    int hist_minb = 8;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
     int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
     int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
                                              // consecutive windows: measured slower (0.45 vs 0.27 ms device, 19.1 vs 16.5 ms zero-copy e2e)
