@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtsd_b200.so")
+LIB_PATH = os.environ.get("TSD_LIB") or os.path.join(_PKG, "libtsd_b200.so")     # TSD_LIB: an alternative build (A/B experiments)
 
 MEM_HOST, MEM_DEVICE = 0, 1
 RUN_DETECT, RUN_RECOGNIZE = 1, 2

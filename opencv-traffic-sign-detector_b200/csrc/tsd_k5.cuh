@@ -110,7 +110,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     __syncwarp();
     // pass A: bin of every pixel + occupancy bitmap + pixel hash
     uint32_t hsh = 0;
-#pragma unroll 4
+#pragma unroll kHistUnroll
     for (int p = lane; p < npx; p += 32) {
         const int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
         int H, S, V;
@@ -134,7 +134,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     for (int i = lane; i < nnz4; i += 32) sw.cnt[i] = 0;
     __syncwarp();
     // pass B: counts through the rank hash; binof[rank] = bin (all writers of a rank store the same value)
-#pragma unroll 4
+#pragma unroll kHistUnroll
     for (int p = lane; p < npx; p += 32) {
         const int bin = sw.binbuf[p];
         const uint32_t word = sw.bitmap[bin >> 5];

@@ -9,7 +9,15 @@
 #include <stdint.h>
 #include <float.h>
 
+#ifndef TSD_K2_UNROLL
+#define TSD_K2_UNROLL 5          // destination rows of the K2 general path unrolled together (loads in flight per lane = 12 x this)
+#endif
+#ifndef TSD_HIST_UNROLL
+#define TSD_HIST_UNROLL 8        // pixels per lane in flight in the two histogram passes (measured: 2: .266, 4: .274, 5: .283, 7-8: .259, 10: .310, 20: .369 ms)
+#endif
+
 namespace tsd {
+constexpr int kK2Unroll = TSD_K2_UNROLL, kHistUnroll = TSD_HIST_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
 
 constexpr int kHistH = 50, kHistS = 60, kHistBins = kHistH * kHistS;   // DET:578
 constexpr int kMaxD = 32;
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     __syncwarp();                                            // (the previous window's rows are consumed)
     s_y[wl][lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
     __syncwarp();
-#pragma unroll 5
+#pragma unroll kK2Unroll
     for (int dy = 0; dy < D; dy++) {
         const int4 yc = s_y[wl][dy];
         const int r0 = yc.x, r1 = yc.y, b0 = yc.z, b1 = yc.w;
