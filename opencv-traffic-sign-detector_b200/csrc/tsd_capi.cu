@@ -539,13 +539,13 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
     if (n_max == 0) return TSD_OK;
     if (npx <= 640) {
         int grid = cdiv(n_max, 4);
-        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
         if (c->hist_minb == 8) k5_hist_kernel<640, 4, 8><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
         else if (c->hist_minb == 10) k5_hist_kernel<640, 4, 10><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
         else k5_hist_kernel<640, 4, 1><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     } else {
         int grid = cdiv(n_max, 3);
-        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
         k5_hist_kernel<1024, 3, 1><<<grid, 96, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     }
     return check_launch(c, "k5_hist");
@@ -1051,7 +1051,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
         uint8_t *red = (uint8_t*)c->b_red.p + wo * ms, *blue = (uint8_t*)c->b_blue.p + wo * ms;
         uint32_t* bits = (uint32_t*)c->b_bits.p + wo * 2 * NW;
         int grid = cdiv((int64_t)cap * 32, 256);
-        if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+        if (grid > c->sm_count * TSD_K3_GRID) grid = c->sm_count * TSD_K3_GRID;
         // inside the chain only the bit-packed masks are consumed (K4); the byte masks (the bit-exact artefact tsd_color_masks returns)
         // are written only when TSD_KEEP_MASKS=1 asks for them
         if (ws <= 4 * 32 * 16)

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restric
 // =====================================================================================================================
 // The fold: one warp per frame.
 // =====================================================================================================================
-constexpr int kFoldWarps = 4;                          // default warps (= frames in flight) per CTA; the kernel reads blockDim
+constexpr int kFoldWarps = TSD_FOLD_WARPS;                          // default warps (= frames in flight) per CTA; the kernel reads blockDim
 
 template <int RMAX, int CAP>
 struct FoldPass1Smem {           // merge workspace of the histogram pass

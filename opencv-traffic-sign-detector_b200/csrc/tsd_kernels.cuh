@@ -12,12 +12,24 @@
 #ifndef TSD_K2_UNROLL
 #define TSD_K2_UNROLL 5          // destination rows of the K2 general path unrolled together (loads in flight per lane = 12 x this)
 #endif
+#ifndef TSD_K3_UNROLL
+#define TSD_K3_UNROLL 4          // pixels per lane in flight in the mask kernel
+#endif
+#ifndef TSD_HIST_GRID
+#define TSD_HIST_GRID 64         // persistent CTAs per SM of k5_hist
+#endif
+#ifndef TSD_K3_GRID
+#define TSD_K3_GRID 32           // persistent CTAs per SM of k3_masks
+#endif
+#ifndef TSD_FOLD_WARPS
+#define TSD_FOLD_WARPS 4         // warps (= frames in flight) per CTA of the warp-per-frame fold
+#endif
 #ifndef TSD_HIST_UNROLL
 #define TSD_HIST_UNROLL 8        // pixels per lane in flight in the two histogram passes (measured: 2: .266, 4: .274, 5: .283, 7-8: .259, 10: .310, 20: .369 ms)
 #endif
 
 namespace tsd {
-constexpr int kK2Unroll = TSD_K2_UNROLL, kHistUnroll = TSD_HIST_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
+constexpr int kK2Unroll = TSD_K2_UNROLL, kHistUnroll = TSD_HIST_UNROLL, kK3Unroll = TSD_K3_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
 
 constexpr int kHistH = 50, kHistS = 60, kHistBins = kHistH * kHistS;   // DET:578
 constexpr int kMaxD = 32;
@@ -706,7 +718,7 @@ __global__ void __launch_bounds__(256) k3_masks_v3_kernel(const uint8_t* __restr
         uint8_t* __restrict__ ro = red + (int64_t)w * ms;
         uint8_t* __restrict__ bo = blue + (int64_t)w * ms;
         uint32_t myr = 0, myb = 0;
-#pragma unroll 4
+#pragma unroll kK3Unroll
         for (int i = 0; i < NW; i++) {
             const int p = i * 32 + lane;
             const bool valid = p < npx;
