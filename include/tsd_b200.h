@@ -159,6 +159,10 @@ TSD_API int tsd_bgr2hsv(tsd_ctx *ctx, const uint8_t *bgr, int64_t npx, uint8_t *
 TSD_API int tsd_score_masks(tsd_ctx *ctx, const uint8_t *red, const uint8_t *blue, int n, int D, int32_t *scores,
                             int32_t *id, int32_t *hundredths, uint8_t *emit, int mem);
 
+/* K3 + K4 in one call: detectionsMaskCorrelation (DET/source.py:229-245) for n windows uint8 [n][D][D][3] -> id (1..6), hundredths of
+ * the winner's score, emit (winner > tolerance).  Host pointers. */
+TSD_API int tsd_score(tsd_ctx *ctx, const uint8_t *windows, int n, int D, int32_t *id, int32_t *hundredths, uint8_t *emit, int mem);
+
 /* K6  cv2.cvtColor(BGR2GRAY) (REC/source.py:388): uint8 [npx]. */
 TSD_API int tsd_bgr2gray(tsd_ctx *ctx, const uint8_t *bgr, int64_t npx, uint8_t *gray, int mem);
 /* K7  computeDescriptors(img, (hog,'HOG')) = cv2.HOGDescriptor.compute (REC/source.py:517-521,487-494):
@@ -167,6 +171,10 @@ TSD_API int tsd_hog(tsd_ctx *ctx, const uint8_t *gray, int n, float *desc, int m
 /* K8  predictProbabilityLDAClassifiers + extractBestPredictions (REC/source.py:565-577,627-641,342-347):
  * X float32 [n][nfeat] -> logits f64 [n][6] (may be NULL), labels int32 [n] (0 = no sign). */
 TSD_API int tsd_lda_predict(tsd_ctx *ctx, const float *X, int n, double tol, double *logits, int32_t *labels, int mem);
+/* K6 + K7 + K8 in one call for n BGR windows uint8 [n][32][32][3]: BGR2GRAY (REC/source.py:388), HOG (:519), predict_proba x6 and
+ * extractBestPredictions (:565-577,627-641) -> labels int32 [n] (0 = no sign).  Host pointers. */
+TSD_API int tsd_recognize(tsd_ctx *ctx, const uint8_t *windows, int n, double tol, int32_t *labels, int mem);
+
 /* K8b predictProbabilityKNNClassifiers (REC/source.py:592-596): Z f64 [n][6] (may be NULL), labels int32 [n]. */
 TSD_API int tsd_knn_predict(tsd_ctx *ctx, const float *X, int n, double *Z, int32_t *labels, int mem);
 

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "tsd_synchronize": (_i, [_vp]),
     "tsd_launch_count": (_i64, [_vp]),
     "tsd_mean_windows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
+    "tsd_score": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "tsd_recognize": (_i, [_vp, _vp, _i, _d, _vp, _i]),
     "tsd_set_gamma_table": (_i, [_vp, _vp]),
     "tsd_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _d, _i, _i, _vp, _i]),
     "tsd_host_register": (_i, [_vp, _i64]),

@@ -920,6 +920,32 @@ int tsd_score_masks(tsd_ctx* c, const uint8_t* red, const uint8_t* blue, int n, 
     return TSD_OK;
 }
 
+// K3 + K4 for a list of windows: detectionsMaskCorrelation (DET:229-245) per window, batched.  Host pointers.
+int tsd_score(tsd_ctx* c, const uint8_t* windows, int n, int D, int32_t* id, int32_t* hundredths, uint8_t* emit, int mem) {
+    if (!c || n < 0 || (n && (!windows || !id || !hundredths || !emit))) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_score takes host pointers; use tsd_enqueue_frames for device-resident batches");
+    if (!c->have_templates) return fail(TSD_E_STATE, "templates not set (tsd_set_templates)");
+    if (D != c->tmpl_D) return fail(TSD_E_INVALID, "D=%d but templates are %dx%d", D, c->tmpl_D, c->tmpl_D);
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    const int npx = D * D;
+    Stage s(c);
+    void *dw, *dr, *db, *di, *dh, *de;
+    TRY(s.in(windows, (size_t)n * npx * 3, &dw));
+    TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx));
+    TRY(s.alloc(&di, (size_t)n * 4)); TRY(s.alloc(&dh, (size_t)n * 4)); TRY(s.alloc(&de, (size_t)n));
+    int grid = cdiv((int64_t)n * 32, 256);
+    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db, npx, nullptr);
+    TRY(check_launch(c, "k3_masks"));
+    k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->cur>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, npx, c->d_tmpl, c->cfg.score_tol_hundredths,
+                                                                     nullptr, (int32_t*)di, (int32_t*)dh, (uint8_t*)de);
+    TRY(check_launch(c, "k4_score"));
+    TRY(s.out(id, di, (size_t)n * 4)); TRY(s.out(hundredths, dh, (size_t)n * 4)); TRY(s.out(emit, de, (size_t)n));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
 int tsd_bgr2gray(tsd_ctx* c, const uint8_t* bgr, int64_t npx, uint8_t* gray, int mem) {
     if (!c || npx < 0 || npx > 0x7fffffffLL || (npx && (!bgr || !gray))) return fail(TSD_E_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
@@ -977,6 +1003,32 @@ int tsd_lda_predict(tsd_ctx* c, const float* X, int n, double tol, double* logit
         TRY(s.out(labels, dy, (size_t)n * 4));
         CU(cudaStreamSynchronize(c->stream));
     }
+    return TSD_OK;
+}
+
+// K6 + K7 + K8 for a list of 32x32 BGR windows: BGR2GRAY (REC:388), HOG (REC:519), the six LDA probabilities and
+// extractBestPredictions (REC:565-577,627-641).  Host pointers.
+int tsd_recognize(tsd_ctx* c, const uint8_t* windows, int n, double tol, int32_t* labels, int mem) {
+    if (!c || n < 0 || (n && (!windows || !labels))) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_recognize takes host pointers; use tsd_enqueue_frames for device-resident batches");
+    if (!c->d_ldaW || c->lda_nfeat != TSD_HOG_LEN) return fail(TSD_E_STATE, "324-feature LDA weights not set (tsd_set_lda)");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    Stage s(c);
+    void *dw, *dg, *dh, *dl;
+    TRY(s.in(windows, (size_t)n * 1024 * 3, &dw));
+    TRY(s.alloc(&dg, (size_t)n * 1024)); TRY(s.alloc(&dh, (size_t)n * TSD_HOG_LEN * 4)); TRY(s.alloc(&dl, (size_t)n * 4));
+    int grid = cdiv((int64_t)n * 1024, 256);
+    if (grid > c->sm_count * 32) grid = c->sm_count * 32;
+    k6_gray_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, 1, n * 1024, 0, (uint8_t*)dg);
+    TRY(check_launch(c, "k6_gray"));
+    int hgrid = cdiv(n, kHogWarps);
+    if (hgrid > c->sm_count * 8) hgrid = c->sm_count * 8;
+    k7_hog_kernel<<<hgrid, kHogWarps * 32, 0, c->cur>>>((uint8_t*)dg, nullptr, n, c->hog, (float*)dh);
+    TRY(check_launch(c, "k7_hog"));
+    TRY(dev_lda(c, (float*)dh, nullptr, n, tol, nullptr, (int32_t*)dl));
+    TRY(s.out(labels, dl, (size_t)n * 4));
+    CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
 }
 

@@ -204,6 +204,21 @@ class Context:
         check(self._L.tsd_score_masks(self._h, ptr(red), ptr(blue), n, D, ptr(sc), ptr(ids), ptr(hs), ptr(em), MEM_HOST))
         return dict(scores=sc, id=ids, hundredths=hs, emit=em.astype(bool))
 
+    def score_windows(self, windows):
+        """K3 + K4 in one call (detectionsMaskCorrelation, DET:229-245) -> dict(id, hundredths, emit)."""
+        windows = _u8(windows)
+        n, D = windows.shape[0], windows.shape[1]
+        ids = np.zeros(n, np.int32); hs = np.zeros(n, np.int32); em = np.zeros(n, np.uint8)
+        check(self._L.tsd_score(self._h, ptr(windows), n, D, ptr(ids), ptr(hs), ptr(em), MEM_HOST))
+        return dict(id=ids, hundredths=hs, emit=em.astype(bool))
+
+    def recognize_windows(self, windows, tol=None):
+        """K6 + K7 + K8 in one call on uint8 [n,32,32,3] BGR windows -> labels int32[n] (0 = no sign)."""
+        windows = _u8(windows).reshape(-1, 32, 32, 3)
+        lab = np.zeros(len(windows), np.int32)
+        check(self._L.tsd_recognize(self._h, ptr(windows), len(windows), float(self.cfg.proba_tol if tol is None else tol), ptr(lab), MEM_HOST))
+        return lab
+
     def bgr2gray(self, bgr):
         """K6: cv2.cvtColor(BGR2GRAY) (REC:388)."""
         bgr = _u8(bgr)

@@ -255,6 +255,21 @@ def test_template_builder_golden(tsd, det_crops, templates, oracle):
     assert np.array_equal(mean6, oracle.mean_masks(det_crops)[2])
 
 
+def test_composite_entry_points(ctx_det, ctx_rec, det_frames, rec_frames):
+    """tsd_score (K3+K4) and tsd_recognize (K6+K7+K8) against the reference's stored outputs for the real frames."""
+    for k in STORED:
+        r = ctx_det.score_windows(det_frames[k + "_p2_windows"])
+        sc = det_frames[k + "_scores"]                                    # [n][2][6] per-template scores of the reference
+        best_r, best_b = sc[:, 0].max(1), sc[:, 1].max(1)
+        win = np.where(best_r > best_b, best_r, best_b)
+        assert np.array_equal(r["hundredths"], np.round(win * 100).astype(np.int32))
+        assert np.array_equal(r["emit"], win > 0.55)
+        exp_id = np.where(best_r > best_b, sc[:, 0].argmax(1), sc[:, 1].argmax(1)) + 1
+        assert np.array_equal(r["id"], exp_id.astype(np.int32))
+        lab = ctx_rec.recognize_windows(rec_frames[k + "_windows"])
+        assert np.array_equal(lab, rec_frames[k + "_pred_lda"])
+
+
 # ---- whole chain ------------------------------------------------------------------------------------------------------
 def _records(det):
     return [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
