@@ -175,6 +175,11 @@ TSD_API int tsd_lda_predict(tsd_ctx *ctx, const float *X, int n, double tol, dou
  * extractBestPredictions (:565-577,627-641) -> labels int32 [n] (0 = no sign).  Host pointers. */
 TSD_API int tsd_recognize(tsd_ctx *ctx, const uint8_t *windows, int n, double tol, int32_t *labels, int mem);
 
+/* EVALUATION ONLY (BASELINE.json north_star: the LDA projection on tensor cores vs FMA): the same decision from mma.sync TF32 logits,
+ * split = 1 (plain TF32) or 3 (3xTF32 with FP32 accumulation).  logits float32 [n][6] (may be NULL), *ms (may be NULL) = device time of
+ * the kernel alone.  The chain and tsd_lda_predict use the f64 FMA kernel (the reference computes in float64).  Host pointers. */
+TSD_API int tsd_lda_predict_tf32(tsd_ctx *ctx, const float *X, int n, double tol, int split, float *logits, int32_t *labels, float *ms, int mem);
+
 /* K8b predictProbabilityKNNClassifiers (REC/source.py:592-596): Z f64 [n][6] (may be NULL), labels int32 [n]. */
 TSD_API int tsd_knn_predict(tsd_ctx *ctx, const float *X, int n, double *Z, int32_t *labels, int mem);
 

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "tsd_launch_count": (_i64, [_vp]),
     "tsd_mean_windows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     "tsd_score": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "tsd_lda_predict_tf32": (_i, [_vp, _vp, _i, _d, _i, _vp, _vp, C.POINTER(C.c_float), _i]),
     "tsd_recognize": (_i, [_vp, _vp, _i, _d, _vp, _i]),
     "tsd_set_gamma_table": (_i, [_vp, _vp]),
     "tsd_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _d, _i, _i, _vp, _i]),

@@ -1032,6 +1032,41 @@ int tsd_recognize(tsd_ctx* c, const uint8_t* windows, int n, double tol, int32_t
     return TSD_OK;
 }
 
+// Evaluation entry point (north_star: "the batched LDA projection ... is evaluated for tensor cores (TF32) against FP32 FMA"):
+// the same decision from TF32 tensor-core logits.  split = 1 (plain TF32) or 3 (3xTF32).  *ms (optional) receives the device time
+// of the kernel alone (CUDA events).  NOT used by the chain: the product path is the f64 kernel (tsd_lda_predict).
+int tsd_lda_predict_tf32(tsd_ctx* c, const float* X, int n, double tol, int split, float* logits, int32_t* labels, float* ms, int mem) {
+    if (!c || n < 0 || (n && (!X || !labels)) || (split != 1 && split != 3)) return fail(TSD_E_INVALID, "bad argument");
+    if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "host pointers only");
+    if (!c->d_ldaW) return fail(TSD_E_STATE, "LDA weights not set (tsd_set_lda)");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TSD_OK;
+    Stage s(c);
+    void *dx, *dl, *dy;
+    TRY(s.in(X, (size_t)n * c->lda_nfeat * 4, &dx));
+    TRY(s.alloc(&dl, (size_t)n * 6 * 4));
+    TRY(s.alloc(&dy, (size_t)n * 4));
+    const int kpad = (c->lda_nfeat + 7) & ~7;
+    const size_t smem = (size_t)2 * kpad * 8 * sizeof(float);
+    int grid = cdiv(cdiv(n, 16), 4);
+    if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {                      // first launch warms up, second is timed
+        CU(cudaEventRecord(e0, c->cur));
+        if (split == 1) k8_lda_tf32_kernel<1><<<grid, 128, smem, c->cur>>>((float*)dx, n, c->lda_nfeat, c->d_ldaW, c->d_ldab, tol, (float*)dl, (int32_t*)dy);
+        else k8_lda_tf32_kernel<3><<<grid, 128, smem, c->cur>>>((float*)dx, n, c->lda_nfeat, c->d_ldaW, c->d_ldab, tol, (float*)dl, (int32_t*)dy);
+        CU(cudaEventRecord(e1, c->cur));
+        TRY(check_launch(c, "k8_lda_tf32"));
+    }
+    if (logits) TRY(s.out(logits, dl, (size_t)n * 6 * 4));
+    TRY(s.out(labels, dy, (size_t)n * 4));
+    CU(cudaStreamSynchronize(c->stream));
+    if (ms) CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return TSD_OK;
+}
+
 int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* labels, int mem) {
     if (!c || n < 0 || (n && (!X || !labels))) return fail(TSD_E_INVALID, "bad argument");
     if (!c->d_Zt) return fail(TSD_E_STATE, "KNN model not set (tsd_set_knn)");

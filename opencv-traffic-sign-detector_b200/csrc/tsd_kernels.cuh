@@ -1536,6 +1536,75 @@ __global__ void __launch_bounds__(256) k8_lda_kernel(const float* __restrict__ X
     }
 }
 
+// K8 on the tensor cores -- the EVALUATION north_star asks for, not the product path.  z = X W + b with mma.sync.m16n8k8 TF32
+// (the contraction is [n,324] x [324,6]: N = 6 pads to 8, far below a tcgen05 tile, so the warp-level MMA is the right tensor
+// instruction here).  SPLIT = 1: plain TF32 (10-bit mantissas).  SPLIT = 3: x = xh + xl, w = wh + wl in TF32, z = xh wh + xh wl +
+// xl wh with FP32 accumulation (the usual 3xTF32 emulation of FP32).  One warp per 16 windows; W (hi and lo parts, [328][8],
+// zero padded) in shared memory.  Measured against the f64 FMA kernel in DESIGN.md (label flips, logit error, time).
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float c[4], const uint32_t a[4], const uint32_t b[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(128) k8_lda_tf32_kernel(const float* __restrict__ X, int n, int nfeat, const double* __restrict__ W,
+                                                          const double* __restrict__ b, double tol, float* __restrict__ logits, int32_t* __restrict__ labels) {
+    extern __shared__ float s_w[];                           // [2][kpad][8]: hi parts, then lo parts
+    const int kpad = (nfeat + 7) & ~7;
+    for (int i = threadIdx.x; i < kpad * 8; i += blockDim.x) {
+        const int f = i >> 3, cidx = i & 7;
+        const double w = (f < nfeat && cidx < 6) ? W[f * 6 + cidx] : 0.0;
+        const float wh = __uint_as_float(to_tf32((float)w));
+        s_w[i] = wh;
+        s_w[kpad * 8 + i] = __uint_as_float(to_tf32((float)(w - (double)wh)));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16; w0 < n; w0 += nwarps * 16) {
+        const int r0 = min(w0 + g, n - 1), r1 = min(w0 + g + 8, n - 1);
+        const float* x0 = X + (int64_t)r0 * nfeat;
+        const float* x1 = X + (int64_t)r1 * nfeat;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < kpad; k0 += 8) {
+            const int ka = k0 + t, kb = k0 + t + 4;
+            const float v0 = ka < nfeat ? __ldg(x0 + ka) : 0.f, v1 = ka < nfeat ? __ldg(x1 + ka) : 0.f;
+            const float v2 = kb < nfeat ? __ldg(x0 + kb) : 0.f, v3 = kb < nfeat ? __ldg(x1 + kb) : 0.f;
+            uint32_t ah[4] = {to_tf32(v0), to_tf32(v1), to_tf32(v2), to_tf32(v3)};
+            uint32_t bh[2] = {__float_as_uint(s_w[ka * 8 + g]), __float_as_uint(s_w[kb * 8 + g])};
+            if (SPLIT == 3) {
+                uint32_t al[4] = {to_tf32(v0 - __uint_as_float(ah[0])), to_tf32(v1 - __uint_as_float(ah[1])),
+                                  to_tf32(v2 - __uint_as_float(ah[2])), to_tf32(v3 - __uint_as_float(ah[3]))};
+                uint32_t bl[2] = {__float_as_uint(s_w[kpad * 8 + ka * 8 + g]), __float_as_uint(s_w[kpad * 8 + kb * 8 + g])};
+                mma_tf32(acc, al, bh);                       // small terms first
+                mma_tf32(acc, ah, bl);
+            }
+            mma_tf32(acc, ah, bh);
+        }
+        // C fragment: acc[0], acc[1] = row g, columns 2t, 2t+1 ; acc[2], acc[3] = row g + 8.  Gather the 6 logits of a row into one lane.
+        float z0[6], z1[6];
+#pragma unroll
+        for (int cidx = 0; cidx < 6; cidx++) {
+            const int src = (lane & ~3) | (cidx >> 1);
+            const float e0 = __shfl_sync(0xffffffffu, acc[cidx & 1], src), e1 = __shfl_sync(0xffffffffu, acc[2 + (cidx & 1)], src);
+            z0[cidx] = e0 + (float)b[cidx]; z1[cidx] = e1 + (float)b[cidx];
+        }
+        if (t == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = w0 + g + 8 * h;
+                if (row < n) {
+                    double zd[6];
+#pragma unroll
+                    for (int cidx = 0; cidx < 6; cidx++) { const float z = h ? z1[cidx] : z0[cidx]; zd[cidx] = (double)z; if (logits) logits[(int64_t)row * 6 + cidx] = z; }
+                    labels[row] = lda_decide(zd, tol);
+                }
+            }
+        }
+    }
+}
+
 // K8b  reducer.transform + KNeighborsClassifier(k).predict  (REC:592-596).  One warp per query: Z = (x - xbar) S in
 // f64, then every lane keeps its k best of the training rows it visits; the warp merges by (distance, index).
 constexpr int kKnnMaxK = 8;

@@ -219,6 +219,15 @@ class Context:
         check(self._L.tsd_recognize(self._h, ptr(windows), len(windows), float(self.cfg.proba_tol if tol is None else tol), ptr(lab), MEM_HOST))
         return lab
 
+    def lda_predict_tf32(self, X, split=3, tol=None):
+        """Evaluation only: K8 on the tensor cores (mma.sync TF32; split 1 = plain, 3 = 3xTF32) -> (logits f32[n,6], labels, kernel ms)."""
+        X = np.ascontiguousarray(X, np.float32)
+        n = len(X)
+        lg = np.zeros((n, 6), np.float32); lab = np.zeros(n, np.int32); ms = C.c_float()
+        check(self._L.tsd_lda_predict_tf32(self._h, ptr(X), n, float(self.cfg.proba_tol if tol is None else tol), int(split), ptr(lg), ptr(lab),
+                                           C.byref(ms), MEM_HOST))
+        return lg, lab, float(ms.value)
+
     def bgr2gray(self, bgr):
         """K6: cv2.cvtColor(BGR2GRAY) (REC:388)."""
         bgr = _u8(bgr)

@@ -486,3 +486,15 @@ def test_errors_are_reported_not_thrown(tsd, templates):
             c.lda_predict(np.zeros((1, 324), np.float32))
     with pytest.raises(tsd.TsdError):
         tsd.Context(device=99)
+
+
+def test_lda_tensor_core_evaluation(ctx_rec, rec_golden):
+    """The TF32 evaluation kernels (not on the product path): 3xTF32 reproduces the f64 labels on the reference's held-out set and
+    its logits agree to 1e-3; plain TF32 logits are off by up to ~0.1 -- larger than the smallest label margin of the data,
+    which is why the product path stays f64."""
+    X = rec_golden["hog"].astype(np.float32)
+    z64, lab64 = ctx_rec.lda_predict(X)
+    z3, lab3, _ = ctx_rec.lda_predict_tf32(X, split=3)
+    z1, lab1, _ = ctx_rec.lda_predict_tf32(X, split=1)
+    assert np.array_equal(lab3, lab64) and np.abs(z3 - z64).max() < 1e-3
+    assert np.abs(z1 - z64).max() < 0.5 and np.abs(z1 - z64).max() > 1e-3
