@@ -56,7 +56,7 @@ struct tsd_ctx {
     std::vector<ChunkInfo> chunks;           // of the last enqueue
     std::vector<cudaEvent_t> ev_chunk;
     int pipe_mode = 0;                       // chunked enqueue as a producer (K1+K2) / consumer (rest) pipeline instead of alternating streams
-    DevBuf b_summary, b_order;
+    DevBuf b_summary, b_order, b_gramdone;
     size_t order_off = 0;                   // offset (ints) of the current chunk inside b_order
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -91,6 +91,7 @@ struct tsd_ctx {
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int pairs_variant = 18;
+    int use_gram = 1;                                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
     int hist_minb = 8;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
     int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
     int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
@@ -217,6 +218,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     { const char* e = getenv("TSD_K2_BY_FRAME"); if (e) c->k2_by_frame = atoi(e); }
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
+    { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
@@ -290,7 +292,7 @@ int tsd_destroy(tsd_ctx* c) {
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
+    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
@@ -611,14 +613,33 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         M = (uint32_t*)c->b_pairs.p + m_row0 * 2 * RW;
         cost = out_count;                                    // [nframes] scratch until the fold writes the survivor counts (order is built first)
         CU(cudaMemsetAsync(cost, 0, (size_t)nframes * 4, c->cur));
+        // frames of up to kGramBM windows: Gram matrix on the tensor cores; larger frames (and TSD_GRAM=0): CUDA-core pair kernel
+        int32_t* gram_done = nullptr;
+        if (c->use_gram) {
+            static bool gdone_[64] = {false};
+            if (!gdone_[c->device & 63]) {
+                CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem)));
+                CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                gdone_[c->device & 63] = true;
+            }
+            TRY(ensure(c, c->b_gramdone, (2 * (c->order_off + nframes) + 2) * 4));
+            gram_done = (int32_t*)c->b_gramdone.p + 2 * c->order_off;                            // [count, frames ...] of this chunk of frames
+            CU(cudaMemsetAsync(gram_done, 0, 4, c->cur));
+            k5_gram_kernel<<<nframes, kGramWarps * 32, sizeof(GramSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, P.hist_tol,
+                                                                                   P.hist_lo, M, cost, gram_done);
+            TRY(check_launch(c, "k5_gram"));
+        }
+        {
         const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
         const size_t psm = kPairWarps * kDenseLen * 2;
+        // with a todo list (the frames k5_gram left over) a grid of resident CTAs walks it; else one CTA per (frame, tile)
+        const int pgrid = gram_done ? (int)std::min<int64_t>((int64_t)nframes * tiles, (int64_t)c->sm_count * 16) : nframes * tiles;
 #define PAIRS_LAUNCH(G, MB)                                                                                                  \
         do {                                                                                                                 \
             static bool done_[64] = {false};                                                                                 \
             if (!done_[c->device & 63]) { CU(cudaFuncSetAttribute(k5_pairs_kernel<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); done_[c->device & 63] = true; } \
-            k5_pairs_kernel<G, MB><<<nframes * tiles, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles, \
-                                                                                     P.hist_tol, P.hist_lo, M, cost);          \
+            k5_pairs_kernel<G, MB><<<pgrid, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles, \
+                                                                                     P.hist_tol, P.hist_lo, M, cost, gram_done); \
         } while (0)
         switch (c->pairs_variant) {                          // TSD_PAIRS = <group><minblocks>: A/B of the software pipeline depth / register budget
             case 41: PAIRS_LAUNCH(4, 1); break;
@@ -635,6 +656,7 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         }
 #undef PAIRS_LAUNCH
         TRY(check_launch(c, "k5_pairs"));
+        }
         mark(c, "k5_pairs");
     }
     {
@@ -741,7 +763,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     TRY(s.alloc(&dmeta, (size_t)n * sizeof(WinMeta)));
     TRY(s.alloc(&dlist, (size_t)n * 4));
     TRY(s.alloc(&dflags, (size_t)n));
-    TRY(s.alloc(&den, (size_t)(n > 0 ? n : 1) * kHistGroups * 4));
+    TRY(s.alloc(&den, (size_t)(n > 0 ? n : 1) * kEnergyRows * 4));
     TRY(s.alloc(&dcnt, (size_t)(nframes + 1) * 4));
     TRY(s.alloc(&dooff, (size_t)(nframes + 1) * 4));
     TRY(s.alloc(&dow, (size_t)n * nbytes));
@@ -1107,7 +1129,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
     uint8_t* windows = (uint8_t*)c->b_windows.p + wo * ws;
     uint32_t* entries = (uint32_t*)c->b_entries.p + wo * es;
     WinMeta* meta = (WinMeta*)c->b_meta.p + wo;
-    float* energy = (float*)c->b_energy.p + wo * kHistGroups;          // [25][cap] block of this chunk
+    float* energy = (float*)c->b_energy.p + wo * kEnergyRows;          // [25 energies + chunk boundaries][cap] block of this chunk
     int32_t *list = (int32_t*)c->b_list.p + wo, *slots = (int32_t*)c->b_slots.p + wo, *id = (int32_t*)c->b_id.p + wo, *hund = (int32_t*)c->b_hund.p + wo;
     uint8_t *flags = (uint8_t*)c->b_flags.p + wo, *emit = (uint8_t*)c->b_emit.p + wo;
     DetRec* det = (DetRec*)c->b_det.p + wo;
@@ -1238,7 +1260,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_windows, cap * ws));
     TRY(ensure(c, c->b_entries, cap * es * 4));
     TRY(ensure(c, c->b_meta, cap * sizeof(WinMeta)));
-    TRY(ensure(c, c->b_energy, cap * kHistGroups * 4));
+    TRY(ensure(c, c->b_energy, cap * kEnergyRows * 4));
     TRY(ensure(c, c->b_list, cap * 4));
     TRY(ensure(c, c->b_flags, cap));
     TRY(ensure(c, c->b_slots, cap * 4));

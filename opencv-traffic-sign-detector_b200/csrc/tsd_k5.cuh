@@ -24,6 +24,13 @@
 namespace tsd {
 
 constexpr int kHistGroups = 25;                      // group = bin / 120 (two H rows)
+// k5_gram walks the bins in chunks of kGramKC; the histogram kernel records where each chunk starts in a window's sorted entry
+// list (u16 cb[1..kGramChunks], cb[kGramChunks] = nnz; two per word) in kGramCbWords extra rows of the energy block
+constexpr int kGramKC = 512;                         // bins per chunk: a multiple of 32 (boundaries = prefix popcounts of bitmap words)
+constexpr int kGramChunks = (kHistBins + kGramKC - 1) / kGramKC;
+constexpr int kGramCbWords = (kGramChunks + 1) / 2;
+constexpr int kEnergyRows = kHistGroups + kGramCbWords;   // rows of the [rows][windows] energy block
+static_assert(kGramKC % 32 == 0 && kEnergyRows <= 32, "chunk boundaries");
 constexpr int kClsUnsure = 3;
 
 __device__ __forceinline__ int classify(double sim, double tol, double lo) {
@@ -41,19 +48,23 @@ __device__ __forceinline__ double correl_from(double s12, double s1x, double Ax,
 // Class from the EXACT integer dot product I = sum_b cnt_x[b]*cnt_y[b].  The f64 value the reference computes is
 // s12 = sum fl32(cnt_x a_x) * fl32(cnt_y a_y) = a_x a_y I (1 + e), |e| <= 2^-23 + O(1e-16); the class is decided here
 // when the approximation is further than 2e-6 (relative to sqrt(denom2)) from both thresholds, else kClsUnsure.
-__device__ __forceinline__ int classify_from_int(int I, const WinMeta& x, const WinMeta& y, double tol, double lo) {
+__device__ __forceinline__ int classify_from_int_s(int I, double xA, double xrA, double xs1, float xa, double yA, double yrA, double ys1, float ya,
+                                                   double tol, double lo) {
     const double scale = 1.0 / (double)kHistBins;
-    const double den2 = x.A * y.A;
+    const double den2 = xA * yA;
     if (!(fabs(den2) > DBL_EPSILON)) return classify(1.0, tol, lo);
-    if (!(den2 > 0.0) || !(x.A > 0.0) || !(y.A > 0.0)) return kClsUnsure;
-    const double num = (double)x.a * (double)y.a * (double)I - x.s1 * y.s1 * scale;
-    const double r = x.rA * y.rA;                            // sqrt(denom2) to ~1e-16
+    if (!(den2 > 0.0) || !(xA > 0.0) || !(yA > 0.0)) return kClsUnsure;
+    const double num = (double)xa * (double)ya * (double)I - xs1 * ys1 * scale;
+    const double r = xrA * yrA;                              // sqrt(denom2) to ~1e-16
     const double m = 2e-6 * r + 1e-300;
     const double hi_t = tol * r, lo_t = lo * r;
     if (num > hi_t + m) return 1;
     if (num < lo_t - m) return 0;
     if (num > lo_t + m && num < hi_t - m) return 2;
     return kClsUnsure;
+}
+__device__ __forceinline__ int classify_from_int(int I, const WinMeta& x, const WinMeta& y, double tol, double lo) {
+    return classify_from_int_s(I, x.A, x.rA, x.s1, x.a, y.A, y.rA, y.s1, y.a, tol, lo);
 }
 
 // Cauchy-Schwarz bound from the group energies: can the pair (x, y) reach the merge band at all?
@@ -103,7 +114,7 @@ __device__ __forceinline__ void load_hsv_lut(HsvLut& t, const Tables* __restrict
 // Returns nnz.  All 32 lanes must call.  On return sw.cnt / sw.binof hold the entries (used to fill a dense copy).
 template <int CAP>
 __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const HsvLut& lut, HistScratch<CAP>& sw,
-                                               uint32_t* __restrict__ e, WinMeta* meta, float* Eg, int64_t e_stride) {
+                                               uint32_t* __restrict__ e, WinMeta* meta, float* Eg, int64_t e_stride, bool gram_aux = false) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
     sw.gsum[lane] = 0;
@@ -170,6 +181,12 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
         // 1e-5, is an upper bound of it (only ever used as a bound: Cauchy-Schwarz pruning in k5_pairs / the fold)
         __syncwarp();
         if (lane < kHistGroups) Eg[(int64_t)lane * e_stride] = a * sqrtf((float)sw.gsum[lane]) * 1.00001f;
+        else if (gram_aux && lane < kEnergyRows) {           // entry index where chunk c starts = occupied bins before bitmap word c * kGramKC / 32
+            const int c1 = 2 * (lane - kHistGroups) + 1, c2 = c1 + 1;
+            const uint32_t p1 = c1 < kGramChunks ? sw.prefix[c1 * (kGramKC / 32)] : (uint32_t)nnz;
+            const uint32_t p2 = c2 < kGramChunks ? sw.prefix[c2 * (kGramKC / 32)] : (uint32_t)nnz;
+            reinterpret_cast<uint32_t*>(Eg)[(int64_t)lane * e_stride] = p1 | (p2 << 16);
+        }
     }
     if (lane == 0) {
         const double A = s11 - s1 * s1 * (1.0 / (double)kHistBins);
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const ui
     if (!staged) {                                           // packed public layout: pixels straight from global memory
         for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps)
             hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
-                                 E_T ? E_T + w : nullptr, e_stride);
+                                 E_T ? E_T + w : nullptr, e_stride, E_T != nullptr);
         return;
     }
     // internal layout: the NEXT window travels into registers (128-bit loads, all in flight together) while the current
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const ui
             for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
         }
         hist_build_warp<CAP>(reinterpret_cast<const uint8_t*>(s_px_w), npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
-                             E_T ? E_T + w : nullptr, e_stride);
+                             E_T ? E_T + w : nullptr, e_stride, E_T != nullptr);
     }
 }
 
@@ -249,15 +266,11 @@ __device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_
     return warp_sum(s12);
 }
 
-template <int G, int MINB>
-__global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
-                                                                   const float* __restrict__ E_T, int64_t e_stride,
-                                                                   const int32_t* __restrict__ offsets, int nframes, int es, int RW,
-                                                                   int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M,
-                                                                   int32_t* __restrict__ frame_cost) {
+template <int G>
+__device__ __forceinline__ void k5_pairs_tile(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+                                              const float* __restrict__ E_T, int64_t e_stride, const int32_t* __restrict__ offsets, int es, int RW,
+                                              double tol, double lo, uint32_t* __restrict__ M, int32_t* __restrict__ frame_cost, int f, int tile) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x / tiles_per_frame, tile = blockIdx.x - f * tiles_per_frame;
-    if (f >= nframes) return;
     const int base = offsets[f], n = offsets[f + 1] - base;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int jl = tile * kPairWarps + wid;
@@ -399,6 +412,302 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
         if (lane == 0) {
             Mrow[i0 >> 5] = bd; Mrow[RW + (i0 >> 5)] = bm;
             if (bm && frame_cost) atomicAdd(frame_cost + f, __popc(bm));     // merge-band pairs: the fold's cost predictor
+        }
+    }
+}
+
+// CTA = (frame, tile of kPairWarps items j).  With `todo` (the frames k5_gram left over: more than kGramBM windows, or a count that
+// does not fit a byte) a small grid walks that list; without it the grid covers every (frame, tile).
+template <int G, int MINB>
+__global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+                                                                   const float* __restrict__ E_T, int64_t e_stride,
+                                                                   const int32_t* __restrict__ offsets, int nframes, int es, int RW,
+                                                                   int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M,
+                                                                   int32_t* __restrict__ frame_cost, const int32_t* __restrict__ todo) {
+    const int nf = todo ? min(todo[0], nframes) : nframes;
+    for (int item = blockIdx.x; item < nf * tiles_per_frame; item += gridDim.x) {
+        const int fi = item / tiles_per_frame, tile = item - fi * tiles_per_frame;
+        k5_pairs_tile<G>(entries, meta, E_T, e_stride, offsets, es, RW, tol, lo, M, frame_cost, todo ? todo[1 + fi] : fi, tile);
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================================
+// k5_gram: the same two bit rows from the GRAM MATRIX of a frame's count histograms on the tensor cores.
+// The integer dot products I[j][i] = sum_b cnt_j[b] cnt_i[b] of ALL pairs of a frame are one matrix product C C^T with
+// C = [n windows][3000 bins] -- exact in u8 x u8 -> s32 (mma.sync m16n8k32) when every count fits a byte, which is what this
+// kernel requires of a frame; frames with a count above 255 (a window dominated by one flat colour) or with more than kGramBM
+// windows are appended to the todo list of k5_pairs.  One CTA per frame.  Per chunk of kGramKC bins the sparse entries are
+// scattered into a dense u8 tile in shared memory (row = window, K-major): the entries a chunk needs are known from the
+// boundaries k5_hist recorded, and travel into a per-warp pool one chunk ahead (cp.async, in flight during the tensor-core phase
+// of the previous chunk); four lanes per row scatter them (rows 96..127 of a large frame are second rows of the first 32 groups).
+// Each warp owns one 32 x 32 block of the lower triangle (2 x 2 ldmatrix.x4 + 8 IMMA per 32 bins) and, when there are fewer
+// blocks than warps, one slice of K; the integer partial sums meet in shared memory, where the lane-per-pair classification
+// (classify_from_int, f64 fallback within 2e-6 of a threshold) reads them.
+// =====================================================================================================================
+constexpr int kGramBM = 128;                           // windows per frame handled here
+constexpr int kGramWarps = 12;                         // 96 four-lane groups; 6 lower-triangle 32 x 32 blocks x 2 K slices for n <= 96
+constexpr int kGramGroups = kGramWarps * 8;
+constexpr int kGramPitch = kGramKC + 16;               // bytes per tile row: an odd number of 16-byte units -> conflict-free ldmatrix
+constexpr int kGramPoolBig = 300, kGramPoolSmall = 150;   // 16-byte pieces (4 entries) per warp and chunk: warps 0..3 (up to 16 rows) / the others;
+constexpr int kGramPoolTotal = 4 * kGramPoolBig + (kGramWarps - 4) * kGramPoolSmall;   // the rare overflow is read from global memory
+constexpr int kGramIPitch = kGramBM + 4;               // words per row of the integer result matrix (aliases the tile)
+static_assert((kGramPitch / 16) % 2 == 1 && kGramBM * kGramIPitch * 4 <= kGramBM * kGramPitch, "gram tile layout");
+static_assert(kGramBM == kGramGroups + 32 && kGramWarps >= 10, "rows 96..127 are the second rows of groups 0..31; 10 blocks for n = 128");
+
+struct __align__(16) GramSmem {
+    unsigned char tile[kGramBM * kGramPitch];
+    uint4 pool[kGramPoolTotal];                             // per warp: the next chunk's entries of its rows
+    double A[kGramBM], rA[kGramBM], s1[kGramBM];
+    float a[kGramBM];
+    int32_t nnz[kGramBM];
+    uint16_t cb[kGramBM][kGramChunks + 2];                  // cb[r][c] = first entry of chunk c in row r's list (cb[r][kGramChunks] = nnz)
+    int32_t big;                                            // some count of the frame does not fit a byte
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_u8_16832(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// exact f64 s12 of (j, i) from the two sparse lists: the same terms in the same order as exact_s12_warp (bins missing in j add +0.0)
+__device__ __forceinline__ double exact_s12_sparse_warp(const uint32_t* ej, int nnz_j, float a_j, const uint32_t* ei, int nnz_i, float a_i) {
+    const int lane = threadIdx.x & 31;
+    double s12 = 0;
+    for (int e = lane; e < nnz_i; e += 32) {
+        const uint32_t v = __ldcg(ei + e);
+        const uint32_t bin = v >> 16;
+        int lo_ = 0, hi_ = nnz_j;
+        while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if ((__ldcg(ej + mid) >> 16) < bin) lo_ = mid + 1; else hi_ = mid; }
+        uint32_t cj = 0;
+        if (lo_ < nnz_j) { const uint32_t u = __ldcg(ej + lo_); if ((u >> 16) == bin) cj = u & 0xffffu; }
+        const float hd = (float)cj * a_j;
+        const float ho = (float)(v & 0xffffu) * a_i;
+        s12 += (double)hd * (double)ho;
+    }
+    return warp_sum(s12);
+}
+
+// Copy the entries chunk c needs of one row per four-lane group into the warp's pool (packed group after group behind `fill`,
+// each from its 16-byte aligned-down start).  off / sp = the row's first piece / pieces staged.  All 32 lanes call.
+__device__ __forceinline__ void gram_issue(const uint16_t* cbrow, bool act, const uint32_t* er, int c, uint4* pool, int cap, int& fill,
+                                           int& off, int& sp) {
+    const int lane = threadIdx.x & 31, sub = lane & 3;
+    const int lo_ = act ? (int)cbrow[c] : 0, hi_ = act ? (int)cbrow[c + 1] : 0;
+    const int a4 = lo_ & ~3;
+    const int np = hi_ > lo_ ? (hi_ - a4 + 3) >> 2 : 0;
+    int incl = np;                                           // scan over the warp's 8 groups (the four lanes of a group hold the same value)
+    int t = __shfl_up_sync(0xffffffffu, incl, 4); if (lane >= 4) incl += t;
+    t = __shfl_up_sync(0xffffffffu, incl, 8); if (lane >= 8) incl += t;
+    t = __shfl_up_sync(0xffffffffu, incl, 16); if (lane >= 16) incl += t;
+    off = fill + incl - np;
+    sp = max(0, min(np, cap - off));
+    for (int pc = sub; pc < sp; pc += 4) cp_async16(pool + off + pc, er + a4 + 4 * pc);
+    fill += __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// Scatter the row's entries of chunk `ch` into its tile row (counts as bytes); the staged ones from the pool, the rest from global memory.
+__device__ __forceinline__ void gram_scatter(const uint16_t* cbrow, int ch, const uint4* pool, int off, int sp, const uint32_t* er,
+                                             unsigned char* trow, int k0) {
+    const int sub = threadIdx.x & 3;
+    const int e_lo = cbrow[ch], e_hi = cbrow[ch + 1];
+    const int a4 = e_lo & ~3, e_st = min(e_hi, a4 + 4 * sp);
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(pool + off) - a4;
+    int e = e_lo + sub;
+#pragma unroll 4
+    for (; e < e_st; e += 4) {
+        const uint32_t v = pw[e];
+        trow[(int)(v >> 16) - k0] = (unsigned char)v;
+    }
+    for (; e < e_hi; e += 4) {                               // (rare) the warp's pool was full
+        const uint32_t v = __ldg(er + e);
+        trow[(int)(v >> 16) - k0] = (unsigned char)v;
+    }
+}
+
+__global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+                                                                    const float* __restrict__ E_T, int64_t e_stride,
+                                                                    const int32_t* __restrict__ offsets, int nframes, int es, int RW,
+                                                                    double tol, double lo, uint32_t* __restrict__ M,
+                                                                    int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GramSmem& S = *reinterpret_cast<GramSmem*>(smem_raw);
+    const int f = blockIdx.x;
+    if (f >= nframes) return;
+    const int base = offsets[f], n = offsets[f + 1] - base;
+    if (n < 2 || n > RW * 32) return;                       // (CTA-uniform) nothing to classify / the general fold's frame
+    if (n > kGramBM) {                                      // left to k5_pairs: todo = [count, frames ...]
+        if (threadIdx.x == 0) todo[1 + atomicAdd(todo, 1)] = f;
+        return;
+    }
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    // scatter role: group = tid / 4 owns row `group` and (frames of more than 96 windows, groups 0..31) row group + 96
+    const int grp = tid >> 2, sub = tid & 3;
+    const int row0 = grp, row1 = grp + kGramGroups;
+    const bool act0 = row0 < n, act1 = grp < 32 && row1 < n;
+    const bool two = n > kGramGroups;                        // (CTA-uniform)
+    const uint32_t* er0 = entries + (int64_t)(base + (act0 ? row0 : 0)) * es;
+    const uint32_t* er1 = entries + (int64_t)(base + (act1 ? row1 : 0)) * es;
+    if (tid == 0) S.big = 0;
+    __syncthreads();
+    if ((act0 && sub == 0) || (act1 && sub == 1)) {
+        const int r = sub == 0 ? row0 : row1;
+        const WinMeta m = meta[base + r];
+        S.A[r] = m.A; S.rA[r] = m.rA; S.s1[r] = m.s1; S.a[r] = m.a; S.nnz[r] = m.nnz;
+        if (m.nnz > 0 && m.a < 1.0f / 255.5f) S.big = 1;     // a = (float)(1 / max count): max count >= 256
+        // the row's chunk boundaries (written by k5_hist): every load address of the scatter is known in advance
+        uint16_t* cbr = S.cb[r];
+        cbr[0] = 0;
+#pragma unroll
+        for (int k = 0; k < kGramCbWords; k++) {
+            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(E_T) + (int64_t)(kHistGroups + k) * e_stride + base + r);
+            cbr[2 * k + 1] = (uint16_t)(wv & 0xffffu);
+            if (2 * k + 2 <= kGramChunks) cbr[2 * k + 2] = (uint16_t)(wv >> 16);
+        }
+    }
+    __syncthreads();
+    if (S.big) {                                             // (CTA-uniform) left to k5_pairs
+        if (tid == 0) todo[1 + atomicAdd(todo, 1)] = f;
+        return;
+    }
+    const uint16_t* const cb0 = S.cb[act0 ? row0 : 0];
+    const uint16_t* const cb1 = S.cb[act1 ? row1 : 0];
+    uint4* const pool = S.pool + (wid < 4 ? wid * kGramPoolBig : 4 * kGramPoolBig + (wid - 4) * kGramPoolSmall);
+    const int pcap = wid < 4 ? kGramPoolBig : kGramPoolSmall;
+    int off0 = 0, sp0 = 0, off1 = 0, sp1 = 0;
+    {
+        int fill = 0;
+        gram_issue(cb0, act0, er0, 0, pool, pcap, fill, off0, sp0);
+        if (two) gram_issue(cb1, act1, er1, 0, pool, pcap, fill, off1, sp1);
+    }
+    {                                                        // pull a later frame's entry rows into L2 (this frame's were pulled by an earlier CTA)
+        const int fp = f + 2 * 148;
+        if (fp < nframes) {
+            const int bp = offsets[fp], np = min(offsets[fp + 1] - bp, kGramBM);
+            for (int i = tid; i < np * 12; i += kGramWarps * 32) {
+                const int r = i / 12, l = i - r * 12;
+                if (l * 32 < es) asm volatile("prefetch.global.L2 [%0];" ::"l"(entries + (int64_t)(bp + r) * es + l * 32));
+            }
+        }
+    }
+    const int nb = (n + 31) >> 5, npad = nb * 32, npairs = nb * (nb + 1) / 2;
+    // MMA role: this warp's 32 x 32 block of the lower triangle, 0:(0,0) 1:(1,0) 2:(1,1) 3:(2,0) ..., and its share of the 32-bin
+    // steps: with fewer blocks than warps several warps split K of one block
+    const int kslices = kGramWarps / npairs, kslice = wid / npairs;
+    int bi = -1, bj = 0;
+    if (kslice < kslices) { bi = 0; int q = wid - kslice * npairs; while (q > bi) { q -= bi + 1; bi++; } bj = q; }
+    int acc[2][4][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[mi][ni][q] = 0;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(S.tile);
+    // ldmatrix row addresses (8 x 16-byte rows per matrix = 8 windows x 16 bins): A fragment = (rows 0-7 | 8-15) x (bins 0-15 | 16-31)
+    // in the order a0..a3; B fragments (both n8 halves of 16 windows) = (n 0-7: bins 0-15, 16-31), (n 8-15: bins 0-15, 16-31):
+    // B[k][n] = C[n][k], so the K-major rows are read untransposed
+    const uint32_t a_addr = tile_s + (uint32_t)((max(bi, 0) * 32 + (lane & 7) + ((lane >> 3) & 1) * 8) * kGramPitch + (lane >> 4) * 16);
+    const uint32_t b_addr = tile_s + (uint32_t)((bj * 32 + (lane & 7) + (lane >> 4) * 8) * kGramPitch + ((lane >> 3) & 1) * 16);
+    unsigned char* const trow0 = S.tile + (size_t)row0 * kGramPitch;
+    unsigned char* const trow1 = S.tile + (size_t)(grp < 32 ? row1 : 0) * kGramPitch;
+#pragma unroll 1
+    for (int ch = 0; ch < kGramChunks; ch++) {
+        const int k0 = ch * kGramKC;
+        {                                                    // the group wipes its rows (rows n .. npad stay zero)
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            if (row0 < npad) {
+                uint4* r4 = reinterpret_cast<uint4*>(trow0);
+#pragma unroll 4
+                for (int i = sub; i < kGramPitch / 16; i += 4) r4[i] = z;
+            }
+            if (grp < 32 && row1 < npad) {
+                uint4* r4 = reinterpret_cast<uint4*>(trow1);
+#pragma unroll 4
+                for (int i = sub; i < kGramPitch / 16; i += 4) r4[i] = z;
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (act0) gram_scatter(cb0, ch, pool, off0, sp0, er0, trow0, k0);
+        if (act1) gram_scatter(cb1, ch, pool, off1, sp1, er1, trow1, k0);
+        __syncwarp();                                        // the pool is free again
+        if (ch + 1 < kGramChunks) {
+            int fill = 0;
+            gram_issue(cb0, act0, er0, ch + 1, pool, pcap, fill, off0, sp0);
+            if (two) gram_issue(cb1, act1, er1, ch + 1, pool, pcap, fill, off1, sp1);
+        }
+        __syncthreads();
+        if (bi >= 0) {
+#pragma unroll 2
+            for (int kk = kslice * 32; kk < kGramKC; kk += kslices * 32) {
+                uint32_t a[2][4], b[2][4];
+                ldmatrix_x4(a[0], a_addr + kk);
+                ldmatrix_x4(a[1], a_addr + 16 * kGramPitch + kk);
+                ldmatrix_x4(b[0], b_addr + kk);
+                ldmatrix_x4(b[1], b_addr + 16 * kGramPitch + kk);
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int nj = 0; nj < 2; nj++) {
+                        mma_u8_16832(acc[mi][nj * 2], a[mi], b[nj][0], b[nj][1]);
+                        mma_u8_16832(acc[mi][nj * 2 + 1], a[mi], b[nj][2], b[nj][3]);
+                    }
+            }
+        }
+        __syncthreads();                                     // the tile is wiped (or becomes the result matrix) next
+    }
+    int32_t* sI = reinterpret_cast<int32_t*>(S.tile);
+    if (kslices > 1) {
+        for (int i = tid; i < npad * kGramIPitch; i += kGramWarps * 32) sI[i] = 0;
+        __syncthreads();
+    }
+    if (bi >= 0) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int row = bi * 32 + mi * 16 + g, col = bj * 32 + ni * 8 + 2 * t;
+                int* d0 = &sI[row * kGramIPitch + col];
+                int* d1 = &sI[(row + 8) * kGramIPitch + col];
+                if (kslices > 1) {
+                    atomicAdd(d0, acc[mi][ni][0]); atomicAdd(d0 + 1, acc[mi][ni][1]);
+                    atomicAdd(d1, acc[mi][ni][2]); atomicAdd(d1 + 1, acc[mi][ni][3]);
+                } else {
+                    d0[0] = acc[mi][ni][0]; d0[1] = acc[mi][ni][1];
+                    d1[0] = acc[mi][ni][2]; d1[1] = acc[mi][ni][3];
+                }
+            }
+    }
+    __syncthreads();
+    for (int jl = 1 + wid; jl < n; jl += kGramWarps) {       // one warp per item j, one earlier item per lane
+        const double Aj = S.A[jl], rAj = S.rA[jl], s1j = S.s1[jl];
+        const float aj = S.a[jl];
+        uint32_t* Mrow = M + (int64_t)(base + jl) * 2 * RW;
+        for (int i0 = 0; i0 < jl; i0 += 32) {
+            const int il = i0 + lane;
+            const bool valid = il < jl;
+            const int ii = valid ? il : 0;
+            int c = 0;
+            if (valid) c = classify_from_int_s(sI[jl * kGramIPitch + ii], Aj, rAj, s1j, aj, S.A[ii], S.rA[ii], S.s1[ii], S.a[ii], tol, lo);
+            unsigned unsure = __ballot_sync(0xffffffffu, valid && c == kClsUnsure);
+            while (unsure) {                                // rare: within 2e-6 of a threshold -> exact f64 evaluation
+                const int k = __ffs(unsure) - 1;
+                unsure &= unsure - 1;
+                const int ik = i0 + k;
+                const double s12 = exact_s12_sparse_warp(entries + (int64_t)(base + jl) * es, S.nnz[jl], aj,
+                                                         entries + (int64_t)(base + ik) * es, S.nnz[ik], S.a[ik]);
+                if (lane == k) c = classify(correl_from(s12, s1j, Aj, S.s1[ik], S.A[ik]), tol, lo);
+            }
+            const unsigned bd = __ballot_sync(0xffffffffu, valid && c == 1), bm = __ballot_sync(0xffffffffu, valid && c == 2);
+            if (lane == 0) {
+                Mrow[i0 >> 5] = bd; Mrow[RW + (i0 >> 5)] = bm;
+                if (bm && frame_cost) atomicAdd(frame_cost + f, __popc(bm));
+            }
         }
     }
 }

@@ -6,6 +6,7 @@
 // scalar numpy / OpenCV code (no FMA contraction).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <float.h>
 
