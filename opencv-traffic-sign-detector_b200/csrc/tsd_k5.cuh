@@ -435,9 +435,10 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
 // =====================================================================================================================
 // k5_gram: the same two bit rows from the GRAM MATRIX of a frame's count histograms on the tensor cores.
 // The integer dot products I[j][i] = sum_b cnt_j[b] cnt_i[b] of ALL pairs of a frame are one matrix product C C^T with
-// C = [n windows][3000 bins] -- exact in u8 x u8 -> s32 (mma.sync m16n8k32) when every count fits a byte, which is what this
-// kernel requires of a frame; frames with a count above 255 (a window dominated by one flat colour) or with more than kGramBM
-// windows are appended to the todo list of k5_pairs.  One CTA per frame.  Per chunk of kGramKC bins the sparse entries are
+// C = [n windows][3000 bins] -- exact in u8 x u8 -> s32 (mma.sync m16n8k32) on the low bytes of the counts, which is what the tile
+// holds; the rare counts above 255 (a window dominated by one flat colour) are corrected exactly from the sparse lists before the
+// classification.  Frames with more than kGramBM windows or more than kGramMaxBig such rows are appended to the todo list of
+// k5_pairs.  One CTA per frame.  Per chunk of kGramKC bins the sparse entries are
 // scattered into a dense u8 tile in shared memory (row = window, K-major): the entries a chunk needs are known from the
 // boundaries k5_hist recorded, and travel into a per-warp pool one chunk ahead (cp.async, in flight during the tensor-core phase
 // of the previous chunk); four lanes per row scatter them (rows 96..127 of a large frame are second rows of the first 32 groups).
@@ -451,6 +452,7 @@ constexpr int kGramGroups = kGramWarps * 8;
 constexpr int kGramPitch = kGramKC + 16;               // bytes per tile row: an odd number of 16-byte units -> conflict-free ldmatrix
 constexpr int kGramPoolBig = 300, kGramPoolSmall = 150;   // 16-byte pieces (4 entries) per warp and chunk: warps 0..3 (up to 16 rows) / the others;
 constexpr int kGramPoolTotal = 4 * kGramPoolBig + (kGramWarps - 4) * kGramPoolSmall;   // the rare overflow is read from global memory
+constexpr int kGramMaxBig = 16;                        // more such rows in one frame (flat frames): the frame goes to k5_pairs
 constexpr int kGramIPitch = kGramBM + 4;               // words per row of the integer result matrix (aliases the tile)
 static_assert((kGramPitch / 16) % 2 == 1 && kGramBM * kGramIPitch * 4 <= kGramBM * kGramPitch, "gram tile layout");
 static_assert(kGramBM == kGramGroups + 32 && kGramWarps >= 10, "rows 96..127 are the second rows of groups 0..31; 10 blocks for n = 128");
@@ -462,7 +464,8 @@ struct __align__(16) GramSmem {
     float a[kGramBM];
     int32_t nnz[kGramBM];
     uint16_t cb[kGramBM][kGramChunks + 2];                  // cb[r][c] = first entry of chunk c in row r's list (cb[r][kGramChunks] = nnz)
-    int32_t big;                                            // some count of the frame does not fit a byte
+    int32_t nbig;                                           // rows with a count that does not fit a byte (the tile holds count & 255;
+    int32_t bigrow[kGramMaxBig];                            //  their pairs are corrected exactly before the classification)
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
@@ -551,13 +554,16 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
     const bool two = n > kGramGroups;                        // (CTA-uniform)
     const uint32_t* er0 = entries + (int64_t)(base + (act0 ? row0 : 0)) * es;
     const uint32_t* er1 = entries + (int64_t)(base + (act1 ? row1 : 0)) * es;
-    if (tid == 0) S.big = 0;
+    if (tid == 0) S.nbig = 0;
     __syncthreads();
     if ((act0 && sub == 0) || (act1 && sub == 1)) {
         const int r = sub == 0 ? row0 : row1;
         const WinMeta m = meta[base + r];
         S.A[r] = m.A; S.rA[r] = m.rA; S.s1[r] = m.s1; S.a[r] = m.a; S.nnz[r] = m.nnz;
-        if (m.nnz > 0 && m.a < 1.0f / 255.5f) S.big = 1;     // a = (float)(1 / max count): max count >= 256
+        if (m.nnz > 0 && m.a < 1.0f / 255.5f) {              // a = (float)(1 / max count): max count >= 256
+            const int q = atomicAdd(&S.nbig, 1);
+            if (q < kGramMaxBig) S.bigrow[q] = r;
+        }
         // the row's chunk boundaries (written by k5_hist): every load address of the scatter is known in advance
         uint16_t* cbr = S.cb[r];
         cbr[0] = 0;
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
         }
     }
     __syncthreads();
-    if (S.big) {                                             // (CTA-uniform) left to k5_pairs
+    if (S.nbig > kGramMaxBig) {                              // (CTA-uniform) left to k5_pairs
         if (tid == 0) todo[1 + atomicAdd(todo, 1)] = f;
         return;
     }
@@ -684,6 +690,41 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
             }
     }
     __syncthreads();
+    if (S.nbig > 0) {                                        // (CTA-uniform, rare) counts above 255: the tile held count & 255
+        // I_true - I_tile of a pair = sum over the bins where either count exceeds 255 of (c_r c_i - (c_r & 255)(c_i & 255)); every
+        // such entry (r, bin) is visited once and corrects its pairs with all other rows i (a pair big in the SAME bin on both sides
+        // is left to the lower row's entry)
+        for (int q = wid; q < S.nbig; q += kGramWarps) {
+            const int r = S.bigrow[q];
+            const uint32_t* erow = entries + (int64_t)(base + r) * es;
+            const int nz = S.nnz[r];
+            for (int e0 = 0; e0 < nz; e0 += 32) {
+                const uint32_t v = e0 + lane < nz ? __ldg(erow + e0 + lane) : 0u;
+                unsigned mb = __ballot_sync(0xffffffffu, (v & 0xffffu) > 255u);
+                while (mb) {
+                    const int k = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const uint32_t vb = __shfl_sync(0xffffffffu, v, k);
+                    const uint32_t bin = vb >> 16;
+                    const int cr = (int)(vb & 0xffffu);
+                    for (int i = lane; i < n; i += 32) {
+                        if (i == r) continue;
+                        const uint32_t* ei = entries + (int64_t)(base + i) * es;
+                        int lo_ = 0, hi_ = S.nnz[i];
+                        const int nzi = hi_;
+                        while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if ((__ldg(ei + mid) >> 16) < bin) lo_ = mid + 1; else hi_ = mid; }
+                        if (lo_ >= nzi) continue;
+                        const uint32_t u = __ldg(ei + lo_);
+                        if ((u >> 16) != bin) continue;
+                        const int ci = (int)(u & 0xffffu);
+                        if (ci > 255 && i < r) continue;
+                        atomicAdd(&sI[max(r, i) * kGramIPitch + min(r, i)], cr * ci - (cr & 255) * (ci & 255));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
     for (int jl = 1 + wid; jl < n; jl += kGramWarps) {       // one warp per item j, one earlier item per lane
         const double Aj = S.A[jl], rAj = S.rA[jl], s1j = S.s1[jl];
         const float aj = S.a[jl];

@@ -306,6 +306,36 @@ def test_chain_synthetic_vs_oracle(ctx_det, oracle, templates, tsd):
         assert _records(det) == exp
 
 
+def test_chain_gram_block_variants_vs_oracle(ctx_det, oracle, templates, tsd):
+    """Frames of ~12, ~45, ~75, ~110 and ~135 windows after the aspect filter in ONE batch: the tensor-core pair kernel (k5_gram)
+    runs with 1, 3, 6 and 10 blocks of its lower triangle (K split over 12, 4, 2 and 1 warps; second rows of the first 32 lane
+    groups above 96 windows) and hands the frames above 128 windows to k5_pairs through its todo list."""
+    red6, blue6 = templates
+    H, W = 800, 1360
+    per_frame = [30, 110, 185, 270, 335, 30, 270, 110, 335, 185, 250, 300]
+    F = len(per_frame)
+    frames = tsd.synth.make_frames(F, H, W, seed=tsd.synth.FRAME_SEED + 5)
+    for f, (y, x, side) in ((2, (100, 200, 260)), (3, (300, 700, 200)), (6, (50, 50, 420)), (9, (400, 900, 300))):
+        frames[f][y:y + side, x:x + side] = np.array([40 + 20 * f, 60, 210 - 15 * f], np.uint8)   # flat patches: some windows with counts > 255
+    bl, off = [], [0]
+    for f, nbx in enumerate(per_frame):
+        b, _ = tsd.synth.make_boxes(1, nbx, H, W, seed=tsd.synth.BOX_SEED + 100 + f)
+        bl.append(b)
+        off.append(off[-1] + len(b))
+    boxes, off = np.concatenate(bl), np.asarray(off, np.int32)
+    det, counts = ctx_det.detect_frames(frames, boxes, off)
+    exp, tot, nwin = [], np.zeros(4, np.int64), []
+    for f in range(F):
+        o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+        tot += o["stage_counts"]
+        nwin.append(int(o["stage_counts"][1]))
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    assert min(nwin) <= 32 and any(32 < v <= 64 for v in nwin) and any(64 < v <= 96 for v in nwin)
+    assert any(96 < v <= 128 for v in nwin) and max(nwin) > 128, nwin
+    assert counts.tolist() == tot.tolist()
+    assert _records(det) == exp
+
+
 def test_chain_flat_frames_vs_oracle(ctx_det, oracle, templates, tsd):
     """Frames made of large flat patches (windows whose histogram puts all 625 pixels into one or two bins, many exactly equal
     windows -> the pop-by-pixel-equality rule, degenerate correlations), mixed with ordinary frames in one batch."""
