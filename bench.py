@@ -354,6 +354,7 @@ def run_b200(args, rank, world, local_rank):
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    ctx.flush()                                              # (overlap mode defers the last batch's join: the stream waits for it here)
     ev1.record(stream)
     ctx.synchronize()
     barrier()

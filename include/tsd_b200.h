@@ -78,6 +78,11 @@ TSD_API int tsd_destroy(tsd_ctx *ctx);
 /* The context's cudaStream_t (as void*), so callers (torch) can order their own work with it. */
 TSD_API void *tsd_stream(tsd_ctx *ctx);
 TSD_API int tsd_synchronize(tsd_ctx *ctx);
+/* Consecutive tsd_enqueue_frames calls alternate between two scratch slots and two internal streams, so the latency-bound fold
+ * of one batch runs under the throughput-bound kernels of the next (TSD_OVERLAP=0 in the environment turns this off).  The
+ * context's stream therefore waits for a batch only when the NEXT batch is enqueued, or when tsd_flush / tsd_synchronize /
+ * tsd_fetch_detections is called: tsd_flush makes tsd_stream() wait for everything enqueued so far without blocking the host. */
+TSD_API int tsd_flush(tsd_ctx *ctx);
 /* Page-lock a caller-owned host buffer (cudaHostRegister, mapped).  tsd_detect_frames with TSD_MEM_HOST reads page-locked
  * frames IN PLACE over PCIe (only the candidate ROIs are transferred); pageable frames are copied whole, in chunks that
  * overlap the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */

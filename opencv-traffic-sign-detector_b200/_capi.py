@@ -51,6 +51,7 @@ _SIGNATURES = {
     "tsd_destroy": (_i, [_vp]),
     "tsd_stream": (_vp, [_vp]),
     "tsd_synchronize": (_i, [_vp]),
+    "tsd_flush": (_i, [_vp]),
     "tsd_launch_count": (_i64, [_vp]),
     "tsd_mean_windows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     "tsd_score": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),

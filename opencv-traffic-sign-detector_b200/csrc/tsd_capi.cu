@@ -52,9 +52,18 @@ struct tsd_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int stream_chunk = -1;                   // TSD_STREAM_CHUNK: frames per chunk (0 = auto, -1 = never chunk = default: measured slower,
                                              // the fold's shared memory footprint keeps other kernels from co-residing)
-    struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; };
+    struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; int sidx; };   // sidx: the chunk's record in b_summary
     std::vector<ChunkInfo> chunks;           // of the last enqueue
     std::vector<cudaEvent_t> ev_chunk;
+    // Default (TSD_OVERLAP=0 turns it off): consecutive tsd_enqueue_frames calls alternate between two scratch slots and two streams, so the latency-bound
+    // fold of one batch runs under the throughput-bound kernels of the next.  tsd_stream() is ordered after a batch only once the
+    // NEXT call, tsd_flush, tsd_synchronize or tsd_fetch_detections has been issued (the join is deferred by one call).
+    int overlap = 1, slot = 0, pending_join = -1;
+    size_t slot_cap = 0, slot_fcap = 0;
+    cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr};
+    cudaStream_t os[2] = {nullptr, nullptr}, hp[2] = {nullptr, nullptr};   // per slot: the chain's stream / a high-priority stream for its fold (TSD_OVERLAP=2)
+    cudaEvent_t ev_hp_a[2] = {nullptr, nullptr}, ev_hp_b[2] = {nullptr, nullptr};
+    bool ov_active = false;
     int pipe_mode = 0;                       // chunked enqueue as a producer (K1+K2) / consumer (rest) pipeline instead of alternating streams
     DevBuf b_summary, b_order, b_gramdone;
     size_t order_off = 0;                   // offset (ints) of the current chunk inside b_order
@@ -189,10 +198,18 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
         CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
         CU(cudaStreamCreateWithPriority(&c->cs[0], cudaStreamNonBlocking, lo_p));
         CU(cudaStreamCreateWithPriority(&c->cs[1], cudaStreamNonBlocking, hi_p));
-        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+            CU(cudaStreamCreateWithPriority(&c->os[i], cudaStreamNonBlocking, lo_p));
+            CU(cudaStreamCreateWithPriority(&c->hp[i], cudaStreamNonBlocking, hi_p));
+            CU(cudaEventCreateWithFlags(&c->ev_hp_a[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_hp_b[i], cudaEventDisableTiming));
+        }
     }
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     { const char* e = getenv("TSD_STREAM_CHUNK"); if (e) c->stream_chunk = atoi(e); }
+    { const char* e = getenv("TSD_OVERLAP"); if (e) c->overlap = atoi(e); }
+    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_slot_fork[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
@@ -295,6 +312,13 @@ int tsd_destroy(tsd_ctx* c) {
     DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_slot_fork[i]) cudaEventDestroy(c->ev_slot_fork[i]);
+        if (c->os[i]) cudaStreamDestroy(c->os[i]);
+        if (c->hp[i]) cudaStreamDestroy(c->hp[i]);
+        if (c->ev_hp_a[i]) cudaEventDestroy(c->ev_hp_a[i]);
+        if (c->ev_hp_b[i]) cudaEventDestroy(c->ev_hp_b[i]);
+    }
     for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
     for (DevBuf* b : more) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
@@ -321,9 +345,22 @@ int tsd_host_unregister(void* p) {
     return TSD_OK;
 }
 
+// TSD_OVERLAP: make the context's stream wait for the batch enqueued last (its join was deferred)
+static int join_pending(tsd_ctx* c) {
+    if (c->pending_join >= 0) { CU(cudaStreamWaitEvent(c->stream, c->ev_join[c->pending_join], 0)); c->pending_join = -1; }
+    return TSD_OK;
+}
+
+int tsd_flush(tsd_ctx* c) {
+    if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    return join_pending(c);
+}
+
 int tsd_synchronize(tsd_ctx* c) {
     if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
     CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
 }
@@ -332,6 +369,7 @@ int64_t tsd_launch_count(tsd_ctx* c) { return c ? c->launches : 0; }
 
 int tsd_set_profiling(tsd_ctx* c, int on) {
     if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    TRY(join_pending(c));
     c->profiling = on != 0;
     c->ev_used = 0;                                          // (re)start accumulating
     return TSD_OK;
@@ -454,7 +492,7 @@ int tsd_set_knn(tsd_ctx* c, const double* xbar, const double* scalings, int nfea
 struct Stage {                                               // stream-ordered temporaries, freed on destruction
     tsd_ctx* c;
     std::vector<void*> ptrs;
-    explicit Stage(tsd_ctx* ctx) : c(ctx) {}
+    explicit Stage(tsd_ctx* ctx) : c(ctx) { join_pending(ctx); }
     ~Stage() { for (void* p : ptrs) cudaFreeAsync(p, c->stream); }
     int alloc(void** p, size_t bytes) {
         CU(cudaMallocAsync(p, bytes ? bytes : 1, c->stream));
@@ -659,6 +697,13 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         }
         mark(c, "k5_pairs");
     }
+    cudaStream_t chain_stream = c->cur;
+    const bool fold_hp = c->ov_active && c->overlap >= 2;   // the latency-bound fold goes first wherever an SM has room: its own high-priority stream
+    if (fold_hp) {
+        CU(cudaEventRecord(c->ev_hp_a[c->slot], chain_stream));
+        CU(cudaStreamWaitEvent(c->hp[c->slot], c->ev_hp_a[c->slot], 0));
+        c->cur = c->hp[c->slot];
+    }
     {
         int rc;
         if (max_n <= 256) rc = npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
@@ -669,7 +714,13 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
     (void)may_exceed;
     k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
-    return check_launch(c, "k5_fold");
+    TRY(check_launch(c, "k5_fold"));
+    if (fold_hp) {
+        CU(cudaEventRecord(c->ev_hp_b[c->slot], c->cur));
+        c->cur = chain_stream;
+        CU(cudaStreamWaitEvent(chain_stream, c->ev_hp_b[c->slot], 0));
+    }
+    return TSD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1242,18 +1293,35 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         ci.f0 = k * CFr; ci.cf = nframes - ci.f0 < CFr ? nframes - ci.f0 : CFr;
         // boxes of the chunk: exact when the offsets are on the host, else bounded by cf * max_boxes_per_frame (and by nb)
         ci.nbcap = !ho.empty() ? ho[ci.f0 + ci.cf] - ho[ci.f0] : (nchunks == 1 ? nb : (int)std::min<int64_t>((int64_t)ci.cf * max_boxes_per_frame, nb));
-        ci.wo = wtot; ci.fo = ci.f0 + k;
+        ci.wo = wtot; ci.fo = ci.f0 + k; ci.sidx = k;
         wtot += (size_t)((ci.nbcap > 0 ? ci.nbcap : 1) + 3) & ~(size_t)3;     // keeps every chunk's slices 16-byte aligned
         c->chunks.push_back(ci);
     }
-    const size_t cap = wtot, fcap = (size_t)nframes + nchunks;
+    size_t cap = wtot, fcap = (size_t)nframes + nchunks;
+    const bool ov = c->overlap && !c->profiling && nchunks == 1;
+    if (ov) {                                                // this batch lives in slot `slot` of doubled scratch buffers
+        c->slot ^= 1;
+        const size_t need_w = (wtot + 63) & ~(size_t)63, need_f = ((size_t)nframes + 2 + 63) & ~(size_t)63;
+        if (need_w > c->slot_cap || need_f > c->slot_fcap) { // the layout changes: nothing may be in flight
+            TRY(join_pending(c));
+            CU(cudaStreamSynchronize(c->stream));
+            if (need_w > c->slot_cap) c->slot_cap = need_w;
+            if (need_f > c->slot_fcap) c->slot_fcap = need_f;
+        }
+        c->chunks[0].wo = (size_t)c->slot * c->slot_cap;
+        c->chunks[0].fo = (int)((size_t)c->slot * c->slot_fcap);
+        c->chunks[0].sidx = c->slot;
+        cap = 2 * c->slot_cap; fcap = 2 * c->slot_fcap;
+    } else {
+        TRY(join_pending(c));
+    }
     TRY(ensure(c, c->b_cnt, fcap * 4));
     TRY(ensure(c, c->b_winoff, fcap * 4));
     TRY(ensure(c, c->b_survcnt, fcap * 4));
     TRY(ensure(c, c->b_survoff, fcap * 4));
     TRY(ensure(c, c->b_detcnt, fcap * 4));
     TRY(ensure(c, c->b_detoff, fcap * 4));
-    TRY(ensure(c, c->b_summary, (size_t)nchunks * 16));
+    TRY(ensure(c, c->b_summary, (size_t)(nchunks > 2 ? nchunks : 2) * 16));
     TRY(ensure(c, c->b_order, fcap * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));
@@ -1282,7 +1350,19 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(ensure(c, c->b_pairs, cap * 2 * RW * sizeof(uint32_t)));
     }
     int rc = TSD_OK;
-    if (nchunks == 1) {
+    if (ov) {
+        const tsd_ctx::ChunkInfo& ci = c->chunks[0];
+        const int sl = c->slot;
+        CU(cudaEventRecord(c->ev_slot_fork[sl], c->stream));
+        CU(cudaStreamWaitEvent(c->os[sl], c->ev_slot_fork[sl], 0));
+        TRY(join_pending(c));                                // the PREVIOUS batch: the context's stream waits for it only now, after this batch's fork
+        c->cur = c->os[sl];
+        c->ov_active = true;
+        rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, ci.sidx);
+        c->ov_active = false;
+        CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
+        c->pending_join = sl;
+    } else if (nchunks == 1) {
         c->cur = c->stream;
         rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, c->chunks[0].nbcap, max_boxes_per_frame, 0, 0, 0);
     } else {
@@ -1335,6 +1415,7 @@ int tsd_stat_hist_entries(tsd_ctx* c, int64_t* total) {
     if (!c || !total) return fail(TSD_E_INVALID, "bad argument");
     if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
     CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     unsigned long long* d = nullptr;
     CU(cudaMallocAsync((void**)&d, 8, c->stream));
     CU(cudaMemsetAsync(d, 0, 8, c->stream));
@@ -1353,9 +1434,11 @@ int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* n
     if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
     CU(cudaSetDevice(c->device));
     static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
+    TRY(join_pending(c));
     const int nchunks = (int)c->chunks.size();
     std::vector<int32_t> h((size_t)nchunks * 4);
-    CU(cudaMemcpyAsync(h.data(), c->b_summary.p, (size_t)nchunks * 16, cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < nchunks; k++)
+        CU(cudaMemcpyAsync(h.data() + 4 * k, (int32_t*)c->b_summary.p + 4 * c->chunks[k].sidx, 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int64_t tw = 0, ts = 0, td = 0;
     for (int k = 0; k < nchunks; k++) { tw += h[4 * k]; ts += h[4 * k + 1]; td += h[4 * k + 2]; }

@@ -82,6 +82,11 @@ class Context:
     def synchronize(self):
         check(self._L.tsd_synchronize(self._h))
 
+    def flush(self):
+        """Make the context's stream wait for every batch enqueued so far (no host block): consecutive enqueue_frames calls run on
+        two internal streams and their join to `stream` is deferred by one call (TSD_OVERLAP=0 disables the overlap)."""
+        check(self._L.tsd_flush(self._h))
+
     def pin(self, array):
         """Page-lock a caller-owned C-contiguous numpy array so that detect_frames reads it in place over PCIe
         (only candidate ROIs are transferred).  Call unpin(array) before the array is freed."""

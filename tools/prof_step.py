@@ -16,6 +16,7 @@ ap.add_argument("--boxes", type=int, default=200)
 ap.add_argument("--H", type=int, default=800)
 ap.add_argument("--W", type=int, default=1360)
 ap.add_argument("--times", action="store_true")
+ap.add_argument("--wall", action="store_true", help="CUDA-event time of the steps enqueued back to back (no per-stage events)")
 ap.add_argument("--mode", default="det", choices=["det", "rec"], help="det: K1 K2 K5 K3 K4 (x1.30, 25x25); rec: K1 K2 K5 K6 K7 K8 (x1.15, 32x32)")
 a = ap.parse_args()
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "det_templates.npz"))
@@ -39,9 +40,21 @@ if a.times:
         one()
     ctx.synchronize()
     ctx.set_profiling(True)
+if a.wall:
+    for _ in range(3):
+        one()
+    ctx.synchronize()
+    st = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
 for _ in range(a.steps):
     one()
+if a.wall:
+    ctx.flush()
+    e1.record(st)
 ctx.synchronize()
+if a.wall:
+    print("ms_per_step %.4f" % (e0.elapsed_time(e1) / a.steps))
 if a.times:
     print({k: round(v / a.steps, 4) for k, v in ctx.stage_times()})
 det, counts = ctx.fetch_detections(int(off[-1]))
