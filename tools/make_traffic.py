@@ -8,7 +8,7 @@ import os
 import subprocess
 import sys
 
-STAGE = [("k2_crop_resize", "k2_crop_resize"), ("k5_hist", "k5_hist"), ("k5_pairs", "k5_pairs"), ("k5_fold", "k5_fold"),
+STAGE = [("k2_crop_resize", "k2_crop_resize"), ("k5_hist", "k5_hist"), ("k5_gram", "k5_pairs"), ("k5_pairs", "k5_pairs"), ("k5_fold", "k5_fold"),
          ("k3_masks", "k3_masks"), ("k4_score", "k4_score"), ("k1_", "k1_expand_filter")]
 rep, nwin, label = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -23,13 +23,13 @@ for r in rows[2:]:
     if st is None:
         continue
     b = sum(float(r[col[k]]) * mult[units[col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    e = res.setdefault(st, {"dram_bytes": 0.0, "launches": 0, "kernel": name.split("(")[0]})
-    e["dram_bytes"] += b
-    e["launches"] += 1
+    e = res.setdefault(st, {}).setdefault(name.split("(")[0], [0.0, 0])     # a stage = one launch of each of its kernels per step
+    e[0] += b
+    e[1] += 1
 final = {}
-for st, e in res.items():
-    per_launch = e["dram_bytes"] / e["launches"] if st != "k1_expand_filter" else e["dram_bytes"]
-    final[st] = {"dram_bytes_per_window": per_launch / nwin, "kernel": e["kernel"], "source": "%s (%d aspect-passing windows)" % (label, nwin)}
+for st, ks in res.items():
+    per_step = sum(b / n for b, n in ks.values())
+    final[st] = {"dram_bytes_per_window": per_step / nwin, "kernel": " + ".join(ks), "source": "%s (%d aspect-passing windows)" % (label, nwin)}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 json.dump(final, open(p, "w"), indent=1)
 print(json.dumps(final, indent=1))
