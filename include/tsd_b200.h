@@ -153,6 +153,21 @@ TSD_API int tsd_preprocess(tsd_ctx *ctx, const uint8_t *frames, int nframes, int
 TSD_API int tsd_mean_windows(tsd_ctx *ctx, const uint8_t *windows, const int32_t *group_offsets, int ngroups, int D,
                              uint8_t *mean_out, int mem);
 
+/* N4 (reporting)  The matching loops of the evaluators.  Host pointers.
+ * tsd_match_detections = checkIfDetectionByTypeOnFileIsCorrectIncorrectDuplicated + getCorrectsAndWrongByTypeOnFile
+ * (DET/source.py:401-450) for all files and types at once: det / gt int32 [n][6] = (frame, x1, y1, x2, y2, type bucket 0..5), gt grouped
+ * by frame (gt_offsets int32 [nframes+1]); status int32 [ndet] (1 = "correct": best same-type ground truth by
+ * sqrt(f(d_TL) f(d_BR)) exceeds tol = 0.85), match int32 [ndet] (its gt row or -1), tally int32 [nframes][6][4] =
+ * (correct, incorrect, not detected, expected).  Needs tsd_set_similarity_table. */
+TSD_API int tsd_match_detections(tsd_ctx *ctx, const int32_t *det, int ndet, const int32_t *gt, const int32_t *gt_offsets, int nframes,
+                                 double tol, int32_t *status, int32_t *match, int32_t *tally);
+/* tsd_match_iou = the loop of precision_recall_curve (Reconocimiento de Objetos/evaluar_resultados.py:224-262) with bboxes_overlap
+ * (:53-89): det int32 [ndet][5] = (left, top, right, bottom, index in the score-descending list) grouped by image and, inside an
+ * image, in list order (det_offsets int32 [nimages+1]); gt int32 [ngt][5] = (left, top, right, bottom, class; -1 = ignore region)
+ * grouped by image (gt_offsets); tp / fp uint8 [ndet] indexed by list position. */
+TSD_API int tsd_match_iou(tsd_ctx *ctx, const int32_t *det, const int32_t *det_offsets, const int32_t *gt, const int32_t *gt_offsets,
+                          int nimages, double ovr, uint8_t *tp, uint8_t *fp);
+
 /* K3  getColorMaskRedOrBlue(img, 'r') and (img, 'b') (DET/source.py:63-89): uint8 [n][D*D] in {0,255} each. */
 TSD_API int tsd_color_masks(tsd_ctx *ctx, const uint8_t *windows, int n, int D, uint8_t *red, uint8_t *blue, int mem);
 /* cv2.cvtColor(BGR2HSV) (DET/source.py:65,576) for npx pixels. */

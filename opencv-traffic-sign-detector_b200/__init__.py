@@ -8,11 +8,12 @@ Layout
   source_rec.py    drop-in mirror of the hot-path functions of "Reconocimiento de Objetos/source.py"
   sharding.py      frame sharding across ranks (one process per GPU) + the reporting gather
   synth.py         synthetic frames / candidate boxes of SURVEY.md section 8(d)
+  evaluate.py      the two evaluators (generateStatistics, precision_recall_curve / AP) with their matching loops on the GPU
 """
 from . import _capi, synth  # noqa: F401
 from ._capi import DET_DTYPE, HOG_LEN, MEM_DEVICE, MEM_HOST, RUN_DETECT, RUN_RECOGNIZE, TsdError, build  # noqa: F401
 from .engine import Context, default_config, similarity_table  # noqa: F401
-from . import sharding, source_det, source_rec  # noqa: F401,E402
+from . import evaluate, sharding, source_det, source_rec  # noqa: F401,E402
 
 __all__ = ["Context", "default_config", "similarity_table", "TsdError", "build", "DET_DTYPE", "HOG_LEN",
            "RUN_DETECT", "RUN_RECOGNIZE", "MEM_HOST", "MEM_DEVICE", "synth"]

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "tsd_stream": (_vp, [_vp]),
     "tsd_synchronize": (_i, [_vp]),
     "tsd_flush": (_i, [_vp]),
+    "tsd_match_detections": (_i, [_vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "tsd_match_iou": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp]),
     "tsd_launch_count": (_i64, [_vp]),
     "tsd_mean_windows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     "tsd_score": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),

@@ -100,6 +100,7 @@ struct tsd_ctx {
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int pairs_variant = 18;
+    int fold_ctas = 0;                                       // TSD_FOLD_CTAS: cap of resident fold CTAs per SM (0 = what fits)
     int use_gram = 1;                                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
     int hist_minb = 8;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
     int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
@@ -236,6 +237,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
+    { const char* e = getenv("TSD_FOLD_CTAS"); if (e) c->fold_ctas = atoi(e); }
     { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
@@ -614,7 +616,8 @@ static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32
     k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter);
     TRY(check_launch(c, "k5_order"));
     int grid = cdiv(nframes, warps);
-    if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
+    const int resident = c->fold_ctas > 0 && c->fold_ctas < per_sm ? c->fold_ctas : per_sm;
+    if (grid > resident * c->sm_count) grid = resident * c->sm_count;
     k5_fold_warp_kernel<RMAX, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter);
     return check_launch(c, "k5_fold_warp");
 }
@@ -948,6 +951,68 @@ int tsd_mean_windows(tsd_ctx* c, const uint8_t* windows, const int32_t* group_of
     mean_windows_kernel<<<ngroups, 32, 0, c->cur>>>((uint8_t*)dw, (int32_t*)dg, ngroups, nbytes, (uint8_t*)dm);
     TRY(check_launch(c, "mean_windows"));
     TRY(s.out(mean_out, dm, (size_t)ngroups * nbytes));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int tsd_match_detections(tsd_ctx* c, const int32_t* det, int ndet, const int32_t* gt, const int32_t* gt_offsets, int nframes, double tol,
+                         int32_t* status, int32_t* match, int32_t* tally) {
+    if (!c || ndet < 0 || nframes < 0 || !gt_offsets || (ndet && (!det || !status || !match)) || (nframes && !tally)) return fail(TSD_E_INVALID, "bad argument");
+    if (!c->d_simtab) return fail(TSD_E_STATE, "similarity table not set (tsd_set_similarity_table)");
+    const int ngt = gt_offsets[nframes];
+    if (ngt < 0 || (ngt && !gt)) return fail(TSD_E_INVALID, "bad ground truth");
+    for (int i = 0; i < ndet; i++) if (det[6 * i + 5] < 0 || det[6 * i + 5] > 5) return fail(TSD_E_INVALID, "detection %d: type bucket %d not in 0..5", i, det[6 * i + 5]);
+    for (int g = 0; g < ngt; g++) if (gt[6 * g + 5] < 0 || gt[6 * g + 5] > 5 || gt[6 * g] < 0 || gt[6 * g] >= nframes) return fail(TSD_E_INVALID, "ground truth %d: bad frame / type bucket", g);
+    CU(cudaSetDevice(c->device));
+    Stage s(c);
+    void *dd = nullptr, *dg = nullptr, *dof, *dst, *dm, *dh, *dt;
+    TRY(s.in(det, (size_t)ndet * 24, &dd));
+    TRY(s.in(gt, (size_t)ngt * 24, &dg));
+    TRY(s.in(gt_offsets, (size_t)(nframes + 1) * 4, &dof));
+    TRY(s.alloc(&dst, (size_t)ndet * 4));
+    TRY(s.alloc(&dm, (size_t)ndet * 4));
+    TRY(s.alloc(&dh, (size_t)ngt));
+    TRY(s.alloc(&dt, (size_t)nframes * 24 * 4));
+    CU(cudaMemsetAsync(dh, 0, ngt > 0 ? ngt : 1, c->stream));
+    CU(cudaMemsetAsync(dt, 0, (size_t)(nframes > 0 ? nframes : 1) * 24 * 4, c->stream));
+    if (ndet) {
+        eval_match_kernel<<<cdiv(ndet, 128), 128, 0, c->cur>>>((const EvalBox*)dd, ndet, (const EvalBox*)dg, (const int32_t*)dof, nframes, c->d_simtab,
+                                                               c->simtab_n, tol, (int32_t*)dst, (int32_t*)dm, (uint8_t*)dh, (int32_t*)dt);
+        TRY(check_launch(c, "eval_match"));
+    }
+    if (ngt) {
+        eval_tally_gt_kernel<<<cdiv(ngt, 128), 128, 0, c->cur>>>((const EvalBox*)dg, ngt, (const uint8_t*)dh, (int32_t*)dt);
+        TRY(check_launch(c, "eval_tally_gt"));
+    }
+    if (ndet) { TRY(s.out(status, dst, (size_t)ndet * 4)); TRY(s.out(match, dm, (size_t)ndet * 4)); }
+    if (nframes) TRY(s.out(tally, dt, (size_t)nframes * 24 * 4));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSD_OK;
+}
+
+int tsd_match_iou(tsd_ctx* c, const int32_t* det, const int32_t* det_offsets, const int32_t* gt, const int32_t* gt_offsets, int nimages, double ovr,
+                  uint8_t* tp, uint8_t* fp) {
+    if (!c || nimages < 0 || !det_offsets || !gt_offsets) return fail(TSD_E_INVALID, "bad argument");
+    const int ndet = det_offsets[nimages], ngt = gt_offsets[nimages];
+    if (ndet < 0 || ngt < 0 || (ndet && (!det || !tp || !fp)) || (ngt && !gt)) return fail(TSD_E_INVALID, "bad argument");
+    for (int i = 0; i < ndet; i++) if (det[5 * i + 4] < 0 || det[5 * i + 4] >= ndet) return fail(TSD_E_INVALID, "detection %d: list index out of range", i);
+    CU(cudaSetDevice(c->device));
+    if (nimages == 0 || ndet == 0) return TSD_OK;
+    Stage s(c);
+    void *dd, *ddo, *dg = nullptr, *dgo, *du, *dtp, *dfp;
+    TRY(s.in(det, (size_t)ndet * 20, &dd));
+    TRY(s.in(det_offsets, (size_t)(nimages + 1) * 4, &ddo));
+    TRY(s.in(gt, (size_t)ngt * 20, &dg));
+    TRY(s.in(gt_offsets, (size_t)(nimages + 1) * 4, &dgo));
+    TRY(s.alloc(&du, (size_t)ngt));
+    TRY(s.alloc(&dtp, (size_t)ndet));
+    TRY(s.alloc(&dfp, (size_t)ndet));
+    CU(cudaMemsetAsync(du, 0, ngt > 0 ? ngt : 1, c->stream));
+    eval_iou_kernel<<<cdiv(nimages, 64), 64, 0, c->cur>>>((const EvalDt*)dd, (const int32_t*)ddo, (const EvalGt*)dg, (const int32_t*)dgo, nimages, ovr,
+                                                          (uint8_t*)du, (uint8_t*)dtp, (uint8_t*)dfp);
+    TRY(check_launch(c, "eval_iou"));
+    TRY(s.out(tp, dtp, (size_t)ndet));
+    TRY(s.out(fp, dfp, (size_t)ndet));
     CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
 }

@@ -1710,6 +1710,89 @@ __global__ void label_emit_kernel(const int32_t* __restrict__ lab, const int32_t
     if (i < n) emit[i] = lab[i] != 0 ? 1 : 0;
 }
 
+// =====================================================================================================
+// N4  the evaluators' matching loops (reporting only).
+// eval_match: checkIfDetectionByTypeOnFileIsCorrectIncorrectDuplicated (DET:425-450) for every detection at once -- best ground
+// truth of the same frame and type bucket by sqrt(f(d_TL) f(d_BR)) (first strict maximum), "correct" when it exceeds tol.  A
+// ground truth beyond the similarity table (a corner further than 255 px: f < 0.16, similarity < 0.4) can never be the match of a
+// correct detection and is skipped.  eval_tally_*: the per (frame, type) counts of getCorrectsAndWrongByTypeOnFile (DET:401-422).
+// =====================================================================================================
+struct EvalBox { int32_t frame, x1, y1, x2, y2, type; };     // type = bucket 0..5 (DET:371-386: anything that is not 1..5 lands in the sixth)
+
+__global__ void eval_match_kernel(const EvalBox* __restrict__ det, int ndet, const EvalBox* __restrict__ gt, const int32_t* __restrict__ gt_offsets,
+                                  int nframes, const double* __restrict__ simtab, int simtab_n, double tol, int32_t* __restrict__ status,
+                                  int32_t* __restrict__ match, uint8_t* __restrict__ gt_hit, int32_t* __restrict__ tally) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ndet) return;
+    const EvalBox d = det[i];
+    double best = -INFINITY;
+    int bi = -1;
+    if (d.frame >= 0 && d.frame < nframes) {
+        for (int g = gt_offsets[d.frame]; g < gt_offsets[d.frame + 1]; g++) {
+            const EvalBox r = gt[g];
+            if (r.type != d.type) continue;
+            const int64_t ax = (int64_t)d.x1 - r.x1, ay = (int64_t)d.y1 - r.y1, bx = (int64_t)d.x2 - r.x2, by = (int64_t)d.y2 - r.y2;
+            const int64_t da = ax * ax + ay * ay, db = bx * bx + by * by;
+            if (da >= simtab_n || db >= simtab_n) continue;
+            const double sim = sqrt(simtab[da] * simtab[db]);
+            if (sim > best) { best = sim; bi = g; }
+        }
+    }
+    const bool ok = bi >= 0 && best > tol;
+    status[i] = ok ? 1 : 0;
+    match[i] = ok ? bi : -1;
+    if (ok) gt_hit[bi] = 1;
+    if (d.frame >= 0 && d.frame < nframes) atomicAdd(&tally[(d.frame * 6 + d.type) * 4 + (ok ? 0 : 1)], 1);
+}
+
+__global__ void eval_tally_gt_kernel(const EvalBox* __restrict__ gt, int ngt, const uint8_t* __restrict__ gt_hit, int32_t* __restrict__ tally) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngt) return;
+    const EvalBox r = gt[g];
+    atomicAdd(&tally[(r.frame * 6 + r.type) * 4 + 3], 1);                 // expected
+    if (!gt_hit[g]) atomicAdd(&tally[(r.frame * 6 + r.type) * 4 + 2], 1); // not detected
+}
+
+// precision_recall_curve's loop (evaluar_resultados.py:224-262): one thread per image walks that image's detections in the global
+// (score-descending) order; bboxes_overlap (:53-89) with the "ignore" rule, LAST maximum (>=), a ground truth is matched once.
+struct EvalGt { int32_t left, top, right, bottom, cls; };
+struct EvalDt { int32_t left, top, right, bottom, index; };     // index = position in the globally sorted detection list
+
+__global__ void eval_iou_kernel(const EvalDt* __restrict__ det, const int32_t* __restrict__ det_offsets, const EvalGt* __restrict__ gt,
+                                const int32_t* __restrict__ gt_offsets, int nimages, double ovr, uint8_t* __restrict__ gt_used,
+                                uint8_t* __restrict__ tp, uint8_t* __restrict__ fp) {
+    const int im = blockIdx.x * blockDim.x + threadIdx.x;
+    if (im >= nimages) return;
+    const int g0 = gt_offsets[im], g1 = gt_offsets[im + 1];
+    for (int k = det_offsets[im]; k < det_offsets[im + 1]; k++) {
+        const EvalDt d = det[k];
+        double maxovr = 0.0;
+        int gsel = g0;
+        const int64_t darea = (int64_t)(d.right - d.left + 1) * (int64_t)(d.bottom - d.top + 1);
+        for (int g = g0; g < g1; g++) {
+            const EvalGt r = gt[g];
+            double covr = 0.0;
+            const int w = min(d.right, r.right) - max(d.left, r.left);
+            if (w > 0) {
+                const int h = min(d.bottom, r.bottom) - max(d.top, r.top);
+                if (h > 0) {
+                    const int64_t inter = (int64_t)w * h;
+                    const int64_t uni = r.cls == -1 ? darea : darea + (int64_t)(r.right - r.left + 1) * (int64_t)(r.bottom - r.top + 1) - inter;
+                    covr = (double)inter / (double)uni;
+                }
+            }
+            if (covr >= maxovr) { maxovr = covr; gsel = g; }
+        }
+        uint8_t t = 0, f = 0;
+        if (g1 > g0 && maxovr > ovr) {
+            if (gt[gsel].cls != -1) {
+                if (!gt_used[gsel]) { t = 1; gt_used[gsel] = 1; } else f = 1;
+            }
+        } else f = 1;
+        tp[d.index] = t; fp[d.index] = f;
+    }
+}
+
 __global__ void fill_u8_kernel(uint8_t* p, int64_t n, uint8_t v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -331,6 +331,26 @@ class Context:
         check(self._L.tsd_mean_windows(self._h, ptr(windows), ptr(group_offsets), ng, D, ptr(out), MEM_HOST))
         return out
 
+    def match_detections(self, det, gt, gt_offsets, tol=0.85):
+        """The matching loops of generateStatistics (DET:401-450) for all files and types at once.  det / gt: int32 [n, 6] =
+        (frame, x1, y1, x2, y2, type bucket 0..5), gt grouped by frame (CSR gt_offsets).  -> status int32 [ndet] (1 correct),
+        match int32 [ndet] (gt row or -1), tally int32 [nframes, 6, 4] = (correct, incorrect, not detected, expected)."""
+        det = _i32(det).reshape(-1, 6); gt = _i32(gt).reshape(-1, 6); gt_offsets = _i32(gt_offsets)
+        nf = len(gt_offsets) - 1
+        status = np.zeros(len(det), np.int32); match = np.full(len(det), -1, np.int32); tally = np.zeros((nf, 6, 4), np.int32)
+        check(self._L.tsd_match_detections(self._h, ptr(det), len(det), ptr(gt), ptr(gt_offsets), nf, float(tol), ptr(status), ptr(match), ptr(tally)))
+        return status, match, tally
+
+    def match_iou(self, det, det_offsets, gt, gt_offsets, ovr=0.5):
+        """The loop of precision_recall_curve (evaluar_resultados.py:224-262).  det int32 [ndet, 5] = (left, top, right, bottom,
+        index in the score-descending list) grouped by image (CSR det_offsets, list order inside an image); gt int32 [ngt, 5] =
+        (left, top, right, bottom, class; -1 = ignore) grouped by image.  -> tp, fp uint8 [ndet] by list position."""
+        det = _i32(det).reshape(-1, 5); gt = _i32(gt).reshape(-1, 5); det_offsets = _i32(det_offsets); gt_offsets = _i32(gt_offsets)
+        ni = len(det_offsets) - 1
+        tp = np.zeros(len(det), np.uint8); fp = np.zeros(len(det), np.uint8)
+        check(self._L.tsd_match_iou(self._h, ptr(det), ptr(det_offsets), ptr(gt), ptr(gt_offsets), ni, float(ovr), ptr(tp), ptr(fp)))
+        return tp, fp
+
     def set_profiling(self, on=True):
         check(self._L.tsd_set_profiling(self._h, int(bool(on))))
 

@@ -56,6 +56,11 @@ def rec_golden():
 
 
 @pytest.fixture(scope="session")
+def eval_golden():
+    return np.load(os.path.join(GOLDEN, "eval_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def rec_frames():
     return np.load(os.path.join(GOLDEN, "rec_frames.npz"))
 

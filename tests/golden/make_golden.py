@@ -228,8 +228,63 @@ def make_pre():
     print("det_pre.npz written")
 
 
+def make_eval():
+    """Outputs of the reference's evaluators on its own files: generateStatistics (DET/source.py:267-330) for the 192 golden
+    detections of det_resultado150.txt against test_alumnos_jpg/gt.txt, and precision_recall_curve + draw_PR_fast
+    (REC/evaluar_resultados.py:199-307) for that file and the two instructor result files.  The inputs travel with the outputs
+    (parsed to arrays) so the tests need nothing from /root/reference."""
+    import importlib.util
+    import io
+    import contextlib
+    src, _ = refload.load_det()
+    _silence_tqdm(src)
+    gt_path = os.path.join(refload.DET_DIR, "test_alumnos_jpg", "gt.txt")
+    lines = open(os.path.join(HERE, "det_resultado150.txt")).read().split()
+    dets = []
+    for ln in lines:
+        f, x1, y1, x2, y2, t, sc = ln.split(";")
+        dets.append((f, int(x1), int(y1), int(x2), int(y2), int(t), float(sc)))
+    files = sorted(f for f in os.listdir(os.path.join(refload.DET_DIR, "test_alumnos_jpg")) if f.endswith(".jpg"))
+    number = [(f, sum(1 for d in dets if d[0] == f)) for f in files]
+    with contextlib.redirect_stdout(io.StringIO()):
+        per_file, by_type, tc, ti, tn, te = src.generateStatistics(dets, gt_path, number)
+    out = {"gt_txt": np.frombuffer(open(gt_path, "rb").read(), np.uint8), "files": np.array(files),
+           "stat_per_file": np.array([[[r[1], r[2], r[3], r[4]] for r in pf[1]] for pf in per_file], np.int32),
+           "stat_by_type": np.array([v for _, v in by_type], np.int32), "stat_totals": np.array([tc, ti, tn, te], np.int32)}
+    refload._stub_matplotlib()
+    spec = importlib.util.spec_from_file_location("ref_evaluar", os.path.join(refload.REC_DIR, "evaluar_resultados.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    # gt.txt names its images NNNNN.ppm while every results file says NNNNN.jpg, so the script as shipped matches nothing (all
+    # detections are false positives, AP = 0: kept as the "asis" case); the informative goldens use the same ground truth with the
+    # extension rewritten -- an input change, the reference code is untouched
+    _, gt_asis = ev.load_results_file(gt_path, "", load_images=False)
+    gt_jpg_path = "/tmp/o_eval_gt_jpg.txt"
+    open(gt_jpg_path, "w").write(open(gt_path).read().replace(".ppm", ".jpg"))
+    _, gt_bb = ev.load_results_file(gt_jpg_path, "", load_images=False)
+    _, det_own = ev.load_results_file(os.path.join(HERE, "det_resultado150.txt"), "", load_images=False)
+    tp, fp, thr, tot = ev.precision_recall_curve(gt_asis, det_own, show=False, ovr=0.5)
+    out["asis_tp"], out["asis_fp"], out["asis_tot"] = tp, fp, np.int64(tot)
+    for tag, path in (("own", os.path.join(HERE, "det_resultado150.txt")),
+                      ("p1", os.path.join(refload.REC_DIR, "resultado_práctica1_jmbuena.txt")),
+                      ("p2", os.path.join(refload.REC_DIR, "resultado_práctica2_jmbuena.txt"))):
+        _, det_bb = ev.load_results_file(path, "", load_images=False)
+        tp, fp, thr, tot = ev.precision_recall_curve(gt_bb, det_bb, show=False, ovr=0.5)
+        rec, prec, ap = ev.draw_PR_fast(tp, fp, tot, show=False)
+        out[tag + "_txt"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+        out[tag + "_tp"], out[tag + "_fp"], out[tag + "_thr"], out[tag + "_tot"] = tp, fp, thr, np.int64(tot)
+        out[tag + "_rec"], out[tag + "_prec"], out[tag + "_ap"] = rec, prec, np.float64(ap)
+        out[tag + "_ap11"] = np.float64(ev.VOColdap(rec, prec))
+        print(tag, "detections", len(tp), "tp", int(tp.sum()), "fp", int(fp.sum()), "tot", tot, "AP %.4f" % ap)
+    np.savez_compressed(os.path.join(HERE, "eval_golden.npz"), **out)
+    print("eval_golden.npz written; totals", tc, ti, tn, te)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "det"
+    if what == "eval":
+        make_eval()
+        sys.exit(0)
     if what == "pre":
         make_pre()
         sys.exit(0)

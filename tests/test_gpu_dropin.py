@@ -179,3 +179,42 @@ def test_training_window_extraction_like_the_reference(tsd, rec_frames, frames3,
     neg2 = R.calculateNegativeTrainResults(train, pos, None)          # second call: served from the cache, no MSER needed
     assert [[e[1] for e in neg2[n]] for n in train] == [[e[1] for e in neg[n]] for n in train]
 
+
+
+def test_evaluators_like_the_reference(tsd, eval_golden, tmp_path):
+    """evaluate.generateStatistics (DET:267-450) and evaluate.precision_recall_curve / draw_PR_fast / VOColdap
+    (REC/evaluar_resultados.py:199-307), matching loops on the GPU, against the outputs of the reference's own functions on its
+    own ground truth and result files."""
+    E, g = tsd.evaluate, eval_golden
+    gt_path = tmp_path / "gt.txt"
+    gt_path.write_bytes(bytes(g["gt_txt"]))
+    dets = []
+    for ln in bytes(g["own_txt"]).decode().split():
+        f, x1, y1, x2, y2, t, sc = ln.split(";")
+        dets.append((f, int(x1), int(y1), int(x2), int(y2), int(t), float(sc)))
+    files = [str(f) for f in g["files"]]
+    number = [(f, sum(1 for d in dets if d[0] == f)) for f in files]
+    per_file, by_type, tc, ti, tn, te = E.generateStatistics(dets, str(gt_path), number)
+    assert [pf[0] for pf in per_file] == files
+    assert np.array_equal(np.array([[r[1:] for r in pf[1]] for pf in per_file]), g["stat_per_file"])
+    assert [n for n, _ in by_type] == E.SIGNALLIST and np.array_equal(np.array([v for _, v in by_type]), g["stat_by_type"])
+    assert [tc, ti, tn, te] == g["stat_totals"].tolist()
+    assert all(pf[2:] == tuple(int(v) for v in np.array([r[1:] for r in pf[1]]).sum(0)) for pf in per_file)
+    # precision / recall
+    gt_jpg = tmp_path / "gt_jpg.txt"
+    gt_jpg.write_text(bytes(g["gt_txt"]).decode().replace(".ppm", ".jpg"))
+    _, gt_bb = E.load_results_file(str(gt_jpg))
+    for tag in ("own", "p1", "p2"):
+        p = tmp_path / (tag + ".txt")
+        p.write_bytes(bytes(g[tag + "_txt"]))
+        _, det_bb = E.load_results_file(str(p))
+        tp, fp, thr, tot = E.precision_recall_curve(gt_bb, det_bb, show=False, ovr=0.5)
+        assert tot == int(g[tag + "_tot"]) and np.array_equal(tp, g[tag + "_tp"]) and np.array_equal(fp, g[tag + "_fp"]) and np.array_equal(thr, g[tag + "_thr"])
+        rec, prec, ap = E.draw_PR_fast(tp, fp, tot, show=False)
+        assert np.array_equal(rec, g[tag + "_rec"]) and np.array_equal(prec, g[tag + "_prec"], equal_nan=True)
+        assert ap == float(g[tag + "_ap"]) and E.VOColdap(rec, prec) == float(g[tag + "_ap11"])
+    _, gt_asis = E.load_results_file(str(gt_path))
+    p = tmp_path / "own.txt"
+    _, det_bb = E.load_results_file(str(p))
+    tp, fp, _, tot = E.precision_recall_curve(gt_asis, det_bb)
+    assert tp.sum() == 0 and np.array_equal(fp, g["asis_fp"]) and tot == int(g["asis_tot"])
