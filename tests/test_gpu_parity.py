@@ -455,6 +455,45 @@ def test_host_paths_agree(tsd, templates, oracle, monkeypatch):
     assert c_pageable.tolist() == c_pinned.tolist() == c_copy.tolist()
 
 
+def test_back_to_back_batches_overlap_slots(tsd, templates, oracle, monkeypatch):
+    """Consecutive enqueue_frames calls alternate between two scratch slots and two internal streams (the fold of one batch
+    overlaps the kernels of the next).  Different batches enqueued back to back without a host sync in between, of different
+    sizes (the second one forces the slot layout to grow), must each give the oracle's records; fetch returns the LAST batch;
+    flush + an event on the context's stream covers everything enqueued; TSD_OVERLAP=0 gives the same records."""
+    import torch
+    red6, blue6 = templates
+    dev = torch.device("cuda", 0)
+    batches = []
+    for k, (F, N) in enumerate(((6, 200), (9, 260), (4, 120))):
+        frames = tsd.synth.make_frames(F, seed=tsd.synth.FRAME_SEED + 40 + k)
+        boxes, off = tsd.synth.make_boxes(F, N, seed=tsd.synth.BOX_SEED + 40 + k)
+        exp = []
+        for f in range(F):
+            o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+            exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+        batches.append((torch.from_numpy(frames).to(dev), torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev), F, int(off[-1]), N, exp))
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("TSD_OVERLAP", overlap)
+        with tsd.Context(0, "det") as ctx:
+            ctx.set_templates(red6, blue6)
+
+            def enqueue(b):
+                ctx.enqueue_frames(b[0].data_ptr(), b[3], 800, 1360, b[1].data_ptr(), b[2].data_ptr(), b[4], max_boxes_per_frame=b[5])
+            for last in (0, 1, 2, 1, 0):                                  # ... A B | A B C | ... : the fetched batch sits in either slot
+                for b in batches[:last + 1]:
+                    enqueue(b)
+                det, _ = ctx.fetch_detections(batches[last][4])
+                assert _records(det) == batches[last][6], (overlap, last)
+            for b in batches:                                             # stream order: flush, then an event on the context's stream
+                enqueue(b)
+            ctx.flush()
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.ExternalStream(ctx.stream, device=dev))
+            ev.synchronize()
+            det, _ = ctx.fetch_detections(batches[2][4])
+            assert _records(det) == batches[2][6]
+
+
 # ---- recognition --------------------------------------------------------------------------------------------------------
 def test_k6_k7_k8_recognition_golden(ctx_rec, rec_golden, rec_frames, oracle):
     g = rec_golden
