@@ -119,8 +119,35 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
     sw.gsum[lane] = 0;
     __syncwarp();
-    // pass A: bin of every pixel + occupancy bitmap + pixel hash
+    // pass A: bin of every pixel + occupancy bitmap + pixel hash.  The kernel is bound by shared-memory wavefronts: with a 4-byte
+    // aligned window (internal layout) a lane takes FOUR consecutive pixels from three aligned words (3 conflict-free LDS.32
+    // instead of 12 byte loads) and stores their bins with one 64-bit store.
     uint32_t hsh = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(px) & 3) == 0 && 4 * ((npx + 3) >> 2) <= CAP;
+    const int ngroups = (npx + 3) >> 2;
+    if (aligned) {
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(px);
+#pragma unroll 2
+        for (int g = lane; g < ngroups; g += 32) {
+            const uint32_t q0 = pw[3 * g], q1 = pw[3 * g + 1], q2 = pw[3 * g + 2];
+            const uint32_t col[4] = {q0 & 0xffffffu, (q0 >> 24) | ((q1 & 0xffffu) << 8), (q1 >> 16) | ((q2 & 0xffu) << 16), q2 >> 8};
+            uint32_t bins[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int p = 4 * g + j;
+                const int b = (int)(col[j] & 255u), gg = (int)((col[j] >> 8) & 255u), r = (int)(col[j] >> 16);
+                int H, S, V;
+                bgr2hsv(b, gg, r, lut.sdiv, lut.hdiv, H, S, V);
+                const int bin = (int)lut.hbin[H] * kHistS + ((S * kHistS) >> 8);
+                bins[j] = (uint32_t)bin;
+                if (p < npx) {
+                    atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
+                    hsh += pix_hash32(p, col[j]);
+                }
+            }
+            *reinterpret_cast<uint2*>(&sw.binbuf[4 * g]) = make_uint2(bins[0] | (bins[1] << 16), bins[2] | (bins[3] << 16));
+        }
+    } else {
 #pragma unroll kHistUnroll
     for (int p = lane; p < npx; p += 32) {
         const int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
@@ -130,6 +157,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
         sw.binbuf[p] = (uint16_t)bin;
         atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
         hsh += pix_hash32(p, (uint32_t)(b | (g << 8) | (r << 16)));
+    }
     }
     __syncwarp();
     // per-word exclusive prefix popcounts (lane owns words 3*lane .. 3*lane+2)
@@ -145,6 +173,22 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     for (int i = lane; i < nnz4; i += 32) sw.cnt[i] = 0;
     __syncwarp();
     // pass B: counts through the rank hash; binof[rank] = bin (all writers of a rank store the same value)
+    if (aligned) {
+#pragma unroll 2
+        for (int g = lane; g < ngroups; g += 32) {
+            const uint2 bb = *reinterpret_cast<const uint2*>(&sw.binbuf[4 * g]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (4 * g + j < npx) {
+                    const int bin = (int)(((j < 2 ? bb.x : bb.y) >> (16 * (j & 1))) & 0xffffu);
+                    const uint32_t word = sw.bitmap[bin >> 5];
+                    const int r = (int)sw.prefix[bin >> 5] + __popc(word & ((1u << (bin & 31)) - 1));
+                    atomicAdd(&sw.cnt[r], 1u);
+                    sw.binof[r] = (uint16_t)bin;
+                }
+            }
+        }
+    } else {
 #pragma unroll kHistUnroll
     for (int p = lane; p < npx; p += 32) {
         const int bin = sw.binbuf[p];
@@ -152,6 +196,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
         const int r = (int)sw.prefix[bin >> 5] + __popc(word & ((1u << (bin & 31)) - 1));
         atomicAdd(&sw.cnt[r], 1u);
         sw.binof[r] = (uint16_t)bin;
+    }
     }
     __syncwarp();
     unsigned mx = 0;
