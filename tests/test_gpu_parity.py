@@ -222,6 +222,41 @@ def test_k5_dedup_adversarial(ctx_det, oracle):
             assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (by_coords, tol, f)
 
 
+def test_k5_dedup_flat_windows_32(ctx_rec, oracle):
+    """32 x 32 windows (1024 pixels: bin counts up to 1024) with a few flat or two-tone windows per frame: the tensor-core pair
+    kernel keeps counts modulo 256 and corrects the pairs of such windows exactly -- also when BOTH windows of a pair exceed 255 in
+    the same bin -- for 2 .. 128 windows per frame; frames with more than 16 such windows, or more than 128 windows, go to k5_pairs."""
+    rng = np.random.default_rng(33)
+    tones = rng.integers(0, 256, (5, 3), dtype=np.uint8)
+    wins, coords, off = [], [], [0]
+    for f, n in enumerate((2, 9, 33, 64, 65, 96, 97, 128, 129, 40, 40, 70)):
+        nflat = (0, 3, 8, 16, 2, 5, 12, 16, 4, 17, 40, 1)[f]
+        for i in range(n):
+            if i < nflat:
+                w = np.empty((32, 32, 3), np.int16)
+                w[:] = tones[int(rng.integers(0, 5))]
+                kind = rng.random()
+                if kind < 0.4:
+                    w[:, int(rng.integers(4, 28)):] = tones[int(rng.integers(0, 5))]         # two-tone
+                elif kind < 0.7:
+                    w[int(rng.integers(8, 24)):] += rng.integers(-6, 7, 3)                   # slightly different lower part
+            else:
+                w = rng.integers(0, 256, (8, 8, 3)).repeat(4, 0).repeat(4, 1).astype(np.int16) + rng.integers(-3, 4, (32, 32, 3))
+            wins.append(np.clip(w, 0, 255).astype(np.uint8))
+            x, y, sd = int(rng.integers(0, 1300)), int(rng.integers(0, 760)), int(rng.integers(20, 80))
+            coords.append((x, y, x + sd, y + sd))
+        order = rng.permutation(n) + off[-1]                              # flat windows anywhere in the list
+        wins[off[-1]:] = [wins[k] for k in order]
+        off.append(len(coords))
+    wins = np.stack(wins); coords = np.array(coords, np.int32); off = np.array(off, np.int32)
+    for tol in (0.85, 0.6):
+        gw, gc, go = ctx_rec.dedup(wins, coords, off, False, tol)
+        for f in range(len(off) - 1):
+            ow, oc = oracle.dedup(wins[off[f]:off[f + 1]], coords[off[f]:off[f + 1]], False, tol)
+            assert go[f + 1] - go[f] == len(oc), (tol, f)
+            assert np.array_equal(gc[go[f]:go[f + 1]], oc) and np.array_equal(gw[go[f]:go[f + 1]], ow), (tol, f)
+
+
 def test_k5_dedup_large_frames(ctx_det, oracle):
     """Frames with 300 / 700 / 1300 windows in one call: the 1024-window warp-per-frame fold, and the frame that exceeds it
     (flagged and redone by the general block-synchronous fold)."""
