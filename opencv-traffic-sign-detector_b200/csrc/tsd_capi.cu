@@ -107,7 +107,7 @@ struct tsd_ctx {
     int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
                                              // consecutive windows: measured slower (0.45 vs 0.27 ms device, 19.1 vs 16.5 ms zero-copy e2e)
     int k2_grid_limit = 0;                   // > 0: persistent K2 with at most this many CTAs (host-memory frames, PCIe-bound)
-    int k2_variant = 2;          // TSD_K2=v2|v3|v4 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
+    int k2_variant = 2;          // TSD_K2=v2|v3|v4|v5 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
     int ev_used = 0;
@@ -238,7 +238,7 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     { const char* e = getenv("TSD_FOLD_CTAS"); if (e) c->fold_ctas = atoi(e); }
-    { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') c->k2_variant = e[1] - '0'; }
+    { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '5') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
     t.sdiv[0] = t.hdiv[0] = 0;
@@ -533,14 +533,16 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     if (n_max == 0) return TSD_OK;
     int g4 = cdiv(n_max, 4);
     if (c->k2_grid_limit > 0 && g4 > c->k2_grid_limit) g4 = c->k2_grid_limit;     // only the v2 kernels loop over windows
-    if (!c->k2_by_frame || c->k2_variant != 2) frame_offsets = nullptr;
+    if (!c->k2_by_frame || (c->k2_variant != 2 && c->k2_variant != 5)) frame_offsets = nullptr;
     if (frame_offsets) g4 = nframes;                         // one CTA per frame (v2 only)
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
-    // TSD_K2 = v2 | v3 | v4 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all three are bit-identical.
+    // TSD_K2 = v2 | v3 | v4 | v5 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all are bit-identical.
     // v3 (staged through shared memory with cp.async) needs 16-byte aligned rows: its 128-bit chunks never leave the frame buffer.
     const bool fast = c->k2_variant == 3 && c->k2_grid_limit == 0 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
     const int gk = cdiv(n_max, kK2Warps);
     const bool v4 = c->k2_variant == 4 && c->k2_grid_limit == 0 && ((uintptr_t)windows % 16 == 0);
+    // TSD_K2=v5: v2 with aligned 32-bit tap loads (needs the number of frames behind `frames`: only the chain knows it)
+    const bool wide = c->k2_variant == 5 && ch == 3 && nframes > 0 && ((uintptr_t)frames % 4 == 0) && rs % 4 == 0 && fs % 4 == 0;
     if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
@@ -549,6 +551,8 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (wide && D == 25) k2_crop_resize_v2_kernel<3, 25, 12, true><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
+    else if (wide && D == 32) k2_crop_resize_v2_kernel<3, 32, 12, true><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
     else if (ch == 3 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
     else if (ch == 3 && D == 32) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 32, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 32, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 32, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
     else if (ch == 1 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<1, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<1, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<1, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }

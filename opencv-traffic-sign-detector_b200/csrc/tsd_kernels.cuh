@@ -251,7 +251,11 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 // byte-iteration).  One warp per window, lane = destination column; the x coefficients live in registers, the y
 // coefficients are computed by lane dy and broadcast by shuffle; each lane walks the D destination rows and reads its
 // 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
-template <int C, int D, int MINB>
+// WIDE (C = 3, 4-byte aligned frames and strides, nframes known): the 6 consecutive bytes a lane needs of a source row (its two
+// taps x 3 channels) come from 2-3 aligned 32-bit loads + a funnel shift instead of 6 byte loads -- the kernel is bound by the L1
+// data pipe (74 % of its wavefront rate with byte loads); windows touching the last row of the last frame keep the byte loads
+// (an aligned word may reach up to 6 bytes past the bytes needed).
+template <int C, int D, int MINB, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
@@ -342,6 +346,35 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     __syncwarp();                                            // (the previous window's rows are consumed)
     s_y[wl][lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
     __syncwarp();
+    if (WIDE && C == 3 && !(win_frame[w] == nframes - 1 && cy + ch == H)) {
+        const unsigned o = (unsigned)(reinterpret_cast<uintptr_t>(px) & 3);
+        const unsigned o8 = o * 8;
+        const uint8_t* pa = px - o;
+        const bool third = o == 3;                           // bytes o .. o+5 of the aligned words: a third word only from offset 3
+#pragma unroll kK2Unroll
+        for (int dy = 0; dy < D; dy++) {
+            const int4 yc = s_y[wl][dy];
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(pa + (int64_t)yc.x * row_stride);
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(pa + (int64_t)yc.y * row_stride);
+            const uint32_t a0 = __ldg(q0), a1 = __ldg(q0 + 1), a2 = third ? __ldg(q0 + 2) : 0u;
+            const uint32_t c0 = __ldg(q1), c1 = __ldg(q1 + 1), c2 = third ? __ldg(q1 + 2) : 0u;
+            const uint32_t lo0 = __funnelshift_r(a0, a1, o8), hi0 = __funnelshift_r(a1, a2, o8);      // bytes 0-3 / 4-7 from the tap
+            const uint32_t lo1 = __funnelshift_r(c0, c1, o8), hi1 = __funnelshift_r(c1, c2, o8);
+            const int t00 = (int)(lo0 & 255u) * xa0 + (int)(lo0 >> 24) * xa1;
+            const int t01 = (int)((lo0 >> 8) & 255u) * xa0 + (int)(hi0 & 255u) * xa1;
+            const int t02 = (int)((lo0 >> 16) & 255u) * xa0 + (int)((hi0 >> 8) & 255u) * xa1;
+            const int t10 = (int)(lo1 & 255u) * xa0 + (int)(lo1 >> 24) * xa1;
+            const int t11 = (int)((lo1 >> 8) & 255u) * xa0 + (int)(hi1 & 255u) * xa1;
+            const int t12 = (int)((lo1 >> 16) & 255u) * xa0 + (int)((hi1 >> 8) & 255u) * xa1;
+            const int b0 = yc.z, b1 = yc.w;
+            if (act) {
+                dst[dy * D * C] = (uint8_t)((((b0 * (t00 >> 4)) >> 16) + ((b1 * (t10 >> 4)) >> 16) + 2) >> 2);
+                dst[dy * D * C + 1] = (uint8_t)((((b0 * (t01 >> 4)) >> 16) + ((b1 * (t11 >> 4)) >> 16) + 2) >> 2);
+                dst[dy * D * C + 2] = (uint8_t)((((b0 * (t02 >> 4)) >> 16) + ((b1 * (t12 >> 4)) >> 16) + 2) >> 2);
+            }
+        }
+        continue;
+    }
 #pragma unroll kK2Unroll
     for (int dy = 0; dy < D; dy++) {
         const int4 yc = s_y[wl][dy];

@@ -49,7 +49,7 @@ def test_k2_resize_sweep(ctx_det, ctx_rec, oracle):
             assert np.array_equal(got1[i], oracle.crop_resize(gray[f], c, D)), (D, c, "grey")
 
 
-@pytest.mark.parametrize("variant", ["v3", "v4"])
+@pytest.mark.parametrize("variant", ["v3", "v4", "v5"])
 def test_k2_experimental_variants_bit_identical(tsd, templates, monkeypatch, variant):
     """The resize kernels kept for A/B measurements (TSD_K2=v3: crop staged in shared memory by cp.async; v4: row reuse +
     staged output) must give exactly the default kernel's windows and detections: compared on the whole chain of 6 frames
