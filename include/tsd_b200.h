@@ -237,6 +237,10 @@ TSD_API int tsd_enqueue_frames(tsd_ctx *ctx, int mode, const uint8_t *d_frames, 
                                int64_t row_stride, int64_t frame_stride, const int32_t *d_boxes,
                                const int32_t *d_box_offsets, int nboxes_total, int max_boxes_per_frame);
 TSD_API int tsd_fetch_detections(tsd_ctx *ctx, tsd_detection *det, int det_cap, int32_t *ndet, int32_t *counts);
+/* Streaming use of the two slots: after  enqueue(batch k); enqueue(batch k+1);  tsd_fetch_previous returns batch k's records
+ * (same arguments as tsd_fetch_detections) while batch k+1 keeps running -- e.g. its K2 pulling ROIs out of page-locked host
+ * frames over PCIe under batch k's GPU-bound kernels.  TSD_E_STATE if there is no such batch. */
+TSD_API int tsd_fetch_previous(tsd_ctx *ctx, tsd_detection *det, int det_cap, int32_t *ndet, int32_t *counts /* [4] or NULL */);
 
 /* Measurement helper: total number of non-zero histogram bins over the windows of the last tsd_enqueue_frames call
  * (the bytes k5_pairs has to read at least once).  Synchronises. */

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "tsd_detect_frames": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "tsd_enqueue_frames": (_i, [_vp, _i, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _i, _i]),
     "tsd_fetch_detections": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "tsd_fetch_previous": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tsd_set_profiling": (_i, [_vp, _i]),
     "tsd_stage_times": (_i, [_vp, _vp, _vp, _i]),
 }

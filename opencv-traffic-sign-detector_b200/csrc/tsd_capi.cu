@@ -54,6 +54,9 @@ struct tsd_ctx {
                                              // the fold's shared memory footprint keeps other kernels from co-residing)
     struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; int sidx; };   // sidx: the chunk's record in b_summary
     std::vector<ChunkInfo> chunks;           // of the last enqueue
+    std::vector<ChunkInfo> prev_chunks;      // of the enqueue before it (overlap mode: tsd_fetch_previous)
+    int prev_nboxes = 0;
+    bool last_was_overlap = false;
     std::vector<cudaEvent_t> ev_chunk;
     // Default (TSD_OVERLAP=0 turns it off): consecutive tsd_enqueue_frames calls alternate between two scratch slots and two streams, so the latency-bound
     // fold of one batch runs under the throughput-bound kernels of the next.  tsd_stream() is ordered after a batch only once the
@@ -1355,6 +1358,9 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         CU(cudaStreamSynchronize(c->stream));
         for (int f = 0; f < nframes; f++) max_boxes_per_frame = ho[f + 1] - ho[f] > max_boxes_per_frame ? ho[f + 1] - ho[f] : max_boxes_per_frame;
     }
+    if (c->last_was_overlap) c->prev_chunks = c->chunks; else c->prev_chunks.clear();   // (tsd_fetch_previous: both batches must sit in slots)
+    c->prev_nboxes = c->last_nboxes;
+    c->last_was_overlap = false;
     c->chunks.clear();
     size_t wtot = 0;
     for (int k = 0; k < nchunks; k++) {
@@ -1372,6 +1378,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         c->slot ^= 1;
         const size_t need_w = (wtot + 63) & ~(size_t)63, need_f = ((size_t)nframes + 2 + 63) & ~(size_t)63;
         if (need_w > c->slot_cap || need_f > c->slot_fcap) { // the layout changes: nothing may be in flight
+            c->prev_chunks.clear();
             TRY(join_pending(c));
             CU(cudaStreamSynchronize(c->stream));
             if (need_w > c->slot_cap) c->slot_cap = need_w;
@@ -1383,6 +1390,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         cap = 2 * c->slot_cap; fcap = 2 * c->slot_fcap;
     } else {
         TRY(join_pending(c));
+        c->prev_chunks.clear();
     }
     TRY(ensure(c, c->b_cnt, fcap * 4));
     TRY(ensure(c, c->b_winoff, fcap * 4));
@@ -1431,6 +1439,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         c->ov_active = false;
         CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
         c->pending_join = sl;
+        c->last_was_overlap = rc == TSD_OK;
     } else if (nchunks == 1) {
         c->cur = c->stream;
         rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, c->chunks[0].nbcap, max_boxes_per_frame, 0, 0, 0);
@@ -1498,20 +1507,16 @@ int tsd_stat_hist_entries(tsd_ctx* c, int64_t* total) {
     return TSD_OK;
 }
 
-int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
-    if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
-    if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
-    CU(cudaSetDevice(c->device));
+static int fetch_impl(tsd_ctx* c, const std::vector<tsd_ctx::ChunkInfo>& chunks, int nboxes, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
     static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
-    TRY(join_pending(c));
-    const int nchunks = (int)c->chunks.size();
+    const int nchunks = (int)chunks.size();
     std::vector<int32_t> h((size_t)nchunks * 4);
     for (int k = 0; k < nchunks; k++)
-        CU(cudaMemcpyAsync(h.data() + 4 * k, (int32_t*)c->b_summary.p + 4 * c->chunks[k].sidx, 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h.data() + 4 * k, (int32_t*)c->b_summary.p + 4 * chunks[k].sidx, 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int64_t tw = 0, ts = 0, td = 0;
     for (int k = 0; k < nchunks; k++) { tw += h[4 * k]; ts += h[4 * k + 1]; td += h[4 * k + 2]; }
-    if (counts) { counts[0] = c->last_nboxes; counts[1] = (int32_t)tw; counts[2] = (int32_t)ts; counts[3] = (int32_t)td; }
+    if (counts) { counts[0] = nboxes; counts[1] = (int32_t)tw; counts[2] = (int32_t)ts; counts[3] = (int32_t)td; }
     *ndet = (int32_t)td;
     if (td > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, (int)td);
     if (td) {
@@ -1519,18 +1524,38 @@ int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* n
         int o = 0;
         for (int k = 0; k < nchunks; k++) {
             const int n = h[4 * k + 2];
-            if (n) CU(cudaMemcpyAsync(det + o, (DetRec*)c->b_det.p + c->chunks[k].wo, (size_t)n * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
+            if (n) CU(cudaMemcpyAsync(det + o, (DetRec*)c->b_det.p + chunks[k].wo, (size_t)n * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
             o += n;
         }
         CU(cudaStreamSynchronize(c->stream));
         o = 0;
         for (int k = 0; k < nchunks; k++) {                  // records carry chunk-local frame indices
-            const int n = h[4 * k + 2], f0 = c->chunks[k].f0;
+            const int n = h[4 * k + 2], f0 = chunks[k].f0;
             if (f0) for (int i = 0; i < n; i++) det[o + i].frame += f0;
             o += n;
         }
     }
     return TSD_OK;
+}
+
+int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
+    if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
+    if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
+    CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
+    return fetch_impl(c, c->chunks, c->last_nboxes, det, det_cap, ndet, counts);
+}
+
+// The batch enqueued BEFORE the last one (overlap mode): the context's stream already waits for it (the last tsd_enqueue_frames
+// joined it after forking its own batch) but not for the last batch, which keeps running while these records are read.
+int tsd_fetch_previous(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
+    if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
+    if (c->prev_chunks.empty() || c->pending_join < 0)
+        return fail(TSD_E_STATE, "no previous batch to fetch (needs two consecutive tsd_enqueue_frames calls in overlap mode, nothing in between)");
+    CU(cudaSetDevice(c->device));
+    const int rc = fetch_impl(c, c->prev_chunks, c->prev_nboxes, det, det_cap, ndet, counts);
+    c->prev_chunks.clear();
+    return rc;
 }
 
 int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
@@ -1617,8 +1642,8 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         if (k + 1 < nchunks) TRY(issue_copy(k + 1));
         CU(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
         TRY(run_chunk((const uint8_t*)c->b_stage[slot].p, f0, cf));
-        CU(cudaEventRecord(c->ev_consumed[slot], c->stream));
-        int rc = fetch_chunk(f0);                            // synchronises the compute stream; the next copy is already in flight
+        int rc = fetch_chunk(f0);                            // joins + synchronises the chunk's streams; the next copy is already in flight
+        CU(cudaEventRecord(c->ev_consumed[slot], c->stream)); // (after the join: the batch ran on an internal stream)
         if (rc == TSD_E_NOMEM) rc_all = rc; else TRY(rc);
     }
     CU(cudaStreamSynchronize(c->copy_stream));

@@ -293,9 +293,12 @@ class Context:
         check(self._L.tsd_enqueue_frames(self._h, int(mode), ptr(int(d_frames)), int(nframes), int(H), int(W), rs, fs,
                                          ptr(int(d_boxes)), ptr(int(d_box_offsets)), int(nboxes_total), int(max_boxes_per_frame)))
 
-    def fetch_detections(self, cap):
+    def fetch_detections(self, cap, previous=False):
+        """Records + stage counts of the last enqueue_frames call; previous=True: of the call before it, while the last batch
+        keeps running (streaming use of the two scratch slots: enqueue(k); enqueue(k+1); fetch(previous=True) -> batch k)."""
         det = np.empty(max(int(cap), 1), DET_DTYPE); nd = C.c_int32(); counts = np.zeros(4, np.int32)
-        check(self._L.tsd_fetch_detections(self._h, ptr(det), len(det), C.byref(nd), ptr(counts)))
+        fn = self._L.tsd_fetch_previous if previous else self._L.tsd_fetch_detections
+        check(fn(self._h, ptr(det), len(det), C.byref(nd), ptr(counts)))
         return det[:nd.value].copy(), counts
 
     def stat_hist_entries(self):

@@ -519,6 +519,17 @@ def test_back_to_back_batches_overlap_slots(tsd, templates, oracle, monkeypatch)
                     enqueue(b)
                 det, _ = ctx.fetch_detections(batches[last][4])
                 assert _records(det) == batches[last][6], (overlap, last)
+            if overlap == "1":                                            # streaming: read batch k while batch k+1 runs
+                enqueue(batches[0]); enqueue(batches[1])
+                prev, _ = ctx.fetch_detections(batches[0][4], previous=True)
+                assert _records(prev) == batches[0][6]
+                enqueue(batches[2])
+                prev, _ = ctx.fetch_detections(batches[1][4], previous=True)
+                assert _records(prev) == batches[1][6]
+                with pytest.raises(tsd.TsdError):
+                    ctx.fetch_detections(batches[1][4], previous=True)   # already taken
+                det, _ = ctx.fetch_detections(batches[2][4])
+                assert _records(det) == batches[2][6]
             for b in batches:                                             # stream order: flush, then an event on the context's stream
                 enqueue(b)
             ctx.flush()
