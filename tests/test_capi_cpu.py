@@ -76,3 +76,23 @@ def test_synth_is_deterministic_and_exercises_paths(tsd, oracle):
     ch = np.minimum(coords[valid][:, 3], 800) - coords[valid][:, 1]
     assert np.any((cw == 50) & (ch == 50)) and np.any((cw == 25) & (ch == 25))      # AREA and copy paths
     assert np.any(coords[valid][:, 2] > 1360) or np.any(coords[valid][:, 3] > 800)    # clipped crops
+
+
+def test_evaluator_host_logic(tsd, eval_golden, tmp_path):
+    """The host side of evaluate.py that needs no GPU: class tables, the results-file parser, VOCap / VOColdap / draw_PR_fast on the
+    reference's own tp / fp flags (tests/golden/eval_golden.npz)."""
+    E, g = tsd.evaluate, eval_golden
+    assert [E.calculateSignType(s) for s in ("0", "7", "11", "14", "17", "13", "38", "6", "12", "42")] == [1, 1, 2, 3, 4, 5, 6, None, None, None]
+    assert [E.compute_class_index(n) for n in (0, 16, 11, 31, 14, 17, 13, 38, 6, 12, 42)] == [1, 1, 2, 2, 3, 4, 5, 6, -1, -1, -1]
+    p = tmp_path / "own.txt"
+    p.write_bytes(bytes(g["own_txt"]))
+    _, boxes = E.load_results_file(str(p))
+    assert sum(len(v) for v in boxes.values()) == len(g["own_tp"]) and all(isinstance(b.score, float) for v in boxes.values() for b in v)
+    gt = tmp_path / "gt.txt"
+    gt.write_bytes(bytes(g["gt_txt"]))
+    _, gtb = E.load_results_file(str(gt))
+    assert sum(1 for v in gtb.values() for b in v if b.class_id != -1) == int(g["own_tot"])
+    for tag in ("own", "p1", "p2"):
+        rec, prec, ap = E.draw_PR_fast(g[tag + "_tp"], g[tag + "_fp"], int(g[tag + "_tot"]), show=False)
+        assert np.array_equal(rec, g[tag + "_rec"]) and np.array_equal(prec, g[tag + "_prec"], equal_nan=True)
+        assert ap == float(g[tag + "_ap"]) and E.VOColdap(rec, prec) == float(g[tag + "_ap11"])
