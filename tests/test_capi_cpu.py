@@ -96,3 +96,29 @@ def test_evaluator_host_logic(tsd, eval_golden, tmp_path):
         rec, prec, ap = E.draw_PR_fast(g[tag + "_tp"], g[tag + "_fp"], int(g[tag + "_tot"]), show=False)
         assert np.array_equal(rec, g[tag + "_rec"]) and np.array_equal(prec, g[tag + "_prec"], equal_nan=True)
         assert ap == float(g[tag + "_ap"]) and E.VOColdap(rec, prec) == float(g[tag + "_ap11"])
+
+
+def test_gram_low_byte_correction_identity():
+    """The arithmetic identity k5_gram relies on (tsd_k5.cuh): with counts kept modulo 256 in the u8 tile, adding
+    c_r*c_i - (c_r & 255)*(c_i & 255) for every entry (r, bin) whose count exceeds 255 and every other row i holding that bin --
+    skipping the visit from the HIGHER row when both counts exceed 255 in the same bin -- restores the exact Gram matrix C C^T."""
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        n, nbins = int(rng.integers(2, 40)), 300
+        Cm = np.zeros((n, nbins), np.int64)
+        for r in range(n):
+            k = int(rng.integers(1, 60))
+            Cm[r, rng.choice(nbins, k, replace=False)] = rng.integers(1, 40, k)
+            if rng.random() < 0.4:                                       # a flat window: one or two bins far above 255
+                Cm[r, rng.choice(8, int(rng.integers(1, 3)), replace=False)] = rng.integers(256, 1025, 1)
+        tile = (Cm & 255) @ (Cm & 255).T
+        for r in range(n):
+            for b in np.nonzero(Cm[r] > 255)[0]:
+                for i in range(n):
+                    if i == r or Cm[i, b] == 0 or (Cm[i, b] > 255 and i < r):
+                        continue
+                    corr = Cm[r, b] * Cm[i, b] - (Cm[r, b] & 255) * (Cm[i, b] & 255)
+                    tile[max(r, i), min(r, i)] += corr
+        exact = Cm @ Cm.T
+        low = np.tril_indices(n, -1)
+        assert np.array_equal(tile[low], exact[low])
