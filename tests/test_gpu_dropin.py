@@ -218,3 +218,53 @@ def test_evaluators_like_the_reference(tsd, eval_golden, tmp_path):
     _, det_bb = E.load_results_file(str(p))
     tp, fp, _, tot = E.precision_recall_curve(gt_asis, det_bb)
     assert tp.sum() == 0 and np.array_equal(fp, g["asis_fp"]) and tot == int(g["asis_tot"])
+
+
+def test_evaluators_random_vs_oracle(tsd):
+    """The GPU matching loops against oracle/evaluate.py on random boxes: several detections per ground truth, identical ground-truth
+    rows, score ties, overlap ties, ignore regions (class -1), images without ground truth, empty inputs."""
+    from oracle import evaluate as O
+    E = tsd.evaluate
+    rng = np.random.default_rng(29)
+    for trial in range(8):
+        nimg = 20
+        gt, det = {}, {}
+        for k in range(nimg):
+            name = "%05d.jpg" % k
+            boxes = []
+            for _ in range(int(rng.integers(0, 6))):
+                x, y, s = int(rng.integers(0, 1200)), int(rng.integers(0, 700)), int(rng.integers(16, 90))
+                boxes.append((x, y, x + s, y + s, int(rng.choice([1, 2, 3, 4, 5, 6, -1]))))
+            if boxes and rng.random() < 0.3:
+                boxes.append(boxes[0])
+            if boxes or rng.random() < 0.5:
+                gt[name] = boxes
+            rows = []
+            for _ in range(int(rng.integers(0, 10))):
+                if boxes and rng.random() < 0.7:
+                    b = boxes[int(rng.integers(0, len(boxes)))]
+                    j = rng.integers(-12, 13, 4)
+                    rows.append((name, b[0] + int(j[0]), b[1] + int(j[1]), b[2] + int(j[2]), b[3] + int(j[3]), float(rng.choice([0.5, 0.6, 0.7, 0.8, 0.9]))))
+                else:
+                    x, y, s = int(rng.integers(0, 1200)), int(rng.integers(0, 700)), int(rng.integers(16, 90))
+                    rows.append((name, x, y, x + s, y + s, float(rng.choice([0.5, 0.6, 0.7]))))
+            if rows:
+                det[name] = rows
+        if trial == 7:
+            det = {}
+        gt_bb = {k: [E.BoundingBox(b[0], b[1], b[2], b[3], class_id=b[4], img_idx=k) for b in v] for k, v in gt.items()}
+        det_bb = {k: [E.BoundingBox(r[1], r[2], r[3], r[4], class_id=1, score=r[5], img_idx=k) for r in v] for k, v in det.items()}
+        tp, fp, thr, tot = E.precision_recall_curve(gt_bb, det_bb, ovr=0.5)
+        det_list = [r for k in sorted(det) for r in det[k]]
+        otp, ofp, othr, otot = O.pr_flags(gt, det_list)
+        assert tot == otot and np.array_equal(tp, otp) and np.array_equal(fp, ofp) and np.array_equal(thr, othr)
+        # similarity-based matching of generateStatistics
+        dets = [(int(r[0][:5]), r[1], r[2], r[3], r[4], int(rng.integers(0, 6))) for r in det_list]
+        gts = sorted(((int(k[:5]), b[0], b[1], b[2], b[3], int(rng.integers(0, 6))) for k in gt for b in gt[k]), key=lambda r: r[0])
+        off = np.zeros(nimg + 1, np.int32)
+        for g in gts:
+            off[g[0] + 1] += 1
+        off = np.cumsum(off).astype(np.int32)
+        st, mt, tally = E.context().match_detections(np.array(dets, np.int32).reshape(-1, 6), np.array(gts, np.int32).reshape(-1, 6), off)
+        ost, omt, otally = O.det_statistics(dets, gts, nimg)
+        assert st.tolist() == ost and mt.tolist() == omt and np.array_equal(tally, otally)
