@@ -1,9 +1,12 @@
-// tsd_k5.cuh -- K5: cleanDuplicatedDetections (DET:177-223) as three kernels.
+// tsd_k5.cuh -- K5: cleanDuplicatedDetections (DET:177-223) as three stages (histograms, pair classes, fold).
 //
 //  k5_hist_kernel  : one WARP per window -> sparse min-max-normalised H-S histogram (calculateHistAndNormalize,
 //                    DET:575-586): entries (bin << 16 | count) sorted by bin, f64 moments, pixel hash, and the energies
 //                    of 25 bin groups (Cauchy-Schwarz bound used by k5_pairs).
-//  k5_pairs_kernel : ALL pairs (i < j) of a frame's windows -> two BIT rows per item j over the earlier items i:
+//  k5_gram_kernel  : the pair classes of a frame of up to 128 windows from the Gram matrix of its count histograms on the tensor
+//                    cores (u8 IMMA, exact integers; see the kernel's header) -- the default producer of the bit rows below.
+//  k5_pairs_kernel : the CUDA-core producer, for the frames k5_gram leaves over (todo list) or all frames with TSD_GRAM=0.
+//                    ALL pairs (i < j) of a frame's windows -> two BIT rows per item j over the earlier items i:
 //                    del[j] (CORREL > tol: the newer window replaces the older one) and mrg[j] (tol*0.8823 <= CORREL <= tol).
 //                    cv2.compareHist(CORREL) (DET:200-202) is decided from the EXACT integer dot product of the bin
 //                    counts, which bounds the f64 value to ~1e-7; only pairs within 1e-6 of a threshold take the exact f64
