@@ -130,7 +130,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     const int ngroups = (npx + 3) >> 2;
     if (aligned) {
         const uint32_t* pw = reinterpret_cast<const uint32_t*>(px);
-#pragma unroll 2
+#pragma unroll kHistGroupUnroll
         for (int g = lane; g < ngroups; g += 32) {
             const uint32_t q0 = pw[3 * g], q1 = pw[3 * g + 1], q2 = pw[3 * g + 2];
             const uint32_t col[4] = {q0 & 0xffffffu, (q0 >> 24) | ((q1 & 0xffffu) << 8), (q1 >> 16) | ((q2 & 0xffu) << 16), q2 >> 8};
@@ -177,7 +177,7 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     __syncwarp();
     // pass B: counts through the rank hash; binof[rank] = bin (all writers of a rank store the same value)
     if (aligned) {
-#pragma unroll 2
+#pragma unroll kHistGroupUnroll
         for (int g = lane; g < ngroups; g += 32) {
             const uint2 bb = *reinterpret_cast<const uint2*>(&sw.binbuf[4 * g]);
 #pragma unroll

@@ -29,7 +29,12 @@
 #define TSD_HIST_UNROLL 8        // pixels per lane in flight in the two histogram passes (measured: 2: .266, 4: .274, 5: .283, 7-8: .259, 10: .310, 20: .369 ms)
 #endif
 
+#ifndef TSD_HIST_GROUP_UNROLL
+#define TSD_HIST_GROUP_UNROLL 2  // groups of 4 pixels per lane in flight in the aligned histogram passes
+#endif
+
 namespace tsd {
+constexpr int kHistGroupUnroll = TSD_HIST_GROUP_UNROLL;
 constexpr int kK2Unroll = TSD_K2_UNROLL, kHistUnroll = TSD_HIST_UNROLL, kK3Unroll = TSD_K3_UNROLL;     // (#pragma unroll takes a constant expression, not a macro)
 
 constexpr int kHistH = 50, kHistS = 60, kHistBins = kHistH * kHistS;   // DET:578
