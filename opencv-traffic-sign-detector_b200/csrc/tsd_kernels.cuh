@@ -30,7 +30,7 @@
 #endif
 
 #ifndef TSD_HIST_GROUP_UNROLL
-#define TSD_HIST_GROUP_UNROLL 2  // groups of 4 pixels per lane in flight in the aligned histogram passes
+#define TSD_HIST_GROUP_UNROLL 2  // groups of 4 pixels per lane in flight in the aligned histogram passes (measured at 4096 frames: 1: .922, 2: .921, 3: .934, 4: .953 ms)
 #endif
 
 namespace tsd {
