@@ -246,6 +246,11 @@ TSD_API int tsd_fetch_previous(tsd_ctx *ctx, tsd_detection *det, int det_cap, in
  * (the bytes k5_pairs has to read at least once).  Synchronises. */
 TSD_API int tsd_stat_hist_entries(tsd_ctx *ctx, int64_t *total);
 
+/* Measurement helper: number of window pairs (since process start, this device) whose class could not be decided from the exact
+ * integer dot product -- cv2.compareHist's value within 2e-6 of a threshold of DET/source.py:203-217 -- and was therefore computed
+ * with the exact float64 evaluation.  reset != 0 zeroes the counter.  Synchronises. */
+TSD_API int tsd_stat_unsure_pairs(tsd_ctx *ctx, int64_t *total, int reset);
+
 /* Device-side stage timing: CUDA events are recorded between the stages of every tsd_enqueue_frames call made after
  * tsd_set_profiling(ctx, 1); tsd_stage_times synchronises and returns, per stage name, the time summed over those
  * calls (names[i] / ms[i] for i < returned count). */

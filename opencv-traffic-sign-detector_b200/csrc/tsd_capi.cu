@@ -46,36 +46,25 @@ struct DevBuf {
 struct tsd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t cur = nullptr;              // the stream kernels are launched on (== stream except inside a chunked enqueue)
-    cudaStream_t cs[2] = {nullptr, nullptr}; // chunk streams: consecutive chunks of a batch alternate, so the latency-bound fold
-                                             // of one chunk overlaps the throughput-bound kernels (and PCIe reads) of the next
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    int stream_chunk = -1;                   // TSD_STREAM_CHUNK: frames per chunk (0 = auto, -1 = never chunk = default: measured slower,
-                                             // the fold's shared memory footprint keeps other kernels from co-residing)
-    struct ChunkInfo { int f0, cf; size_t wo; int fo; int nbcap; int sidx; };   // sidx: the chunk's record in b_summary
-    std::vector<ChunkInfo> chunks;           // of the last enqueue
-    std::vector<ChunkInfo> prev_chunks;      // of the enqueue before it (overlap mode: tsd_fetch_previous)
-    int prev_nboxes = 0;
-    bool last_was_overlap = false;
-    std::vector<cudaEvent_t> ev_chunk;
+    cudaStream_t cur = nullptr;              // the stream kernels are launched on (== stream except inside an overlapped enqueue)
+    // One batch = one tsd_enqueue_frames call.  wo / fo = first window slot / first per-frame entry of the batch in the scratch arrays,
+    // nbcap = upper bound of its windows, sidx = its record in b_summary.
+    struct Batch { int nframes = 0; size_t wo = 0; int fo = 0; int nbcap = 0; int sidx = 0; int nboxes = 0; bool valid = false, in_slot = false; };
+    Batch last, prev;                        // the last enqueue / the one before it (overlap mode: tsd_fetch_previous)
     // Default (TSD_OVERLAP=0 turns it off): consecutive tsd_enqueue_frames calls alternate between two scratch slots and two streams, so the latency-bound
     // fold of one batch runs under the throughput-bound kernels of the next.  tsd_stream() is ordered after a batch only once the
     // NEXT call, tsd_flush, tsd_synchronize or tsd_fetch_detections has been issued (the join is deferred by one call).
     int overlap = 1, slot = 0, pending_join = -1;
-    size_t slot_cap = 0, slot_fcap = 0;
-    cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr};
-    cudaStream_t os[2] = {nullptr, nullptr}, hp[2] = {nullptr, nullptr};   // per slot: the chain's stream / a high-priority stream for its fold (TSD_OVERLAP=2)
-    cudaEvent_t ev_hp_a[2] = {nullptr, nullptr}, ev_hp_b[2] = {nullptr, nullptr};
-    bool ov_active = false;
-    int pipe_mode = 0;                       // chunked enqueue as a producer (K1+K2) / consumer (rest) pipeline instead of alternating streams
+    size_t slot_cap = 0, slot_fcap = 0;      // windows / per-frame entries per slot
+    int slot_rw = 1;                         // words per bit row of the pair-class matrix the slot layout is sized for (sticky maximum)
+    cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t os[2] = {nullptr, nullptr};                                // per slot: the chain's stream
     DevBuf b_summary, b_order, b_gramdone;
-    size_t order_off = 0;                   // offset (ints) of the current chunk inside b_order
+    size_t order_off = 0;                    // offset (ints) of the current batch inside b_order
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf b_stage[2], b_hboxes, b_hoff;
     int zero_copy = 1;                       // K2 reads page-locked host frames in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
-    int zc_pipe = 0;                         // (producer/consumer chunk pipeline for the zero-copy path: measured slower, off)
-    int zc_chunk = 0, zc_grid = 0;           // zero-copy host path: frames per stream chunk / K2 CTAs per SM (0 = off: measured no gain)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
     tsd_config cfg;
     int64_t launches = 0;
@@ -98,19 +87,13 @@ struct tsd_ctx {
     // grow-only scratch
     DevBuf b_coords, b_winframe, b_windows, b_entries, b_meta, b_list, b_flags, b_cnt, b_winoff, b_survcnt, b_survoff,
         b_slots, b_pairs, b_energy, b_red, b_blue, b_bits, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
-    // last enqueue
-    int last_nframes = 0, last_mode = 0, last_nboxes = 0, last_detcap = 0;
+    int last_mode = 0;
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
-    int pairs_variant = 18;
-    int fold_ctas = 0;                                       // TSD_FOLD_CTAS: cap of resident fold CTAs per SM (0 = what fits)
-    int use_gram = 1;                                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
-    int hist_minb = 8;                       // TSD_HIST_MINB: min CTAs/SM of k5_hist (register budget)
-    int k2_minb = 12;                        // TSD_K2_MINB: min CTAs/SM of the K2 v2 kernel (register budget): 8 -> 64 regs, 10 -> 48, 12 -> 40
-    int k2_by_frame = 0;                     // TSD_K2_BY_FRAME=1: K2 CTAs take whole frames (L1 reuse of overlapping ROIs) instead of 4
-                                             // consecutive windows: measured slower (0.45 vs 0.27 ms device, 19.1 vs 16.5 ms zero-copy e2e)
-    int k2_grid_limit = 0;                   // > 0: persistent K2 with at most this many CTAs (host-memory frames, PCIe-bound)
-    int k2_variant = 2;          // TSD_K2=v2|v3|v4|v5 in the environment: resize kernel variant (A/B measurements; v2 is the fastest measured)
+    int use_gram = 1;                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
+    // function attributes (dynamic shared memory opt-in) are set once per context: per-context flags, no process-wide statics
+    int fold_per_sm[4] = {0, 0, 0, 0};       // resident CTAs per SM of the four k5_fold_warp instantiations (0 = not queried yet)
+    bool attr_gram = false, attr_pairs = false;
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
     int ev_used = 0;
@@ -181,49 +164,22 @@ static double eucl_similarity_d2(long long d2) {             // DET:459-462 with
     return 1.0 / (1.0 + pow(M_E, ((0.154 * pow(d, 1.2)) - 31.8) / (0.2 * d)));
 }
 
-int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
-    if (!out) return fail(TSD_E_INVALID, "ctx out pointer is NULL");
-    *out = nullptr;
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(TSD_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
-    if (device < 0 || device >= ndev) return fail(TSD_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
-    CU(cudaSetDevice(device));
-    tsd_ctx* c = new tsd_ctx();
-    c->device = device;
-    if (cfg) c->cfg = *cfg; else tsd_config_default(&c->cfg, 0);
-    if (c->cfg.window < 2 || c->cfg.window > kMaxD) { delete c; return fail(TSD_E_INVALID, "window %d not in [2,%d]", c->cfg.window, kMaxD); }
+static int create_impl(tsd_ctx* c, int device) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->cur = c->stream;
-    {
-        int lo_p = 0, hi_p = 0;                              // numerically lower = higher priority
-        CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
-        CU(cudaStreamCreateWithPriority(&c->cs[0], cudaStreamNonBlocking, lo_p));
-        CU(cudaStreamCreateWithPriority(&c->cs[1], cudaStreamNonBlocking, hi_p));
-        for (int i = 0; i < 2; i++) {
-            CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
-            CU(cudaStreamCreateWithPriority(&c->os[i], cudaStreamNonBlocking, lo_p));
-            CU(cudaStreamCreateWithPriority(&c->hp[i], cudaStreamNonBlocking, hi_p));
-            CU(cudaEventCreateWithFlags(&c->ev_hp_a[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&c->ev_hp_b[i], cudaEventDisableTiming));
-        }
-    }
-    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    { const char* e = getenv("TSD_STREAM_CHUNK"); if (e) c->stream_chunk = atoi(e); }
-    { const char* e = getenv("TSD_OVERLAP"); if (e) c->overlap = atoi(e); }
-    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_slot_fork[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&c->os[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_slot_fork[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
+    { const char* e = getenv("TSD_OVERLAP"); if (e) c->overlap = atoi(e) != 0; }
     { const char* e = getenv("TSD_ZEROCOPY"); if (e) c->zero_copy = e[0] != '0'; }
-    { const char* e = getenv("TSD_ZC_CHUNK"); if (e) c->zc_chunk = atoi(e); }
-    { const char* e = getenv("TSD_ZC_GRID"); if (e) c->zc_grid = atoi(e); }
-    { const char* e = getenv("TSD_ZC_PIPE"); if (e) c->zc_pipe = atoi(e); }
-    { const char* e = getenv("TSD_PIPE"); if (e) c->pipe_mode = atoi(e); }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
+    { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
+    { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -234,14 +190,6 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    { const char* e = getenv("TSD_HIST_MINB"); if (e) c->hist_minb = atoi(e); }
-    { const char* e = getenv("TSD_K2_MINB"); if (e) c->k2_minb = atoi(e); }
-    { const char* e = getenv("TSD_K2_BY_FRAME"); if (e) c->k2_by_frame = atoi(e); }
-    { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
-    { const char* e = getenv("TSD_PAIRS"); if (e && atoi(e) > 0) c->pairs_variant = atoi(e); }
-    { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
-    { const char* e = getenv("TSD_FOLD_CTAS"); if (e) c->fold_ctas = atoi(e); }
-    { const char* e = getenv("TSD_K2"); if (e && e[0] == 'v' && e[1] >= '2' && e[1] <= '5') c->k2_variant = e[1] - '0'; }
     // tables
     Tables t;
     t.sdiv[0] = t.hdiv[0] = 0;
@@ -302,6 +250,24 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
             }
         }
     }
+    return TSD_OK;
+}
+
+int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
+    if (!out) return fail(TSD_E_INVALID, "ctx out pointer is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(TSD_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (device < 0 || device >= ndev) return fail(TSD_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    tsd_ctx* c = new tsd_ctx();
+    c->device = device;
+    if (cfg) c->cfg = *cfg; else tsd_config_default(&c->cfg, 0);
+    if (c->cfg.window < 2 || c->cfg.window > kMaxD) { delete c; return fail(TSD_E_INVALID, "window %d not in [2,%d]", c->cfg.window, kMaxD); }
+    const int rc = create_impl(c, device);
+    if (rc != TSD_OK) { tsd_destroy(c); return rc; }         // one cleanup path: whatever was created so far is released (g_err is kept)
     *out = c;
     return TSD_OK;
 }
@@ -309,29 +275,25 @@ int tsd_create(tsd_ctx** out, int device, const tsd_config* cfg) {
 int tsd_destroy(tsd_ctx* c) {
     if (!c) return TSD_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; i++) if (c->os[i]) cudaStreamSynchronize(c->os[i]);
     DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
-                      &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores};
+                      &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores,
+                      &c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    DevBuf* more[] = {&c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
-    for (int i = 0; i < 2; i++) { if (c->cs[i]) cudaStreamDestroy(c->cs[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < 2; i++) {
         if (c->ev_slot_fork[i]) cudaEventDestroy(c->ev_slot_fork[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
         if (c->os[i]) cudaStreamDestroy(c->os[i]);
-        if (c->hp[i]) cudaStreamDestroy(c->hp[i]);
-        if (c->ev_hp_a[i]) cudaEventDestroy(c->ev_hp_a[i]);
-        if (c->ev_hp_b[i]) cudaEventDestroy(c->ev_hp_b[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
-    for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
-    for (DevBuf* b : more) if (b->p) cudaFree(b->p);
-    for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TSD_OK;
 }
@@ -433,6 +395,8 @@ int tsd_set_templates(tsd_ctx* c, const uint8_t* red6, const uint8_t* blue6) {
             h->lut[k][tp] = (uint8_t)v;
         }
     }
+    // the batch enqueued last may still be running on an internal stream (overlap mode) and reading d_tmpl: order the upload after it
+    if (join_pending(c) != TSD_OK) { delete h; return TSD_E_CUDA; }
     cudaError_t e = cudaMemcpyAsync(c->d_tmpl, h, sizeof *h, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     delete h;
@@ -447,6 +411,7 @@ int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
     CU(cudaSetDevice(c->device));
     // the kernel treats d2 >= n as "no action": require f(n-1) small enough that sqrt(f) < tol*merge_factor for both passes
     if (sqrt(f[n - 1]) >= c->cfg.coord_tol * c->cfg.merge_factor) return fail(TSD_E_INVALID, "similarity table too short: f(%d)=%g", n - 1, f[n - 1]);
+    TRY(join_pending(c));
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_simtab) CU(cudaFree(c->d_simtab));
     c->d_simtab = nullptr;
@@ -460,6 +425,7 @@ int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
 int tsd_set_lda(tsd_ctx* c, const double* W, const double* b, int nfeat) {
     if (!c || !W || !b || nfeat < 1 || nfeat > 4096) return fail(TSD_E_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_ldaW) cudaFree(c->d_ldaW);
     if (c->d_ldab) cudaFree(c->d_ldab);
@@ -476,6 +442,7 @@ int tsd_set_knn(tsd_ctx* c, const double* xbar, const double* scalings, int nfea
     if (!c || !xbar || !scalings || !Ztrain || !ytrain || nfeat < 1 || ntrain < 1 || k < 1 || k > kKnnMaxK)
         return fail(TSD_E_INVALID, "bad argument (k must be 1..%d)", kKnnMaxK);
     CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     CU(cudaStreamSynchronize(c->stream));
     void* old[] = {c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : old) if (p) cudaFree(p);
@@ -531,39 +498,24 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
 
 // out_stride = bytes between output windows: D*D*ch (public packed layout) or win_stride() (internal, zero padded)
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
-                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride,
-                           const int32_t* frame_offsets = nullptr, int nframes = 0) {
+                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride) {
     if (n_max == 0) return TSD_OK;
-    int g4 = cdiv(n_max, 4);
-    if (c->k2_grid_limit > 0 && g4 > c->k2_grid_limit) g4 = c->k2_grid_limit;     // only the v2 kernels loop over windows
-    if (!c->k2_by_frame || (c->k2_variant != 2 && c->k2_variant != 5)) frame_offsets = nullptr;
-    if (frame_offsets) g4 = nframes;                         // one CTA per frame (v2 only)
+    const int g4 = cdiv(n_max, 4);
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
-    // TSD_K2 = v2 | v3 | v4 | v5 (default v2, the fastest measured on B200) selects the resize kernel for A/B measurements; all are bit-identical.
-    // v3 (staged through shared memory with cp.async) needs 16-byte aligned rows: its 128-bit chunks never leave the frame buffer.
-    const bool fast = c->k2_variant == 3 && c->k2_grid_limit == 0 && ((uintptr_t)frames % 16 == 0) && rs % 16 == 0 && fs % 16 == 0 && ((int64_t)W * ch) % 16 == 0;
-    const int gk = cdiv(n_max, kK2Warps);
-    const bool v4 = c->k2_variant == 4 && c->k2_grid_limit == 0 && ((uintptr_t)windows % 16 == 0);
-    // TSD_K2=v5: v2 with aligned 32-bit tap loads (needs the number of frames behind `frames`: only the chain knows it)
-    const bool wide = c->k2_variant == 5 && ch == 3 && nframes > 0 && ((uintptr_t)frames % 4 == 0) && rs % 4 == 0 && fs % 4 == 0;
-    if (fast && ch == 3 && D == 25) k2_crop_resize_v3_kernel<3, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 3 && D == 32) k2_crop_resize_v3_kernel<3, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 1 && D == 25) k2_crop_resize_v3_kernel<1, 25><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (fast && ch == 1 && D == 32) k2_crop_resize_v3_kernel<1, 32><<<gk, kK2Warps * 32, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 3 && D == 25) k2_crop_resize_v4_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 3 && D == 32) k2_crop_resize_v4_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 1 && D == 25) k2_crop_resize_v4_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (v4 && ch == 1 && D == 32) k2_crop_resize_v4_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (wide && D == 25) k2_crop_resize_v2_kernel<3, 25, 12, true><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
-    else if (wide && D == 32) k2_crop_resize_v2_kernel<3, 32, 12, true><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes);
-    else if (ch == 3 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
-    else if (ch == 3 && D == 32) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<3, 32, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<3, 32, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<3, 32, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
-    else if (ch == 1 && D == 25) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<1, 25, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<1, 25, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<1, 25, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
-    else if (ch == 1 && D == 32) { if (c->k2_minb == 10) k2_crop_resize_v2_kernel<1, 32, 10><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else if (c->k2_minb == 12) k2_crop_resize_v2_kernel<1, 32, 12><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); else k2_crop_resize_v2_kernel<1, 32, 8><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, frame_offsets, nframes); }
+    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
     else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
     return check_launch(c, "k2_crop_resize");
+}
+
+// words per bit row of the pair-class matrix for frames of up to max_n windows (the warp fold handles at most 1024)
+static inline int pair_row_words(int max_n) {
+    if (max_n > 1024) max_n = 1024;
+    return ((max_n > 1 ? max_n : 1) + 31) / 32;
 }
 
 static int dev_scan(tsd_ctx* c, const int32_t* counts, int n, int32_t* offsets) {
@@ -589,9 +541,7 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
     if (npx <= 640) {
         int grid = cdiv(n_max, 4);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
-        if (c->hist_minb == 8) k5_hist_kernel<640, 4, 8><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
-        else if (c->hist_minb == 10) k5_hist_kernel<640, 4, 10><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
-        else k5_hist_kernel<640, 4, 1><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<640, 4, 8><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     } else {
         int grid = cdiv(n_max, 3);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
@@ -601,14 +551,13 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
 }
 
 // K5: both (or one) passes of cleanDuplicatedDetections.  max_n = upper bound of windows per frame (host-known), ncap = total
-// windows (rows of the pair-class bit matrix).  max_n <= 1024: all-pairs classification (k5_pairs) + one warp per frame
+// windows (rows of the pair-class bit matrix).  max_n <= 1024: all-pairs classification (k5_gram / k5_pairs) + one warp per frame
 // (k5_fold_warp); larger frames: the general block-synchronous fold (k5_fold_kernel).
 template <int RMAX, int CAP>
-static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost) {
+static int launch_fold_warp(tsd_ctx* c, int variant, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost) {
     const int warps = RMAX <= 256 ? kFoldWarps : 2;
     const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<RMAX, CAP>);
-    static int per_sm_dev[64] = {0};                         // function attributes are per device: keyed by the context's device
-    int& per_sm = per_sm_dev[c->device & 63];
+    int& per_sm = c->fold_per_sm[variant];
     if (!per_sm) {
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -623,15 +572,15 @@ static int launch_fold_warp(tsd_ctx* c, const FoldParams& P, int nframes, uint32
     k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter);
     TRY(check_launch(c, "k5_order"));
     int grid = cdiv(nframes, warps);
-    const int resident = c->fold_ctas > 0 && c->fold_ctas < per_sm ? c->fold_ctas : per_sm;
-    if (grid > resident * c->sm_count) grid = resident * c->sm_count;
+    if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
     k5_fold_warp_kernel<RMAX, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter);
     return check_launch(c, "k5_fold_warp");
 }
 
+// M = the batch's rows of the pair-class bit matrix (2 * RW words per window, RW = words per bit row for max_n windows per frame).
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, size_t ncap, size_t m_row0, float* E_T, int64_t e_stride) {
+                    int max_n, uint32_t* M, float* E_T, int64_t e_stride) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
@@ -642,9 +591,8 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     if (nframes == 0) return TSD_OK;
     // max_n is only an upper bound (raw boxes per frame); frames with more than 1024 aspect-passing windows are flagged by
     // the warp-per-frame fold (out_count = -1) and redone by the general block-synchronous fold below
-    const bool may_exceed = max_n > 1024;
-    if (may_exceed) max_n = 1024;
-    const int RW = ((max_n > 1 ? max_n : 1) + 31) / 32;
+    const int RW = pair_row_words(max_n);
+    if (max_n > 1024) max_n = 1024;
     // Corner similarity can only act when sqrt(f1 f2) >= coord_lo, i.e. both f >= coord_lo^2: squared distances at or
     // beyond `cut` are class 0 without a table lookup (f is non-increasing in d2).
     int cut = c->simtab_n;
@@ -654,83 +602,49 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         while (lo_i < hi_i) { int mid = (lo_i + hi_i) / 2; if (c->h_simtab[mid] < thr) hi_i = mid; else lo_i = mid + 1; }
         cut = lo_i > 0 ? lo_i : 1;
     }
-    uint32_t* M = nullptr;
     int32_t* cost = nullptr;
     if (do_hist) {
-        TRY(ensure(c, c->b_pairs, (m_row0 + (ncap > 0 ? ncap : 1)) * 2 * RW * sizeof(uint32_t)));     // (already large enough inside a chunked enqueue)
-        M = (uint32_t*)c->b_pairs.p + m_row0 * 2 * RW;
         cost = out_count;                                    // [nframes] scratch until the fold writes the survivor counts (order is built first)
         CU(cudaMemsetAsync(cost, 0, (size_t)nframes * 4, c->cur));
         // frames of up to kGramBM windows: Gram matrix on the tensor cores; larger frames (and TSD_GRAM=0): CUDA-core pair kernel
         int32_t* gram_done = nullptr;
         if (c->use_gram) {
-            static bool gdone_[64] = {false};
-            if (!gdone_[c->device & 63]) {
+            if (!c->attr_gram) {
                 CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem)));
                 CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                gdone_[c->device & 63] = true;
+                c->attr_gram = true;
             }
-            TRY(ensure(c, c->b_gramdone, (2 * (c->order_off + nframes) + 2) * 4));
-            gram_done = (int32_t*)c->b_gramdone.p + 2 * c->order_off;                            // [count, frames ...] of this chunk of frames
+            gram_done = (int32_t*)c->b_gramdone.p + 2 * c->order_off;                            // [count, frames ...] of this batch
             CU(cudaMemsetAsync(gram_done, 0, 4, c->cur));
             k5_gram_kernel<<<nframes, kGramWarps * 32, sizeof(GramSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, P.hist_tol,
-                                                                                   P.hist_lo, M, cost, gram_done);
+                                                                                   P.hist_lo, M, cost, gram_done, 2 * c->sm_count);
             TRY(check_launch(c, "k5_gram"));
         }
         {
-        const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
-        const size_t psm = kPairWarps * kDenseLen * 2;
-        // with a todo list (the frames k5_gram left over) a grid of resident CTAs walks it; else one CTA per (frame, tile)
-        const int pgrid = gram_done ? (int)std::min<int64_t>((int64_t)nframes * tiles, (int64_t)c->sm_count * 16) : nframes * tiles;
-#define PAIRS_LAUNCH(G, MB)                                                                                                  \
-        do {                                                                                                                 \
-            static bool done_[64] = {false};                                                                                 \
-            if (!done_[c->device & 63]) { CU(cudaFuncSetAttribute(k5_pairs_kernel<G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); done_[c->device & 63] = true; } \
-            k5_pairs_kernel<G, MB><<<pgrid, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles, \
-                                                                                     P.hist_tol, P.hist_lo, M, cost, gram_done); \
-        } while (0)
-        switch (c->pairs_variant) {                          // TSD_PAIRS = <group><minblocks>: A/B of the software pipeline depth / register budget
-            case 41: PAIRS_LAUNCH(4, 1); break;
-            case 43: PAIRS_LAUNCH(4, 3); break;
-            case 44: PAIRS_LAUNCH(4, 4); break;
-            case 23: PAIRS_LAUNCH(2, 3); break;
-            case 24: PAIRS_LAUNCH(2, 4); break;
-            case 14: PAIRS_LAUNCH(1, 4); break;
-            case 18: PAIRS_LAUNCH(1, 8); break;
-            case 116: PAIRS_LAUNCH(1, 16); break;
-            case 16: PAIRS_LAUNCH(1, 6); break;
-            case 13: PAIRS_LAUNCH(1, 3); break;
-            default: PAIRS_LAUNCH(1, 8); break;
-        }
-#undef PAIRS_LAUNCH
-        TRY(check_launch(c, "k5_pairs"));
+            const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
+            const size_t psm = kPairWarps * kDenseLen * 2;
+            // with a todo list (the frames k5_gram left over) a grid of resident CTAs walks it; else one CTA per (frame, tile)
+            const int pgrid = gram_done ? (int)std::min<int64_t>((int64_t)nframes * tiles, (int64_t)c->sm_count * 16) : nframes * tiles;
+            if (!c->attr_pairs) {
+                CU(cudaFuncSetAttribute(k5_pairs_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                c->attr_pairs = true;
+            }
+            k5_pairs_kernel<1, 8><<<pgrid, kPairWarps * 32, psm, c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, tiles,
+                                                                             P.hist_tol, P.hist_lo, M, cost, gram_done);
+            TRY(check_launch(c, "k5_pairs"));
         }
         mark(c, "k5_pairs");
     }
-    cudaStream_t chain_stream = c->cur;
-    const bool fold_hp = c->ov_active && c->overlap >= 2;   // the latency-bound fold goes first wherever an SM has room: its own high-priority stream
-    if (fold_hp) {
-        CU(cudaEventRecord(c->ev_hp_a[c->slot], chain_stream));
-        CU(cudaStreamWaitEvent(c->hp[c->slot], c->ev_hp_a[c->slot], 0));
-        c->cur = c->hp[c->slot];
-    }
     {
         int rc;
-        if (max_n <= 256) rc = npx <= 640 ? launch_fold_warp<256, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, P, nframes, M, RW, cut, cost);
-        else rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, P, nframes, M, RW, cut, cost);
+        if (max_n <= 256) rc = npx <= 640 ? launch_fold_warp<256, 640>(c, 0, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, 1, P, nframes, M, RW, cut, cost);
+        else rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, 2, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, 3, P, nframes, M, RW, cut, cost);
         if (rc != TSD_OK) return rc;
     }
     // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
-    (void)may_exceed;
     k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
-    TRY(check_launch(c, "k5_fold"));
-    if (fold_hp) {
-        CU(cudaEventRecord(c->ev_hp_b[c->slot], c->cur));
-        c->cur = chain_stream;
-        CU(cudaStreamWaitEvent(chain_stream, c->ev_hp_b[c->slot], 0));
-    }
-    return TSD_OK;
+    return check_launch(c, "k5_fold");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -759,7 +673,16 @@ int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W
     if (row_stride < (int64_t)W * channels || frame_stride < row_stride * (H - 1) + (int64_t)W * channels) return fail(TSD_E_INVALID, "bad strides");
     if (n && (!coords || !win_frame || !windows)) return fail(TSD_E_INVALID, "NULL argument");
     CU(cudaSetDevice(c->device));
+    // Device pointers: the kernel zero-fills a window whose clipped crop is empty (cv2.resize would raise; the chain never asks for
+    // one: K1 drops such boxes).  Host pointers are checked here, like the reference's own exceptions.
     if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows, D * D * channels);
+    for (int i = 0; i < n; i++) {
+        const int32_t* q = coords + 4 * (size_t)i;
+        if (win_frame[i] < 0 || win_frame[i] >= nframes) return fail(TSD_E_INVALID, "window %d: frame %d not in [0,%d)", i, win_frame[i], nframes);
+        if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[3] < 0) return fail(TSD_E_INVALID, "window %d: negative coordinate (numpy slicing would wrap around)", i);
+        if (std::min(q[2], W) <= std::min(q[0], W) || std::min(q[3], H) <= std::min(q[1], H))
+            return fail(TSD_E_INVALID, "window %d: empty crop after clipping to the frame (cv2.resize would raise)", i);
+    }
     Stage s(c);
     void *df, *dc, *dwf, *dw;
     TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * channels, &df));
@@ -775,10 +698,13 @@ int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W
 int tsd_windows(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
                 const int32_t* boxes, const int32_t* box_offsets, double enlarge, int D, uint8_t* windows, int32_t* coords,
                 int32_t* win_offsets, int32_t* total, int mem) {
-    if (!c || !frames || !box_offsets || !win_offsets || nframes < 1 || D < 2 || D > kMaxD) return fail(TSD_E_INVALID, "bad argument");
+    if (!c || !frames || !box_offsets || !win_offsets || nframes < 1 || H < 1 || W < 1 || D < 2 || D > kMaxD) return fail(TSD_E_INVALID, "bad argument");
+    if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
     if (mem != TSD_MEM_HOST) return fail(TSD_E_INVALID, "tsd_windows takes host pointers; use tsd_enqueue_frames for device-resident batches");
     CU(cudaSetDevice(c->device));
     const int nb = box_offsets[nframes];
+    if (nb < 0 || (nb && !boxes)) return fail(TSD_E_INVALID, "bad boxes");
+    for (int f = 0; f < nframes; f++) if (box_offsets[f + 1] < box_offsets[f]) return fail(TSD_E_INVALID, "box_offsets must not decrease (frame %d)", f);
     Stage s(c);
     void *df, *db, *dbo, *dcnt, *dwo, *dc, *dwf, *dw;
     TRY(s.in(frames, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3, &df));
@@ -840,8 +766,10 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     int max_n = 0;
     for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
     c->order_off = 0;
+    TRY(ensure(c, c->b_pairs, (size_t)(n > 0 ? n : 1) * 2 * pair_row_words(max_n) * sizeof(uint32_t)));
+    TRY(ensure(c, c->b_gramdone, (size_t)(2 * nframes + 2) * 4));
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (size_t)n, 0, (float*)den, n));
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (float*)den, n));
     TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
     if (nframes) {
         k5_gather_kernel<<<nframes, 128, 0, c->cur>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
@@ -888,7 +816,7 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
     if (mem == TSD_MEM_HOST) { TRY(s.in(windows, (size_t)n * npx * 3, &dw)); TRY(s.alloc(&dr, (size_t)n * npx)); TRY(s.alloc(&db, (size_t)n * npx)); }
     int grid = cdiv((int64_t)n * 32, 256);
     if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-    k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db,
+    k3_masks_generic_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db,
                                                     npx, nullptr);       // public layout: packed windows and masks
     TRY(check_launch(c, "k3_masks"));
     if (mem == TSD_MEM_HOST) { TRY(s.out(red, dr, (size_t)n * npx)); TRY(s.out(blue, db, (size_t)n * npx)); CU(cudaStreamSynchronize(c->stream)); }
@@ -898,6 +826,7 @@ int tsd_color_masks(tsd_ctx* c, const uint8_t* windows, int n, int D, uint8_t* r
 int tsd_set_gamma_table(tsd_ctx* c, const uint8_t* table256) {
     if (!c || !table256) return fail(TSD_E_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     CU(cudaMemcpyAsync(c->d_gamma, table256, 256, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
@@ -1081,7 +1010,7 @@ int tsd_score(tsd_ctx* c, const uint8_t* windows, int n, int D, int32_t* id, int
     TRY(s.alloc(&di, (size_t)n * 4)); TRY(s.alloc(&dh, (size_t)n * 4)); TRY(s.alloc(&de, (size_t)n));
     int grid = cdiv((int64_t)n * 32, 256);
     if (grid > c->sm_count * 8) grid = c->sm_count * 8;
-    k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db, npx, nullptr);
+    k3_masks_generic_kernel<<<grid, 256, 0, c->cur>>>((uint8_t*)dw, nullptr, nullptr, n, npx, npx * 3, c->d_tab, bounds_of(c->cfg), (uint8_t*)dr, (uint8_t*)db, npx, nullptr);
     TRY(check_launch(c, "k3_masks"));
     k4_score_kernel<<<cdiv((int64_t)n * 32, 128), 128, 0, c->cur>>>((uint8_t*)dr, (uint8_t*)db, nullptr, n, npx, npx, c->d_tmpl, c->cfg.score_tol_hundredths,
                                                                      nullptr, (int32_t*)di, (int32_t*)dh, (uint8_t*)de);
@@ -1236,15 +1165,15 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 }
 
 // ---- whole chain -------------------------------------------------------------------------------------------------
-// One chunk of frames through the whole chain on c->cur.  wo = first window slot of the chunk in the per-window scratch,
-// fo = first entry of the chunk in the per-frame scratch arrays (cf + 1 entries), nbcap = upper bound of the chunk's boxes.
-static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, int H, int W, int64_t row_stride, int64_t frame_stride,
-                         const int32_t* d_boxes, const int32_t* d_box_offsets, int nbcap, int maxb, size_t wo, int fo, int chunk_index,
-                         int phase = 3 /* bit 0: K1+K2 (the part that reads the frames), bit 1: everything after */) {
+// One batch of frames through the whole chain on c->cur.  B.wo = first window slot of the batch in the per-window scratch,
+// B.fo = first entry in the per-frame scratch arrays (nframes + 1 entries), B.nbcap = upper bound of the batch's windows;
+// M = the batch's rows of the pair-class bit matrix.
+static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+                         const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M) {
     const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
-    const int nb = nbcap;
-    const size_t cap = nbcap > 0 ? nbcap : 1;
+    const int cf = B.nframes, nb = B.nbcap, fo = B.fo;
+    const size_t cap = nb > 0 ? nb : 1, wo = B.wo;
     int32_t *cnt = (int32_t*)c->b_cnt.p + fo, *winoff = (int32_t*)c->b_winoff.p + fo, *survcnt = (int32_t*)c->b_survcnt.p + fo, *survoff = (int32_t*)c->b_survoff.p + fo;
     int32_t *detcnt = (int32_t*)c->b_detcnt.p + fo, *detoff = (int32_t*)c->b_detoff.p + fo;
     int32_t* coords = (int32_t*)c->b_coords.p + wo * 4;
@@ -1252,27 +1181,24 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
     uint8_t* windows = (uint8_t*)c->b_windows.p + wo * ws;
     uint32_t* entries = (uint32_t*)c->b_entries.p + wo * es;
     WinMeta* meta = (WinMeta*)c->b_meta.p + wo;
-    float* energy = (float*)c->b_energy.p + wo * kEnergyRows;          // [25 energies + chunk boundaries][cap] block of this chunk
+    float* energy = (float*)c->b_energy.p + wo * kEnergyRows;          // [25 energies + chunk boundaries][cap] block of this batch
     int32_t *list = (int32_t*)c->b_list.p + wo, *slots = (int32_t*)c->b_slots.p + wo, *id = (int32_t*)c->b_id.p + wo, *hund = (int32_t*)c->b_hund.p + wo;
     uint8_t *flags = (uint8_t*)c->b_flags.p + wo, *emit = (uint8_t*)c->b_emit.p + wo;
     DetRec* det = (DetRec*)c->b_det.p + wo;
     c->order_off = (size_t)fo;
     const int32_t* d_nwin = winoff + cf;
-    if (phase & 1) {
-        mark(c, "start");
-        // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
-        TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
-        mark(c, "k1_expand_filter");
-        // K2 (DET:123-124)
-        TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws, winoff, cf));
-        mark(c, "k2_crop_resize");
-    }
-    if (!(phase & 2)) return TSD_OK;
+    mark(c, "start");
+    // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
+    TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
+    mark(c, "k1_expand_filter");
+    // K2 (DET:123-124)
+    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
+    mark(c, "k2_crop_resize");
     // K5 (DET:127-129)
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 list, flags, survcnt, maxb, cap, wo, energy, (int64_t)cap));
+                 list, flags, survcnt, maxb, M, energy, (int64_t)cap));
     TRY(dev_scan(c, survcnt, cf, survoff));
     k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
     TRY(check_launch(c, "k5_gather"));
@@ -1290,7 +1216,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
             k3_masks_v3_kernel<4><<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, c->d_mlut, c->keep_masks ? red : nullptr,
                                                             c->keep_masks ? blue : nullptr, ms, bits);
         else
-            k3_masks_v2_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
+            k3_masks_generic_kernel<<<grid, 256, 0, c->cur>>>(windows, slots, d_nsurv, nb, npx, ws, c->d_tab, bounds_of(c->cfg), red, blue, ms, bits);
         TRY(check_launch(c, "k3_masks"));
         mark(c, "k3_masks");
         if (NW == 20)
@@ -1327,7 +1253,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int cf, 
     TRY(check_launch(c, "det_count"));
     TRY(dev_scan(c, detcnt, cf, detoff));
     det_write_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, id, hund, (int4*)coords, slots, survoff, detoff, cf, (int)cap, det,
-                                                                        winoff + cf, survoff + cf, (int32_t*)c->b_summary.p + 4 * chunk_index);
+                                                                        winoff + cf, survoff + cf, (int32_t*)c->b_summary.p + 4 * B.sidx);
     TRY(check_launch(c, "det_write"));
     mark(c, "detections");
     return TSD_OK;
@@ -1343,54 +1269,44 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     if (mode == TSD_RUN_DETECT && (!c->have_templates || c->tmpl_D != D)) return fail(TSD_E_STATE, "templates not set for D=%d", D);
     if (mode == TSD_RUN_RECOGNIZE && (!c->d_ldaW || D != 32 || c->lda_nfeat != TSD_HOG_LEN)) return fail(TSD_E_STATE, "recognition needs D=32 and 324-feature LDA weights");
     CU(cudaSetDevice(c->device));
-    // ---- chunking: consecutive chunks alternate between two streams ------------------------------------------------
-    int CFr = nframes;
-    if (!c->profiling && c->stream_chunk >= 0) {
-        CFr = c->stream_chunk > 0 ? c->stream_chunk : (nframes + 7) / 8;
-        if (c->stream_chunk == 0 && CFr < 256) CFr = 256;
-        if (CFr > nframes) CFr = nframes;
-    }
-    const int nchunks = (nframes + CFr - 1) / CFr;
-    std::vector<int32_t> ho;
     if (max_boxes_per_frame <= 0) {                          // not given: one small D2H of the CSR offsets (synchronises)
-        ho.resize(nframes + 1);
+        std::vector<int32_t> ho(nframes + 1);
         CU(cudaMemcpyAsync(ho.data(), d_box_offsets, (size_t)(nframes + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         for (int f = 0; f < nframes; f++) max_boxes_per_frame = ho[f + 1] - ho[f] > max_boxes_per_frame ? ho[f + 1] - ho[f] : max_boxes_per_frame;
     }
-    if (c->last_was_overlap) c->prev_chunks = c->chunks; else c->prev_chunks.clear();   // (tsd_fetch_previous: both batches must sit in slots)
-    c->prev_nboxes = c->last_nboxes;
-    c->last_was_overlap = false;
-    c->chunks.clear();
-    size_t wtot = 0;
-    for (int k = 0; k < nchunks; k++) {
-        tsd_ctx::ChunkInfo ci;
-        ci.f0 = k * CFr; ci.cf = nframes - ci.f0 < CFr ? nframes - ci.f0 : CFr;
-        // boxes of the chunk: exact when the offsets are on the host, else bounded by cf * max_boxes_per_frame (and by nb)
-        ci.nbcap = !ho.empty() ? ho[ci.f0 + ci.cf] - ho[ci.f0] : (nchunks == 1 ? nb : (int)std::min<int64_t>((int64_t)ci.cf * max_boxes_per_frame, nb));
-        ci.wo = wtot; ci.fo = ci.f0 + k; ci.sidx = k;
-        wtot += (size_t)((ci.nbcap > 0 ? ci.nbcap : 1) + 3) & ~(size_t)3;     // keeps every chunk's slices 16-byte aligned
-        c->chunks.push_back(ci);
-    }
-    size_t cap = wtot, fcap = (size_t)nframes + nchunks;
-    const bool ov = c->overlap && !c->profiling && nchunks == 1;
+    const int RW = pair_row_words(max_boxes_per_frame);
+    c->prev = c->last;                                       // (tsd_fetch_previous: valid only while both batches sit in slots)
+    if (!c->prev.in_slot) c->prev.valid = false;
+    c->last = tsd_ctx::Batch();
+    tsd_ctx::Batch B;
+    B.nframes = nframes; B.nbcap = nb; B.nboxes = nb;
+    const size_t need_w = (((size_t)(nb > 0 ? nb : 1) + 3) & ~(size_t)3);
+    size_t cap = need_w, fcap = (size_t)nframes + 1, mwords = need_w * 2 * RW, m_off = 0;
+    const bool ov = c->overlap && !c->profiling;
     if (ov) {                                                // this batch lives in slot `slot` of doubled scratch buffers
         c->slot ^= 1;
-        const size_t need_w = (wtot + 63) & ~(size_t)63, need_f = ((size_t)nframes + 2 + 63) & ~(size_t)63;
-        if (need_w > c->slot_cap || need_f > c->slot_fcap) { // the layout changes: nothing may be in flight
-            c->prev_chunks.clear();
+        const size_t sw = (need_w + 63) & ~(size_t)63, sf = ((size_t)nframes + 2 + 63) & ~(size_t)63;
+        if (sw > c->slot_cap || sf > c->slot_fcap || RW > c->slot_rw) {
+            // The slot layout changes (slot 1 starts at slot_cap windows, slot_fcap frames, slot_cap * 2 * slot_rw pair-class
+            // words): nothing may be in flight in either slot.  All three are sticky maxima, so a batch never reaches into the
+            // other slot whatever its own RW is.
+            c->prev.valid = false;
             TRY(join_pending(c));
             CU(cudaStreamSynchronize(c->stream));
-            if (need_w > c->slot_cap) c->slot_cap = need_w;
-            if (need_f > c->slot_fcap) c->slot_fcap = need_f;
+            if (sw > c->slot_cap) c->slot_cap = sw;
+            if (sf > c->slot_fcap) c->slot_fcap = sf;
+            if (RW > c->slot_rw) c->slot_rw = RW;
         }
-        c->chunks[0].wo = (size_t)c->slot * c->slot_cap;
-        c->chunks[0].fo = (int)((size_t)c->slot * c->slot_fcap);
-        c->chunks[0].sidx = c->slot;
+        B.wo = (size_t)c->slot * c->slot_cap;
+        B.fo = (int)((size_t)c->slot * c->slot_fcap);
+        B.sidx = c->slot; B.in_slot = true;
         cap = 2 * c->slot_cap; fcap = 2 * c->slot_fcap;
+        mwords = 2 * c->slot_cap * 2 * (size_t)c->slot_rw;
+        m_off = (size_t)c->slot * c->slot_cap * 2 * (size_t)c->slot_rw;
     } else {
         TRY(join_pending(c));
-        c->prev_chunks.clear();
+        c->prev.valid = false;
     }
     TRY(ensure(c, c->b_cnt, fcap * 4));
     TRY(ensure(c, c->b_winoff, fcap * 4));
@@ -1398,8 +1314,9 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_survoff, fcap * 4));
     TRY(ensure(c, c->b_detcnt, fcap * 4));
     TRY(ensure(c, c->b_detoff, fcap * 4));
-    TRY(ensure(c, c->b_summary, (size_t)(nchunks > 2 ? nchunks : 2) * 16));
-    TRY(ensure(c, c->b_order, fcap * 4));
+    TRY(ensure(c, c->b_summary, 2 * 16));
+    TRY(ensure(c, c->b_order, (fcap + 2) * 4));
+    TRY(ensure(c, c->b_gramdone, (2 * fcap + 4) * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));
     TRY(ensure(c, c->b_windows, cap * ws));
@@ -1421,61 +1338,28 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(ensure(c, c->b_gray, cap * npx));
         TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
     }
-    {   // the pair-class bit rows are sized here (not inside dev_fold) so that no chunk can trigger a reallocation
-        const int mb = max_boxes_per_frame > 1024 ? 1024 : max_boxes_per_frame;
-        const int RW = ((mb > 1 ? mb : 1) + 31) / 32;
-        TRY(ensure(c, c->b_pairs, cap * 2 * RW * sizeof(uint32_t)));
-    }
+    TRY(ensure(c, c->b_pairs, mwords * sizeof(uint32_t)));
+    uint32_t* M = (uint32_t*)c->b_pairs.p + m_off;
     int rc = TSD_OK;
     if (ov) {
-        const tsd_ctx::ChunkInfo& ci = c->chunks[0];
         const int sl = c->slot;
         CU(cudaEventRecord(c->ev_slot_fork[sl], c->stream));
         CU(cudaStreamWaitEvent(c->os[sl], c->ev_slot_fork[sl], 0));
         TRY(join_pending(c));                                // the PREVIOUS batch: the context's stream waits for it only now, after this batch's fork
         c->cur = c->os[sl];
-        c->ov_active = true;
-        rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, ci.sidx);
-        c->ov_active = false;
+        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M);
         CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
         c->pending_join = sl;
-        c->last_was_overlap = rc == TSD_OK;
-    } else if (nchunks == 1) {
-        c->cur = c->stream;
-        rc = enqueue_chain(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, c->chunks[0].nbcap, max_boxes_per_frame, 0, 0, 0);
     } else {
-        CU(cudaEventRecord(c->ev_fork, c->stream));
-        for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(c->cs[i], c->ev_fork, 0));
-        while ((int)c->ev_chunk.size() < nchunks) {
-            cudaEvent_t e;
-            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->ev_chunk.push_back(e);
-        }
-        for (int k = 0; k < nchunks && rc == TSD_OK; k++) {
-            const tsd_ctx::ChunkInfo& ci = c->chunks[k];
-            // offsets stay absolute (the kernels index `d_boxes` with them), so the box base pointer is not advanced
-            const uint8_t* fr = d_frames + (size_t)ci.f0 * frame_stride;
-            if (c->pipe_mode) {
-                // producer / consumer: K1+K2 of every chunk on cs[0] (low priority; PCIe-bound when the frames are host memory),
-                // the rest of the chain of chunk k on cs[1] (high priority) as soon as its windows exist -> it runs under K2 of chunk k+1
-                c->cur = c->cs[0];
-                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k, 1);
-                if (rc != TSD_OK) break;
-                CU(cudaEventRecord(c->ev_chunk[k], c->cs[0]));
-                CU(cudaStreamWaitEvent(c->cs[1], c->ev_chunk[k], 0));
-                c->cur = c->cs[1];
-                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k, 2);
-            } else {
-                c->cur = c->cs[k & 1];
-                rc = enqueue_chain(c, mode, fr, ci.cf, H, W, row_stride, frame_stride, d_boxes, d_box_offsets + ci.f0, ci.nbcap, max_boxes_per_frame, ci.wo, ci.fo, k);
-            }
-        }
         c->cur = c->stream;
-        for (int i = 0; i < 2; i++) { CU(cudaEventRecord(c->ev_join[i], c->cs[i])); CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0)); }
+        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M);
     }
     c->cur = c->stream;
-    if (rc != TSD_OK) return rc;
-    c->last_nframes = nframes; c->last_mode = mode; c->last_nboxes = nb; c->last_detcap = (int)cap;
+    if (rc != TSD_OK) { c->prev.valid = false; return rc; }
+    B.valid = true;
+    c->last = B;
+    c->last_mode = mode;
+    if (!ov) c->prev.valid = false;
     return TSD_OK;
 }
 
@@ -1491,14 +1375,13 @@ __global__ void sum_nnz_kernel(const WinMeta* __restrict__ meta, const int32_t* 
 
 int tsd_stat_hist_entries(tsd_ctx* c, int64_t* total) {
     if (!c || !total) return fail(TSD_E_INVALID, "bad argument");
-    if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
+    if (!c->last.valid) return fail(TSD_E_STATE, "nothing enqueued");
     CU(cudaSetDevice(c->device));
     TRY(join_pending(c));
     unsigned long long* d = nullptr;
     CU(cudaMallocAsync((void**)&d, 8, c->stream));
     CU(cudaMemsetAsync(d, 0, 8, c->stream));
-    for (const tsd_ctx::ChunkInfo& ci : c->chunks)
-        sum_nnz_kernel<<<64, 256, 0, c->stream>>>((const WinMeta*)c->b_meta.p + ci.wo, (const int32_t*)c->b_winoff.p + ci.fo + ci.cf, d);
+    sum_nnz_kernel<<<64, 256, 0, c->stream>>>((const WinMeta*)c->b_meta.p + c->last.wo, (const int32_t*)c->b_winoff.p + c->last.fo + c->last.nframes, d);
     unsigned long long h = 0;
     CU(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaFreeAsync(d, c->stream));
@@ -1507,60 +1390,60 @@ int tsd_stat_hist_entries(tsd_ctx* c, int64_t* total) {
     return TSD_OK;
 }
 
-static int fetch_impl(tsd_ctx* c, const std::vector<tsd_ctx::ChunkInfo>& chunks, int nboxes, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
-    static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
-    const int nchunks = (int)chunks.size();
-    std::vector<int32_t> h((size_t)nchunks * 4);
-    for (int k = 0; k < nchunks; k++)
-        CU(cudaMemcpyAsync(h.data() + 4 * k, (int32_t*)c->b_summary.p + 4 * chunks[k].sidx, 16, cudaMemcpyDeviceToHost, c->stream));
+// Pairs (over the life of the process, all contexts of this device) that were decided by the exact f64 evaluation because their
+// integer-dot classification came within 2e-6 of a threshold.  reset != 0 zeroes the counter after reading.  Synchronises.
+int tsd_stat_unsure_pairs(tsd_ctx* c, int64_t* total, int reset) {
+    if (!c || !total) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
     CU(cudaStreamSynchronize(c->stream));
-    int64_t tw = 0, ts = 0, td = 0;
-    for (int k = 0; k < nchunks; k++) { tw += h[4 * k]; ts += h[4 * k + 1]; td += h[4 * k + 2]; }
-    if (counts) { counts[0] = nboxes; counts[1] = (int32_t)tw; counts[2] = (int32_t)ts; counts[3] = (int32_t)td; }
-    *ndet = (int32_t)td;
-    if (td > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, (int)td);
-    if (td) {
+    unsigned long long h = 0;
+    CU(cudaMemcpyFromSymbol(&h, g_unsure_pairs, sizeof h));
+    if (reset) { const unsigned long long z = 0; CU(cudaMemcpyToSymbol(g_unsure_pairs, &z, sizeof z)); }
+    *total = (int64_t)h;
+    return TSD_OK;
+}
+
+static int fetch_impl(tsd_ctx* c, const tsd_ctx::Batch& B, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
+    static_assert(sizeof(tsd_detection) == sizeof(DetRec), "record layout");
+    int32_t h[4] = {0, 0, 0, 0};                             // {windows, survivors, detections, -} written by det_write
+    CU(cudaMemcpyAsync(h, (int32_t*)c->b_summary.p + 4 * B.sidx, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (counts) { counts[0] = B.nboxes; counts[1] = h[0]; counts[2] = h[1]; counts[3] = h[2]; }
+    *ndet = h[2];
+    if (h[2] > det_cap) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, h[2]);
+    if (h[2]) {
         if (!det) return fail(TSD_E_INVALID, "det is NULL");
-        int o = 0;
-        for (int k = 0; k < nchunks; k++) {
-            const int n = h[4 * k + 2];
-            if (n) CU(cudaMemcpyAsync(det + o, (DetRec*)c->b_det.p + chunks[k].wo, (size_t)n * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
-            o += n;
-        }
+        CU(cudaMemcpyAsync(det, (DetRec*)c->b_det.p + B.wo, (size_t)h[2] * sizeof(DetRec), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        o = 0;
-        for (int k = 0; k < nchunks; k++) {                  // records carry chunk-local frame indices
-            const int n = h[4 * k + 2], f0 = chunks[k].f0;
-            if (f0) for (int i = 0; i < n; i++) det[o + i].frame += f0;
-            o += n;
-        }
     }
     return TSD_OK;
 }
 
 int tsd_fetch_detections(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
     if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
-    if (c->last_nframes == 0) return fail(TSD_E_STATE, "nothing enqueued");
+    if (!c->last.valid) return fail(TSD_E_STATE, "nothing enqueued");
     CU(cudaSetDevice(c->device));
     TRY(join_pending(c));
-    return fetch_impl(c, c->chunks, c->last_nboxes, det, det_cap, ndet, counts);
+    return fetch_impl(c, c->last, det, det_cap, ndet, counts);
 }
 
 // The batch enqueued BEFORE the last one (overlap mode): the context's stream already waits for it (the last tsd_enqueue_frames
 // joined it after forking its own batch) but not for the last batch, which keeps running while these records are read.
 int tsd_fetch_previous(tsd_ctx* c, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts) {
     if (!c || !ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
-    if (c->prev_chunks.empty() || c->pending_join < 0)
+    if (!c->prev.valid || c->pending_join < 0)
         return fail(TSD_E_STATE, "no previous batch to fetch (needs two consecutive tsd_enqueue_frames calls in overlap mode, nothing in between)");
     CU(cudaSetDevice(c->device));
-    const int rc = fetch_impl(c, c->prev_chunks, c->prev_nboxes, det, det_cap, ndet, counts);
-    c->prev_chunks.clear();
+    const int rc = fetch_impl(c, c->prev, det, det_cap, ndet, counts);
+    c->prev.valid = false;
     return rc;
 }
 
 int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
                       const int32_t* boxes, const int32_t* box_offsets, tsd_detection* det, int det_cap, int32_t* ndet, int32_t* counts, int mem) {
-    if (!c || !frames || !box_offsets || nframes < 1) return fail(TSD_E_INVALID, "bad argument");
+    if (!c || !frames || !box_offsets || nframes < 1 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
+    if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
     CU(cudaSetDevice(c->device));
     if (mem == TSD_MEM_DEVICE) {
         int32_t nb = 0;
@@ -1570,9 +1453,11 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         return tsd_fetch_detections(c, det, det_cap, ndet, counts);
     }
     const int nb = box_offsets[nframes];
-    if (nb && !boxes) return fail(TSD_E_INVALID, "boxes is NULL");
+    if (nb < 0 || (nb && !boxes)) return fail(TSD_E_INVALID, "boxes is NULL");
     if (!ndet || det_cap < 0) return fail(TSD_E_INVALID, "bad argument");
+    for (int f = 0; f < nframes; f++) if (box_offsets[f + 1] < box_offsets[f]) return fail(TSD_E_INVALID, "box_offsets must not decrease (frame %d)", f);
     // boxes + offsets: one small upload
+    TRY(join_pending(c));
     TRY(ensure(c, c->b_hboxes, (size_t)(nb > 0 ? nb : 1) * 16));
     TRY(ensure(c, c->b_hoff, (size_t)(nframes + 1) * 4));
     if (nb) CU(cudaMemcpyAsync(c->b_hboxes.p, boxes, (size_t)nb * 16, cudaMemcpyHostToDevice, c->stream));
@@ -1585,7 +1470,7 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         int max_n = 0;
         for (int f = f0; f < f0 + cf; f++) max_n = box_offsets[f + 1] - box_offsets[f] > max_n ? box_offsets[f + 1] - box_offsets[f] : max_n;
         // offsets stay absolute: the kernels index `boxes` with them, so the base pointer is the whole box array
-        return tsd_enqueue_frames(c, mode, d_frames, cf, H, W, row_stride, frame_stride, d_boxes, d_off + f0, box_offsets[f0 + cf] - box_offsets[f0], max_n);
+        return tsd_enqueue_frames(c, mode, d_frames, cf, H, W, row_stride, frame_stride, d_boxes, d_off + f0, box_offsets[f0 + cf] - box_offsets[f0], max_n > 0 ? max_n : 1);
     };
     auto fetch_chunk = [&](int f0) -> int {
         int32_t nd = 0, cnt[4];
@@ -1604,26 +1489,15 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         // (~0.5 MB of a 3.26 MB frame at 200 candidates), measured 3.3x faster than copying whole frames (profiles/).
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            // K2 is PCIe-bound here: a persistent grid of 2 CTAs per SM keeps the bus busy and leaves the SMs to the other
-            // kernels; the batch is split into chunks on two streams so that the chain of chunk k runs under the PCIe
-            // reads of chunk k+1 (TSD_ZC_CHUNK frames per chunk, 0 = one chunk; TSD_ZC_GRID CTAs per SM, 0 = full grid)
-            const int save_chunk = c->stream_chunk, save_limit = c->k2_grid_limit, save_pipe = c->pipe_mode;
-            if (!c->profiling) {
-                c->stream_chunk = c->zc_chunk > 0 ? c->zc_chunk : -1;
-                c->k2_grid_limit = c->zc_grid * c->sm_count;
-                c->pipe_mode = c->zc_pipe;
-            }
-            int rc = run_chunk((const uint8_t*)at.devicePointer, 0, nframes);
-            c->stream_chunk = save_chunk; c->k2_grid_limit = save_limit; c->pipe_mode = save_pipe;
-            TRY(rc);
-            rc = fetch_chunk(0);
+            TRY(run_chunk((const uint8_t*)at.devicePointer, 0, nframes));
+            const int rc = fetch_chunk(0);
             *ndet = nd_total;
             if (counts) for (int i = 0; i < 4; i++) counts[i] = tot[i];
             return rc;
         }
         cudaGetLastError();
     }
-    // chunked, double-buffered: the H2D copy of chunk k+1 (copy stream) overlaps the chain of chunk k (compute stream)
+    // pageable frames: chunked, double-buffered whole-frame copies; the H2D copy of chunk k+1 (copy stream) overlaps the chain of chunk k
     const int CF = c->chunk_frames < nframes ? c->chunk_frames : nframes;
     const int nchunks = (nframes + CF - 1) / CF;
     const size_t frame_bytes = (size_t)row_stride * (H - 1) + (size_t)W * 3;

@@ -35,6 +35,9 @@ constexpr int kGramCbWords = (kGramChunks + 1) / 2;
 constexpr int kEnergyRows = kHistGroups + kGramCbWords;   // rows of the [rows][windows] energy block
 static_assert(kGramKC % 32 == 0 && kEnergyRows <= 32, "chunk boundaries");
 constexpr int kClsUnsure = 3;
+// Statistics: pairs whose integer-dot classification came within 2e-6 of a threshold and were decided by the exact f64 evaluation
+// (tsd_stat_unsure_pairs; the tests use it to prove that path is exercised).  Rare, so the atomic costs nothing.
+__device__ unsigned long long g_unsure_pairs = 0;
 
 __device__ __forceinline__ int classify(double sim, double tol, double lo) {
     return sim > tol ? 1 : ((lo <= sim && sim <= tol) ? 2 : 0);
@@ -448,6 +451,7 @@ __device__ __forceinline__ void k5_pairs_tile(const uint32_t* __restrict__ entri
         }
         if (need) c = classify_from_int(Ik, mj, mi, tol, lo);
         unsigned unsure = __ballot_sync(0xffffffffu, need && c == kClsUnsure);
+        if (unsure && lane == 0) atomicAdd(&g_unsure_pairs, (unsigned long long)__popc(unsure));
         while (unsure) {                                    // rare: within 2e-6 of a threshold -> exact f64 evaluation
             const int k = __ffs(unsure) - 1;
             unsure &= unsure - 1;
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
                                                                     const float* __restrict__ E_T, int64_t e_stride,
                                                                     const int32_t* __restrict__ offsets, int nframes, int es, int RW,
                                                                     double tol, double lo, uint32_t* __restrict__ M,
-                                                                    int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo) {
+                                                                    int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo, int prefetch_ahead) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GramSmem& S = *reinterpret_cast<GramSmem*>(smem_raw);
     const int f = blockIdx.x;
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
         if (two) gram_issue(cb1, act1, er1, 0, pool, pcap, fill, off1, sp1);
     }
     {                                                        // pull a later frame's entry rows into L2 (this frame's were pulled by an earlier CTA)
-        const int fp = f + 2 * 148;
+        const int fp = f + prefetch_ahead;                   // = CTAs resident at once (2 per SM)
         if (fp < nframes) {
             const int bp = offsets[fp], np = min(offsets[fp + 1] - bp, kGramBM);
             for (int i = tid; i < np * 12; i += kGramWarps * 32) {
@@ -784,6 +788,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
             int c = 0;
             if (valid) c = classify_from_int_s(sI[jl * kGramIPitch + ii], Aj, rAj, s1j, aj, S.A[ii], S.rA[ii], S.s1[ii], S.a[ii], tol, lo);
             unsigned unsure = __ballot_sync(0xffffffffu, valid && c == kClsUnsure);
+            if (unsure && lane == 0) atomicAdd(&g_unsure_pairs, (unsigned long long)__popc(unsure));
             while (unsure) {                                // rare: within 2e-6 of a threshold -> exact f64 evaluation
                 const int k = __ffs(unsure) - 1;
                 unsure &= unsure - 1;
@@ -958,6 +963,7 @@ __device__ __forceinline__ void fold_classify_against(FoldWarpSmem<RMAX, CAP>& s
             const WinMeta mq = load_meta_cg(P.meta + q);
             int c = classify_from_int(Ik, mj, mq, P.hist_tol, P.hist_lo);
             if (c == kClsUnsure) {
+                atomicAdd(&g_unsure_pairs, 1ull);
                 const uint32_t* eo = P.entries + (int64_t)q * P.es;
                 double s12 = 0;
                 for (int i = 0; i < mq.nnz; i++) {

@@ -76,6 +76,12 @@ __device__ __forceinline__ void bgr2hsv(int b, int g, int r, const int32_t* __re
     V = v;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -254,42 +260,27 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 
 // K2 v2: same arithmetic, restructured for instruction count (v1 was issue-bound at ~100 instructions per output
 // byte-iteration).  One warp per window, lane = destination column; the x coefficients live in registers, the y
-// coefficients are computed by lane dy and broadcast by shuffle; each lane walks the D destination rows and reads its
+// coefficients are computed by lane dy and broadcast through shared memory; each lane walks the D destination rows and reads its
 // 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
-// WIDE (C = 3, 4-byte aligned frames and strides, nframes known): the 6 consecutive bytes a lane needs of a source row (its two
-// taps x 3 channels) come from 2-3 aligned 32-bit loads + a funnel shift instead of 6 byte loads -- the kernel is bound by the L1
-// data pipe (74 % of its wavefront rate with byte loads); windows touching the last row of the last frame keep the byte loads
-// (an aligned word may reach up to 6 bytes past the bytes needed).
-template <int C, int D, int MINB, bool WIDE = false>
-__global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
+// (Variants that lost on B200 -- crop staged in shared memory with cp.async, row reuse + staged output, aligned 32-bit tap loads,
+// one CTA per frame -- are documented with their measurements in DESIGN.md section 8 and live in the git history of round 1.)
+template <int C, int D>
+__global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride, const int32_t* __restrict__ frame_offsets, int nframes) {
+    uint8_t* __restrict__ windows, int out_stride) {
     __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    // one window per warp; the grid normally covers all windows (one trip), a smaller grid makes the warps persistent
-    // (host-memory frames: the kernel is PCIe-bound and should leave the SMs to the other stream's kernels)
-    // With frame_offsets (CSR of the windows per frame) a CTA takes whole FRAMES: the windows of one frame overlap heavily
-    // (nested / jittered MSER boxes), so their source bytes are fetched once into this SM's L1 instead of once per SM.
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, w_end = n, w_step = nwarps, f = blockIdx.x;
-    if (frame_offsets) {
-        if (f >= nframes) return;
-        w = frame_offsets[f] + (threadIdx.x >> 5); w_end = min(frame_offsets[f + 1], n); w_step = blockDim.x >> 5;
-    }
-    for (;; w += w_step) {
-    if (w >= w_end) {
-        if (!frame_offsets) break;
-        f += gridDim.x;
-        if (f >= nframes) break;
-        w = frame_offsets[f] + (threadIdx.x >> 5) - w_step; w_end = min(frame_offsets[f + 1], n);
-        continue;
-    }
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {     // (the grid normally covers all windows: one trip)
     const int4 c = coords[w];
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
-    if (cw <= 0 || ch <= 0) continue;
+    if (cw <= 0 || ch <= 0) {                                // empty crop (cv2.resize would raise; K1 never emits one): a defined, all-zero window
+        for (int i = lane; i < out_stride; i += 32) windows[(int64_t)w * out_stride + i] = 0;
+        continue;
+    }
     const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
     uint8_t* __restrict__ dst = windows + (int64_t)w * out_stride + lane * C;
     if (D * D * C + lane < out_stride) windows[(int64_t)w * out_stride + D * D * C + lane] = 0;    // zero pad (< 16 bytes)
@@ -351,35 +342,6 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     __syncwarp();                                            // (the previous window's rows are consumed)
     s_y[wl][lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
     __syncwarp();
-    if (WIDE && C == 3 && !(win_frame[w] == nframes - 1 && cy + ch == H)) {
-        const unsigned o = (unsigned)(reinterpret_cast<uintptr_t>(px) & 3);
-        const unsigned o8 = o * 8;
-        const uint8_t* pa = px - o;
-        const bool third = o == 3;                           // bytes o .. o+5 of the aligned words: a third word only from offset 3
-#pragma unroll kK2Unroll
-        for (int dy = 0; dy < D; dy++) {
-            const int4 yc = s_y[wl][dy];
-            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(pa + (int64_t)yc.x * row_stride);
-            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(pa + (int64_t)yc.y * row_stride);
-            const uint32_t a0 = __ldg(q0), a1 = __ldg(q0 + 1), a2 = third ? __ldg(q0 + 2) : 0u;
-            const uint32_t c0 = __ldg(q1), c1 = __ldg(q1 + 1), c2 = third ? __ldg(q1 + 2) : 0u;
-            const uint32_t lo0 = __funnelshift_r(a0, a1, o8), hi0 = __funnelshift_r(a1, a2, o8);      // bytes 0-3 / 4-7 from the tap
-            const uint32_t lo1 = __funnelshift_r(c0, c1, o8), hi1 = __funnelshift_r(c1, c2, o8);
-            const int t00 = (int)(lo0 & 255u) * xa0 + (int)(lo0 >> 24) * xa1;
-            const int t01 = (int)((lo0 >> 8) & 255u) * xa0 + (int)(hi0 & 255u) * xa1;
-            const int t02 = (int)((lo0 >> 16) & 255u) * xa0 + (int)((hi0 >> 8) & 255u) * xa1;
-            const int t10 = (int)(lo1 & 255u) * xa0 + (int)(lo1 >> 24) * xa1;
-            const int t11 = (int)((lo1 >> 8) & 255u) * xa0 + (int)(hi1 & 255u) * xa1;
-            const int t12 = (int)((lo1 >> 16) & 255u) * xa0 + (int)((hi1 >> 8) & 255u) * xa1;
-            const int b0 = yc.z, b1 = yc.w;
-            if (act) {
-                dst[dy * D * C] = (uint8_t)((((b0 * (t00 >> 4)) >> 16) + ((b1 * (t10 >> 4)) >> 16) + 2) >> 2);
-                dst[dy * D * C + 1] = (uint8_t)((((b0 * (t01 >> 4)) >> 16) + ((b1 * (t11 >> 4)) >> 16) + 2) >> 2);
-                dst[dy * D * C + 2] = (uint8_t)((((b0 * (t02 >> 4)) >> 16) + ((b1 * (t12 >> 4)) >> 16) + 2) >> 2);
-            }
-        }
-        continue;
-    }
 #pragma unroll kK2Unroll
     for (int dy = 0; dy < D; dy++) {
         const int4 yc = s_y[wl][dy];
@@ -401,270 +363,6 @@ __global__ void __launch_bounds__(128, MINB) k2_crop_resize_v2_kernel(
     }
 }
 
-// K2 v4: v2 (direct gather through L1) + two cheap savings: (1) the horizontal pass of a source row is reused by the next
-// destination row when both touch it (for the typical 1.4x down-scale that removes 28 % of the byte loads and multiplies),
-// (2) the destination window is assembled in shared memory and leaves as 128-bit stores (zero pad included).
-template <int C, int D>
-__global__ void __launch_bounds__(128) k2_crop_resize_v4_kernel(
-    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride) {
-    constexpr int OUTB = (D * D * C + 15) & ~15;
-    __shared__ __align__(16) uint8_t s_out[4][OUTB];
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int w = blockIdx.x * 4 + wl;
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    if (w >= n) return;
-    const int4 c = coords[w];
-    const int cx = min(c.x, W), cy = min(c.y, H);
-    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
-    if (cw <= 0 || ch <= 0) return;
-    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
-    uint8_t* __restrict__ gout = windows + (int64_t)w * out_stride;
-    uint8_t* so = s_out[wl];
-    const bool act = lane < D;
-    const int li = act ? lane : 0;
-    if (lane < OUTB - D * D * C) so[D * D * C + lane] = 0;   // zero pad of the internal layout
-    uint8_t* sp = so + li * C;
-    if (cw == D && ch == D) {                               // same size: copy
-        const uint8_t* p = src + li * C;
-#pragma unroll 5
-        for (int dy = 0; dy < D; dy++) {
-#pragma unroll
-            for (int k = 0; k < C; k++) { const uint8_t v = __ldg(p + (int64_t)dy * row_stride + k); if (act) sp[dy * D * C + k] = v; }
-        }
-    } else if (cw == 2 * D && ch == 2 * D) {                // INTER_AREA 2x2 fast path
-        const uint8_t* p = src + 2 * li * C;
-#pragma unroll 5
-        for (int dy = 0; dy < D; dy++) {
-            const uint8_t* q0 = p + (int64_t)(2 * dy) * row_stride;
-            const uint8_t* q1 = q0 + row_stride;
-#pragma unroll
-            for (int k = 0; k < C; k++) {
-                const int v = (__ldg(q0 + k) + __ldg(q0 + C + k) + __ldg(q1 + k) + __ldg(q1 + C + k) + 2) >> 2;
-                if (act) sp[dy * D * C + k] = (uint8_t)v;
-            }
-        }
-    } else {
-        // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
-        int xs0, xd1, xa0, xa1, yr0, yr1, yb0, yb1;
-        {
-            const double scale = 1.0 / ((double)D / (double)cw);
-            float f = (float)(((double)li + 0.5) * scale - 0.5);
-            int s = (int)floorf(f); f -= (float)s;
-            if (s < 0) { f = 0.f; s = 0; }
-            if (s >= cw - 1) { f = 0.f; s = cw - 1; }
-            xs0 = s * C;
-            xd1 = (min(s + 1, cw - 1) - s) * C;
-            xa0 = __float2int_rn((1.f - f) * 2048.f);
-            xa1 = __float2int_rn(f * 2048.f);
-        }
-        {
-            const double scale = 1.0 / ((double)D / (double)ch);
-            float f = (float)(((double)li + 0.5) * scale - 0.5);
-            int s = (int)floorf(f); f -= (float)s;
-            yr0 = min(max(s, 0), ch - 1);
-            yr1 = min(max(s + 1, 0), ch - 1);
-            yb0 = __float2int_rn((1.f - f) * 2048.f);
-            yb1 = __float2int_rn(f * 2048.f);
-        }
-        const uint8_t* px = src + xs0;
-        int prev_r1 = -1;
-        int T1p[C];
-#pragma unroll
-        for (int k = 0; k < C; k++) T1p[k] = 0;
-#pragma unroll 5
-        for (int dy = 0; dy < D; dy++) {
-            const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
-            const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
-            int T0[C], T1[C];
-            if (r0 == prev_r1) {                            // warp-uniform: row r0 was this lane's lower row one step ago
-#pragma unroll
-                for (int k = 0; k < C; k++) T0[k] = T1p[k];
-            } else {
-                const uint8_t* p0 = px + (int64_t)r0 * row_stride;
-#pragma unroll
-                for (int k = 0; k < C; k++) T0[k] = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
-            }
-            if (r1 == r0) {
-#pragma unroll
-                for (int k = 0; k < C; k++) T1[k] = T0[k];
-            } else {
-                const uint8_t* p1 = px + (int64_t)r1 * row_stride;
-#pragma unroll
-                for (int k = 0; k < C; k++) T1[k] = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
-            }
-            prev_r1 = r1;
-#pragma unroll
-            for (int k = 0; k < C; k++) {
-                T1p[k] = T1[k];
-                const int v = (((b0 * (T0[k] >> 4)) >> 16) + ((b1 * (T1[k] >> 4)) >> 16) + 2) >> 2;
-                if (act) sp[dy * D * C + k] = (uint8_t)v;
-            }
-        }
-    }
-    __syncwarp();
-    if (out_stride == OUTB) {                               // internal layout: 128-bit stores
-        const uint4* s4 = reinterpret_cast<const uint4*>(so);
-        uint4* g4 = reinterpret_cast<uint4*>(gout);
-        for (int i = lane; i < OUTB / 16; i += 32) g4[i] = s4[i];
-    } else {                                                // packed public layout
-        for (int i = lane; i < D * D * C; i += 32) gout[i] = so[i];
-    }
-}
-
-// K2 v3: the crop is first STAGED in shared memory with 128-bit cp.async loads (only the rows the resize touches, whole
-// row segments, 16-byte aligned chunks), then every tap is a shared-memory byte read.  v2 was bound by the LSU issue rate of
-// its 12 global byte loads per output pixel row; here the global side moves 16 bytes per load and the horizontal pass of a
-// source row is reused by the next destination row when both touch it.  The destination rows are processed in two halves so
-// that the staging buffer holds at most D+3 source rows (shared memory per warp stays under 8 KB -> 28 warps per SM).
-// The output window is assembled in shared memory and written with 128-bit stores (zero pad included).  Needs
-// row_stride % 16 == 0, W*C % 16 == 0 and a 16-byte aligned frame base (host checks, else v2); crops wider than kK2Pitch
-// bytes per row take the direct-gather path of v2 inside this kernel (same arithmetic).
-constexpr int kK2Pitch = 208;                         // staged bytes per row (crop width * C + alignment slack)
-constexpr int kK2Warps = 4;
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int C, int D>
-__global__ void __launch_bounds__(kK2Warps * 32) k2_crop_resize_v3_kernel(
-    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride) {
-    constexpr int HALF = (D + 1) / 2;
-    constexpr int MAXSLOT = 2 * HALF + 2;
-    constexpr int OUTB = (D * D * C + 15) & ~15;
-    __shared__ __align__(16) uint8_t s_reg[kK2Warps][MAXSLOT * kK2Pitch];
-    __shared__ __align__(16) uint8_t s_out[kK2Warps][OUTB];
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int w = blockIdx.x * kK2Warps + wl;
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    if (w >= n) return;
-    const int4 c = coords[w];
-    const int cx = min(c.x, W), cy = min(c.y, H);
-    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
-    if (cw <= 0 || ch <= 0) return;
-    const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
-    uint8_t* __restrict__ gout = windows + (int64_t)w * out_stride;
-    const bool act = lane < D;
-    const int li = act ? lane : 0;
-    const bool same = cw == D && ch == D, area = cw == 2 * D && ch == 2 * D;
-    // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
-    int xs0 = li * C, xd1 = 0, xa0 = 2048, xa1 = 0, yr0 = li, yr1 = li, yb0 = 2048, yb1 = 0;
-    if (area) { xs0 = 2 * li * C; xd1 = C; xa1 = 2048; yr0 = 2 * li; yr1 = 2 * li + 1; }
-    else if (!same) {
-        {
-            const double scale = 1.0 / ((double)D / (double)cw);
-            float f = (float)(((double)li + 0.5) * scale - 0.5);
-            int s = (int)floorf(f); f -= (float)s;
-            if (s < 0) { f = 0.f; s = 0; }
-            if (s >= cw - 1) { f = 0.f; s = cw - 1; }
-            xs0 = s * C;
-            xd1 = (min(s + 1, cw - 1) - s) * C;
-            xa0 = __float2int_rn((1.f - f) * 2048.f);
-            xa1 = __float2int_rn(f * 2048.f);
-        }
-        {
-            const double scale = 1.0 / ((double)D / (double)ch);
-            float f = (float)(((double)li + 0.5) * scale - 0.5);
-            int s = (int)floorf(f); f -= (float)s;
-            yr0 = min(max(s, 0), ch - 1);
-            yr1 = min(max(s + 1, 0), ch - 1);
-            yb0 = __float2int_rn((1.f - f) * 2048.f);
-            yb1 = __float2int_rn(f * 2048.f);
-        }
-    }
-    const int o = (int)((uintptr_t)src & 15);               // same for every row: row_stride % 16 == 0
-    const bool staged = o + cw * C <= kK2Pitch;
-    const int cpr = (o + cw * C + 15) >> 4;                  // 16-byte chunks per staged row
-    uint8_t* reg = s_reg[wl];
-    uint8_t* so = s_out[wl];
-    if (lane < OUTB - D * D * C) so[D * D * C + lane] = 0;   // zero pad of the internal layout
-    const uint8_t* sx = reg + o + xs0;
-    const uint8_t* gx = src + xs0;
-    int prev_r1 = -1;
-    int T1p[C];
-#pragma unroll
-    for (int k = 0; k < C; k++) T1p[k] = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        const int dy0 = half * HALF, dy1 = half ? D : HALF;
-        const int rfirst = __shfl_sync(0xffffffffu, yr0, dy0), rlast = __shfl_sync(0xffffffffu, yr1, dy1 - 1);
-        const bool dense_rows = rlast - rfirst + 1 <= MAXSLOT;   // slot = row - rfirst ; else slot = 2*(dy-dy0) (+1)
-        if (staged) {
-            __syncwarp();                                    // the previous half's taps are done
-            const int nslots = dense_rows ? rlast - rfirst + 1 : 2 * (dy1 - dy0);
-            const int total = nslots * cpr;
-            const uint8_t* g0 = src - o;
-            for (int i0 = 0; i0 < total; i0 += 32) {         // uniform trip count: every lane takes part in the shuffles
-                const int i = i0 + lane;
-                const bool ok = i < total;
-                const int sl = ok ? i / cpr : 0, ck = i - sl * cpr;
-                const int ra = __shfl_sync(0xffffffffu, yr0, (dy0 + (sl >> 1)) & 31), rb = __shfl_sync(0xffffffffu, yr1, (dy0 + (sl >> 1)) & 31);
-                const int row = dense_rows ? rfirst + sl : ((sl & 1) ? rb : ra);
-                if (ok) cp_async16(reg + sl * kK2Pitch + ck * 16, g0 + (int64_t)row * row_stride + ck * 16);
-            }
-            cp_async_wait_all();
-            __syncwarp();
-        }
-        for (int dy = dy0; dy < dy1; dy++) {
-            const int r0 = __shfl_sync(0xffffffffu, yr0, dy), r1 = __shfl_sync(0xffffffffu, yr1, dy);
-            const int b0 = __shfl_sync(0xffffffffu, yb0, dy), b1 = __shfl_sync(0xffffffffu, yb1, dy);
-            int T0[C], T1[C];
-            if (staged) {
-                const int s0 = dense_rows ? r0 - rfirst : 2 * (dy - dy0), s1 = dense_rows ? r1 - rfirst : 2 * (dy - dy0) + 1;
-                if (r0 == prev_r1) {
-#pragma unroll
-                    for (int k = 0; k < C; k++) T0[k] = T1p[k];
-                } else {
-                    const uint8_t* p = sx + s0 * kK2Pitch;
-#pragma unroll
-                    for (int k = 0; k < C; k++) T0[k] = p[k] * xa0 + p[xd1 + k] * xa1;
-                }
-                if (r1 == r0) {
-#pragma unroll
-                    for (int k = 0; k < C; k++) T1[k] = T0[k];
-                } else {
-                    const uint8_t* p = sx + s1 * kK2Pitch;
-#pragma unroll
-                    for (int k = 0; k < C; k++) T1[k] = p[k] * xa0 + p[xd1 + k] * xa1;
-                }
-            } else {
-                const uint8_t* p0 = gx + (int64_t)r0 * row_stride;
-                const uint8_t* p1 = gx + (int64_t)r1 * row_stride;
-#pragma unroll
-                for (int k = 0; k < C; k++) {
-                    T0[k] = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
-                    T1[k] = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
-                }
-            }
-            prev_r1 = r1;
-#pragma unroll
-            for (int k = 0; k < C; k++) {
-                T1p[k] = T1[k];
-                int v;
-                if (same) v = T0[k] >> 11;                                     // copy: p * 2048 >> 11
-                else if (area) v = (((T0[k] + T1[k]) >> 11) + 2) >> 2;         // (s00+s01+s10+s11+2)>>2, all four weights 2048
-                else v = (((b0 * (T0[k] >> 4)) >> 16) + ((b1 * (T1[k] >> 4)) >> 16) + 2) >> 2;
-                if (act) so[(dy * D + lane) * C + k] = (uint8_t)v;
-            }
-        }
-    }
-    __syncwarp();
-    // 128-bit stores of the assembled window (internal layout) or byte stores (packed public layout)
-    if (out_stride == OUTB) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(so);
-        uint4* g4 = reinterpret_cast<uint4*>(gout);
-        for (int i = lane; i < OUTB / 16; i += 32) g4[i] = s4[i];
-    } else {
-        for (int i = lane; i < D * D * C; i += 32) gout[i] = so[i];
-    }
-}
-
 // =====================================================================================================
 // K3  getColorMaskRedOrBlue(img,'r'/'b')  (DET:63-89), SURVEY A.3.  One thread per pixel; integer HSV tables.
 // `slots` (optional) = indirection to the surviving windows inside the work buffer.
@@ -672,7 +370,7 @@ __global__ void __launch_bounds__(kK2Warps * 32) k2_crop_resize_v3_kernel(
 // K3 v2: one warp per window, lane-strided pixels (coalesced byte loads, stride 3), mask bytes written with stride `ms`
 // (npx for the public packed layout, padded to 16 for the internal one) and, optionally, the same masks bit-packed
 // (pixel p -> word p>>5, bit p&31; [w][0..NW) red, [w][NW..2NW) blue) which is what K4 consumes inside the chain.
-__global__ void __launch_bounds__(256) k3_masks_v2_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
+__global__ void __launch_bounds__(256) k3_masks_generic_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ slots,
                                                           const int32_t* __restrict__ n_ptr, int n_max, int npx, int ws,
                                                           const Tables* __restrict__ tab, HsvBounds hb, uint8_t* __restrict__ red,
                                                           uint8_t* __restrict__ blue, int ms, uint32_t* __restrict__ bits) {

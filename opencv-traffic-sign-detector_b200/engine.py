@@ -307,6 +307,12 @@ class Context:
         check(self._L.tsd_stat_hist_entries(self._h, C.byref(t)))
         return int(t.value)
 
+    def stat_unsure_pairs(self, reset=False):
+        """Pairs decided by the exact float64 compareHist evaluation (within 2e-6 of a threshold) since process start / the last reset."""
+        t = C.c_int64()
+        check(self._L.tsd_stat_unsure_pairs(self._h, C.byref(t), int(bool(reset))))
+        return int(t.value)
+
     def preprocess(self, frames, clip_limit=2.0, tiles=(8, 8), gamma=2):
         """grayAndEnhanceContrast (DET:135-152) for a batch: BGR2GRAY -> CLAHE -> GaussianBlur 3x3 -> gamma LUT.
         frames uint8 [F,H,W,3] or [H,W,3] -> uint8 [F,H,W] (or [H,W])."""

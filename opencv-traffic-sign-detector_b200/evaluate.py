@@ -8,6 +8,7 @@
     plotting / image display of the script is not mirrored.
 """
 import csv
+import os
 
 import numpy as np
 
@@ -20,9 +21,10 @@ _ctx = None
 
 
 def context():
+    """Process-wide context of the evaluators on cuda:0 (or $TSD_DEVICE, like source_det / source_rec)."""
     global _ctx
     if _ctx is None:
-        _ctx = engine.Context(0, "det")
+        _ctx = engine.Context(device=int(os.environ.get("TSD_DEVICE", "0")), flavour="det")
     return _ctx
 
 

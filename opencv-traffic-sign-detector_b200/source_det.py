@@ -132,7 +132,12 @@ def cleanDuplicatedDetections(imageDetections, isSimilarityByEuclideanDistanceON
     wins = np.stack([np.asarray(i[0], np.uint8) for i in items])
     coords = np.array([i[1] for i in items], np.int32)
     ow, oc, _ = context().dedup(wins, coords, np.array([0, len(items)], np.int32), isSimilarityByEuclideanDistanceON, tolerance)
-    tail = tuple(items[0][2:])      # file (and label): identical for every item of a frame (DET:219-221 keeps detection[2])
+    # A survivor keeps its own (file[, label]); a merged one takes them from the absorbing (incoming) item (DET:219-221).  The
+    # reference only ever calls this with one frame's list, where every tail is the same -- anything else is refused rather
+    # than answered with the wrong tail.
+    tail = tuple(items[0][2:])
+    if any(tuple(i[2:]) != tail for i in items):
+        raise ValueError("cleanDuplicatedDetections: items of one call must share (file[, label]) -- one frame's list per call")
     return [(ow[i], tuple(int(v) for v in oc[i])) + tail for i in range(len(oc))]
 
 

@@ -51,6 +51,40 @@ def det_windows50():
 
 
 @pytest.fixture(scope="session")
+def det_full150():
+    """Every stage output of the reference for ALL 150 test frames (tests/golden/make_golden.py full)."""
+    return np.load(os.path.join(GOLDEN, "det_full150.npz"))
+
+
+@pytest.fixture(scope="session")
+def resultado150():
+    """The reference's resultado.txt for the 150 test frames, sorted file order (192 lines)."""
+    return open(os.path.join(GOLDEN, "det_resultado150.txt")).read().split()
+
+
+@pytest.fixture(scope="session")
+def jpeg24():
+    """24 real test frames stored as their original JPEG bytes -> dict(index int32[24] into the 150 sorted files, files, frames
+    uint8 [24,800,1360,3]).  The pixels must be the ones the reference decoded when the goldens were made (sha1 stored beside the
+    bytes); a cv2 build that decodes differently cannot check K2 on these frames and skips."""
+    import hashlib
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(os.path.join(GOLDEN, "det_jpeg24.npz"))
+    frames = []
+    for i in range(len(g["index"])):
+        img = cv2.imdecode(g["jpeg"][g["jpeg_offsets"][i]:g["jpeg_offsets"][i + 1]], cv2.IMREAD_COLOR)
+        if hashlib.sha1(img.tobytes()).digest() != g["sha1"][i].tobytes():
+            pytest.skip("this cv2 build decodes %s differently from the container the goldens were made in" % g["files"][i])
+        frames.append(img)
+    return dict(index=g["index"], files=[str(f) for f in g["files"]], frames=np.stack(frames))
+
+
+@pytest.fixture(scope="session")
+def rec_gray_golden():
+    return np.load(os.path.join(GOLDEN, "rec_gray_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def rec_golden():
     return np.load(os.path.join(GOLDEN, "rec_golden.npz"))
 

@@ -6,6 +6,8 @@ consumes the committed fixtures.  Usage:
     python tests/golden/make_golden.py det      # detection goldens (about 1 min)
     python tests/golden/make_golden.py rec      # recognition goldens (needs MSERTrain.val: about 7 min first time)
     python tests/golden/make_golden.py crops    # inputs of calculateMeanMasks (class crops, reference order)
+    python tests/golden/make_golden.py full     # full-dataset KAT: all 150 frames + 24 frames as JPEG bytes (about 1 min)
+    python tests/golden/make_golden.py gray     # GRAY descriptor classifiers (needs MSERTrain.val like rec)
 
 Everything stored here is an output of the reference's own functions (DET/source.py, REC/source.py)
 called through tests/golden/refload.py; the oracle (oracle/) is NOT involved in producing them.
@@ -22,6 +24,11 @@ Files written
   det_pre.npz              sha1 + a 64x128 crop of grayAndEnhanceContrast's output for the three stored frames
   det_crops.npz            the 708 class crops calculateMeanMasks reads (decoded BGR), in the reference's iteration order
   rec_frames.npz           recognition-flavour (x1.15, 32x32) window extraction for the stored frames
+  det_full150.npz          ALL 150 test frames (sorted): MSER boxes, K1 coords, post-resize windows (input of the fold), survivors of
+                           both de-duplication passes, final detection tuples (= det_resultado150.txt line by line)
+  det_jpeg24.npz           24 of those frames as their original JPEG bytes (+ sha1 of the pixels cv2.imread decodes here), chosen
+                           for the most windows / detections: K2 runs on real pixels for them
+  rec_gray_golden.npz      GRAY descriptor branch (REC/source.py:520-521): 1024-feature LDA / KNN weights, logits, labels
 """
 import hashlib
 import os
@@ -123,6 +130,74 @@ def make_det():
     print("stage counts raw/aspect/survivors/detections:", stage.tolist(), "lines", len(lines), "sha1(sorted)", sha)
 
 
+def make_full(n_jpeg=24):
+    """Full-dataset known-answer test (BASELINE north_star: bit-exact detections on test_alumnos_jpg): every stage output of the
+    reference's own functions for ALL 150 frames, in sorted file order.  The lines must equal det_resultado150.txt (asserted)."""
+    src, const = refload.load_det()
+    _silence_tqdm(src)
+    const.TRAIN_PATH = os.path.join(refload.DET_DIR, "train_jpg")
+    const.TEST_PATH = os.path.join(refload.DET_DIR, "test_alumnos_jpg")
+    red, blue = src.calculateMeanMasks()
+    g = np.load(os.path.join(HERE, "det_templates.npz"))
+    assert np.array_equal(np.stack([m for m, _ in red]), g["red6"]) and np.array_equal(np.stack([m for m, _ in blue]), g["blue6"])
+    mser = cv2.MSER_create(delta=7, min_area=200, max_area=2000, max_variation=0.15)
+    files = sorted(f for f in os.listdir(const.TEST_PATH) if f.endswith(".jpg"))
+    A = dict(boxes=[], box_offsets=[0], valid=[], coords_all=[], windows=[], coords=[], offsets=[0], p1_offsets=[0], p1_coords=[],
+             surv_offsets=[0], surv_windows=[], surv_coords=[], det_offsets=[0], det_coords=[], det_ids=[], det_scores=[])
+    lines, per_frame = [], []
+    for f in files:
+        img = cv2.imread(os.path.join(const.TEST_PATH, f))
+        boxes = np.asarray(mser.detectRegions(src.grayAndEnhanceContrast(img))[1], np.int32).reshape(-1, 4)
+        coords = [src.makeWindowBiggerOrDiscardFakeDetections(b, 1.30) for b in boxes]
+        items = [(cv2.resize(src.cropImageByCoords(c, img), (25, 25)), c, f) for c in coords if c is not None]
+        p1 = src.cleanDuplicatedDetections(list(items), False, 0.85)
+        p2 = src.cleanDuplicatedDetections(list(p1), True, 0.95)
+        dets = [src.detectionsMaskCorrelation(d, red, blue, 0.55) for d in p2]
+        dets = [d for d in dets if d is not None]
+        lines.extend(src.createDetectionsStrings(dets))
+        A["boxes"].append(boxes); A["box_offsets"].append(A["box_offsets"][-1] + len(boxes))
+        A["valid"].extend(c is not None for c in coords)
+        A["coords_all"].extend(c if c is not None else (0, 0, 0, 0) for c in coords)
+        A["windows"].extend(i[0] for i in items); A["coords"].extend(i[1] for i in items)
+        A["offsets"].append(A["offsets"][-1] + len(items))
+        A["p1_coords"].extend(i[1] for i in p1); A["p1_offsets"].append(A["p1_offsets"][-1] + len(p1))
+        A["surv_windows"].extend(i[0] for i in p2); A["surv_coords"].extend(i[1] for i in p2)
+        A["surv_offsets"].append(A["surv_offsets"][-1] + len(p2))
+        A["det_coords"].extend(d[1:5] for d in dets); A["det_ids"].extend(d[5] for d in dets)
+        A["det_scores"].extend(d[6] for d in dets); A["det_offsets"].append(A["det_offsets"][-1] + len(dets))
+        per_frame.append((len(items), len(dets)))
+    stored = open(os.path.join(HERE, "det_resultado150.txt")).read().split()
+    assert [ln.strip() for ln in lines] == stored, "the reference no longer reproduces det_resultado150.txt"
+    np.savez_compressed(
+        os.path.join(HERE, "det_full150.npz"), files=np.array(files), boxes=np.concatenate(A["boxes"]).astype(np.int32),
+        box_offsets=np.array(A["box_offsets"], np.int32), valid=np.array(A["valid"], bool),
+        coords_all=np.array(A["coords_all"], np.int32).reshape(-1, 4), offsets=np.array(A["offsets"], np.int32),
+        windows=np.stack(A["windows"]), coords=np.array(A["coords"], np.int32), p1_offsets=np.array(A["p1_offsets"], np.int32),
+        p1_coords=np.array(A["p1_coords"], np.int32), surv_offsets=np.array(A["surv_offsets"], np.int32),
+        surv_windows=np.stack(A["surv_windows"]), surv_coords=np.array(A["surv_coords"], np.int32),
+        det_offsets=np.array(A["det_offsets"], np.int32), det_coords=np.array(A["det_coords"], np.int32).reshape(-1, 4),
+        det_ids=np.array(A["det_ids"], np.int32), det_scores=np.array(A["det_scores"], np.float64))
+    # frames stored as image bytes: half by detections, half by windows (the heaviest real cases of K2 / K5 / K3+K4)
+    by_det = sorted(range(len(files)), key=lambda i: (-per_frame[i][1], -per_frame[i][0]))
+    by_win = sorted(range(len(files)), key=lambda i: (-per_frame[i][0], -per_frame[i][1]))
+    pick = []
+    for a, b in zip(by_det, by_win):
+        for i in (a, b):
+            if i not in pick and len(pick) < n_jpeg:
+                pick.append(i)
+    pick.sort()
+    blobs, sha = [], []
+    for i in pick:
+        raw = open(os.path.join(const.TEST_PATH, files[i]), "rb").read()
+        img = cv2.imread(os.path.join(const.TEST_PATH, files[i]))
+        assert np.array_equal(cv2.imdecode(np.frombuffer(raw, np.uint8), cv2.IMREAD_COLOR), img)
+        blobs.append(np.frombuffer(raw, np.uint8)); sha.append(np.frombuffer(hashlib.sha1(img.tobytes()).digest(), np.uint8))
+    np.savez(os.path.join(HERE, "det_jpeg24.npz"), index=np.array(pick, np.int32), files=np.array([files[i] for i in pick]),
+             jpeg=np.concatenate(blobs), jpeg_offsets=np.cumsum([0] + [len(b) for b in blobs]).astype(np.int64), sha1=np.stack(sha))
+    print("det_full150.npz: boxes", A["box_offsets"][-1], "windows", A["offsets"][-1], "survivors", A["surv_offsets"][-1], "detections",
+          A["det_offsets"][-1], "| jpeg frames", len(pick), "windows", sum(per_frame[i][0] for i in pick), "detections", sum(per_frame[i][1] for i in pick))
+
+
 def make_rec(workdir="/tmp/o_rec"):
     src, const = refload.load_rec()
     _silence_tqdm(src)
@@ -184,6 +259,48 @@ def make_rec(workdir="/tmp/o_rec"):
             fr[k + "_hog"] = np.stack([desc[0].compute(g) for g in fr[k + "_gray"]])
             fr[k + "_pred_lda"] = np.array(src.predictProbability(cl, None, [(h, None, None, 0) for h in fr[k + "_hog"]], 0.5)[0], np.int32)
         np.savez_compressed(os.path.join(HERE, "rec_frames.npz"), **fr)
+    finally:
+        os.chdir(cwd)
+
+
+def make_gray(workdir="/tmp/o_rec"):
+    """GRAY_LDA_LDABAYES and GRAY_LDA_KNN (REC/constants.py:10-12; REC/source.py:520-521 image.ravel()): same seeds, same split and
+    same shuffle as make_rec -- asserted against rec_golden.npz's grey windows -- with the 1024-byte raw-pixel descriptor."""
+    src, const = refload.load_rec()
+    _silence_tqdm(src)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        random.seed(0); np.random.seed(0)
+        const.TRAIN_PATH = "train_jpg"; const.TRAIN_PATH_REAL_RESULTS = "train_jpg/gt.txt"
+        mser = src.initializeMSER((7, 200, 2000, 1.0))
+        desc = src.initializeFeatureDescriptor("GRAY")
+        data, imgs = src.loadTrainData(mser)
+        tr, te = src.extractEvaluationTestResults(data, 0.1)
+        trd, ted = src.calculateDescriptors(tr, desc), src.calculateDescriptors(te, desc)
+        cl = src.createClassifiers("LDABAYES")
+        src.fitClassifiers(cl, "LDA", trd)
+        flat = src.flatData(list(ted.values())); random.shuffle(flat)
+        X = np.stack([d[0] for d in flat])                                               # uint8 [n,1024]
+        ref = np.load(os.path.join(HERE, "rec_golden.npz"))
+        assert np.array_equal(X.reshape(-1, 32, 32), ref["gray"]), "split / shuffle differs from make_rec"
+        pred, true = src.predictProbability(cl, None, flat, 0.5)
+        assert np.array_equal(np.array(true, np.int32), ref["true"])
+        W = np.stack([c.coef_[0] for c in cl[0]], 1)                                      # [1024,6] f64
+        b = np.array([c.intercept_[0] for c in cl[0]])
+        logits = np.stack([c.decision_function([d[0] for d in flat]) for c in cl[0]], 1)
+        proba1 = np.stack([c.predict_proba([d[0] for d in flat])[:, 1] for c in cl[0]], 1)
+        random.seed(0); np.random.seed(0)
+        clk = src.createClassifiers("KNN")
+        reducer, Z, tags = src.fitClassifiers(clk, "LDA", trd)
+        predk, truek = src.predictProbability(clk, reducer, flat, 0.5)
+        Zq = reducer[0].transform([d[0] for d in flat])
+        np.savez_compressed(
+            os.path.join(HERE, "rec_gray_golden.npz"), lda_W=W, lda_b=b, logits=logits, proba1=proba1, pred_lda=np.array(pred, np.int32),
+            knn_xbar=reducer[0].xbar_, knn_scalings=reducer[0].scalings_[:, :6], knn_Ztrain=np.asarray(Z, np.float64),
+            knn_ytrain=np.array(tags, np.int32), knn_Zq=Zq, pred_knn=np.array(list(predk), np.int32))
+        print("gray: n =", len(flat), "acc lda", np.mean(np.array(pred) == np.array(true)), "acc knn",
+              np.mean(np.array(list(predk)) == np.array(true)), "min |logit|", np.abs(logits).min())
     finally:
         os.chdir(cwd)
 
@@ -284,6 +401,12 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "det"
     if what == "eval":
         make_eval()
+        sys.exit(0)
+    if what == "full":
+        make_full()
+        sys.exit(0)
+    if what == "gray":
+        make_gray()
         sys.exit(0)
     if what == "pre":
         make_pre()

@@ -49,30 +49,6 @@ def test_k2_resize_sweep(ctx_det, ctx_rec, oracle):
             assert np.array_equal(got1[i], oracle.crop_resize(gray[f], c, D)), (D, c, "grey")
 
 
-@pytest.mark.parametrize("variant", ["v3", "v4", "v5"])
-def test_k2_experimental_variants_bit_identical(tsd, templates, monkeypatch, variant):
-    """The resize kernels kept for A/B measurements (TSD_K2=v3: crop staged in shared memory by cp.async; v4: row reuse +
-    staged output) must give exactly the default kernel's windows and detections: compared on the whole chain of 6 frames
-    (the chain is where the internal 16-byte layout, which v3/v4 need, is used) and on a 640-px-wide sweep."""
-    red6, blue6 = templates
-    frames = tsd.synth.make_frames(6)
-    boxes, off = tsd.synth.make_boxes(6, 200)
-    rng = np.random.default_rng(9)
-    sweep = rng.integers(0, 256, (1, 416, 640, 3), dtype=np.uint8)
-    coords = np.array([(x0, y0, x0 + w, y0 + h) for h in (1, 7, 24, 25, 26, 49, 50, 51, 64, 65, 130, 300)
-                       for w in (1, 13, 25, 50, 63, 64, 65, 69, 70, 200) for x0, y0 in ((0, 0), (5, 3), (640 - min(w, 600), 416 - min(h, 400)))], np.int32)
-    res = {}
-    for v in ("v2", variant):
-        monkeypatch.setenv("TSD_K2", v)
-        with tsd.Context(0, "det") as ctx:
-            ctx.set_templates(red6, blue6)
-            det, counts = ctx.detect_frames(frames, boxes, off)
-            wins, wc, wo = ctx.windows(frames, boxes, off)
-            res[v] = (det, counts, wins, wc, ctx.crop_resize(sweep, coords))
-    for a_, b_ in zip(res["v2"], res[variant]):
-        assert np.array_equal(a_, b_)
-
-
 def test_k2_golden_frames(ctx_det, det_frames, frames3):
     for k in STORED:
         v = det_frames[k + "_valid"]
@@ -546,7 +522,9 @@ def test_k6_k7_k8_recognition_golden(ctx_rec, rec_golden, rec_frames, oracle):
     hog = ctx_rec.hog(g["gray"])
     ref = g["hog"]
     rel = np.abs(hog - ref) / np.maximum(np.abs(ref), 1e-2)
-    assert rel.max() < 1e-4, rel.max()                                   # north_star: HOG within 1e-4 relative
+    assert rel.max() < 1e-4, rel.max()                                   # north_star: HOG within 1e-4 relative (measured: 8e-7)
+    # the same bound WITHOUT the 1e-2 floor: purely relative down to features of 1e-3, plus 1e-7 absolute below that
+    assert np.all(np.abs(hog - ref) <= 1e-4 * np.abs(ref) + 1e-7), float(np.max(np.abs(hog - ref) - 1e-4 * np.abs(ref)))
     assert np.abs(ctx_rec.hog(np.full((1, 32, 32), 9, np.uint8))).max() == 0.0    # constant image -> all zeros, no NaN
     lg, lab = ctx_rec.lda_predict(g["hog"])
     assert np.max(np.abs(lg - g["logits"])) < 1e-9
