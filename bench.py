@@ -32,6 +32,14 @@ UNIQUE_FRAMES = 32
 METRIC = "candidate windows/sec (1360x800 frames, ~200 MSER candidates/frame, detection scoring)"
 
 
+def bench_config(world):
+    """`config` of the JSON line: identical keys and values for both arms (the per-arm batch size is reported beside it)."""
+    return {"workload": "synthetic 1360x800 BGR frames, 200 MSER-like candidates/frame, detection-only scoring (BASELINE configs[2])",
+            "boxes_per_frame": NBOX, "window": D, "frame_bytes": H * W * 3, "parallelism": "frames sharded by image, dp%d" % world,
+            "l2": "inputs larger than L2: every step reads its own batch of distinct resident frames (3.26 MB each, >= 100 MB per step), "
+                  "so no step finds its frames in the 126 MB L2"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -114,23 +122,24 @@ class ClockSampler:
                 "power_w_max": max((p for _, _, p in self.samples), default=None), "reasons": reasons}
 
 
-def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7):
+def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7, enlarge=1.30, D=D, Hf=H, Wf=W, recognize=False):
     """SURVEY.md section 8(d) per-unit figures x the units one launch processes (independent of the implementation).
     K2: in 3*min(w_c,2D)*min(h_c,2D) + out 3*D*D per aspect-passing window; k5_hist: 3*D*D + 16 per window; k5_pairs:
     the sparse histograms + moments + energies read once, bit rows written; k5_fold: in 3*D*D+16 per input window, out
-    3*D*D+16 per survivor; K3: 3*D*D in, bit-packed masks out (160 B); K4: 160 B in, 8 out."""
+    3*D*D+16 per survivor; K3: 3*D*D in, bit-packed masks out (160 B); K4: 160 B in, 8 out; K6: 3*D*D in, D*D out;
+    K7: D*D in, 324 f32 out; K8: 324 f32 in, 6 f64 logits + label out."""
     b = boxes.astype(np.int64)
     w, h = b[:, 2].astype(np.float64), b[:, 3].astype(np.float64)
-    pm1 = 1.30 - 1
+    pm1 = enlarge - 1
     ratio = w / np.maximum(h, 1e-300)
     ok = (0.8 < ratio) & (ratio < 1.20)
     x1 = np.maximum(b[:, 0] - w * pm1 * 0.5, 0).astype(np.int64); y1 = np.maximum(b[:, 1] - h * pm1 * 0.5, 0).astype(np.int64)
     x2 = (b[:, 0] + b[:, 2] + w * pm1 * 0.5).astype(np.int64); y2 = (b[:, 1] + b[:, 3] + h * pm1 * 0.5).astype(np.int64)
-    cw = np.minimum(x2, W) - np.minimum(x1, W); ch = np.minimum(y2, H) - np.minimum(y1, H)
+    cw = np.minimum(x2, Wf) - np.minimum(x1, Wf); ch = np.minimum(y2, Hf) - np.minimum(y1, Hf)
     k2_in = (3 * np.minimum(cw, 2 * D) * np.minimum(ch, 2 * D))[ok].sum()
     npass, nsurv = int(ok.sum()), int(counts[2])
     px = D * D
-    return {
+    alg = {
         "k1_expand_filter": int(len(b) * 33),
         "k2_crop_resize": int(k2_in + npass * 3 * px),
         "k5_hist": int(npass * (3 * px + 16)),
@@ -138,12 +147,15 @@ def algorithmic_bytes(boxes, offsets, counts, hist_entries=0, row_words=7):
         # two bit rows written per window
         "k5_pairs": int(4 * hist_entries + npass * (48 + 100 + 8 * row_words)),
         "k5_fold": int(npass * (3 * px + 16) + nsurv * (3 * px + 16)),
+        "detections": int(counts[3] * 32),
+    }
+    if recognize:
+        alg.update({"k6_gray": int(nsurv * 4 * px), "k7_hog": int(nsurv * (px + 324 * 4)), "k8_lda": int(nsurv * (324 * 4 + 49))})
+    else:
         # inside the chain K3 hands K4 bit-packed masks (2 x 20 words per window); the byte masks of SURVEY's 2*D*D figure are
         # written only by the tsd_color_masks entry point (TSD_KEEP_MASKS=1 restores them in the chain)
-        "k3_masks": int(nsurv * (3 * px + 8 * ((px + 31) // 32))),
-        "k4_score": int(nsurv * (8 * ((px + 31) // 32) + 8)),
-        "detections": int(counts[3] * 32),
-    }, npass
+        alg.update({"k3_masks": int(nsurv * (3 * px + 8 * ((px + 31) // 32))), "k4_score": int(nsurv * (8 * ((px + 31) // 32) + 8))})
+    return alg, npass
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -176,8 +188,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "frames_per_sec": F * args.steps / dt,
-        "config": {"workload": "synthetic 1360x800 BGR frames, 200 MSER-like candidates/frame, detection-only scoring (BASELINE configs[2])",
-                   "frames_per_step": F, "boxes_per_frame": NBOX},
+        "config": bench_config(args.gpus), "frames_per_step": F,
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
                          "sample": "%d frames x %d candidates per step (%d per core), oracle/ref_port.py = reference pipeline with cv2 + its Python loops" % (F, NBOX, fpc)},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,51 +232,136 @@ def _time_steps(torch, stream, ctx, fn, steps=10, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
-def secondary_runs(torch, tsd_b200, dev, local_rank, ctx_det, stream_det):
-    """Two more device-resident measurements, reported beside the headline (not bench lines of their own):
-    (1) the recognition flavour of the chain (K1 K2 K5 K6 K7 K8, x1.15 / 32x32, BASELINE configs[3]) on 1024 synthetic
-        frames with the LDA weights fitted by the reference (tests/golden/rec_golden.npz);
-    (2) the detection chain on REAL frames with REAL cv2.MSER boxes: the three stored test frames and the
-        boxes the reference's MSER produced for them, tiled to 1024 frames."""
-    out = {}
+def _staged(torch, ctx, stream, fn, steps):
+    """Per-stage device times (ms per step) of `steps` enqueues with the library's stage events on (serialised batches)."""
+    ctx.set_profiling(True)
+    for _ in range(steps):
+        fn()
+    ctx.synchronize()
+    st = {k: v / steps for k, v in ctx.stage_times()}
+    ctx.set_profiling(False)
+    return st
+
+
+def recognize_run(torch, tsd_b200, dev, local_rank, rank, world, dist, peak):
+    """BASELINE configs[3]: the detect + recognise chain (K1 K2 K5 K5 K6 K7 K8, x1.15 / 32x32, HOG + 6 LDA in f64) on 1024
+    synthetic frames PER RANK with the LDA weights the reference fitted (tests/golden/rec_golden.npz).  Runs on every rank: the
+    value is the whole job's windows/s over the slowest rank's device time, so the 2/4/8-GPU lines carry detect+recognise."""
     F = 1024
-    try:
-        uniq = tsd_b200.synth.make_frames(16)
-        boxes, off = tsd_b200.synth.make_boxes(F, NBOX)
-        d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(F, device=dev) % 16].contiguous()
-        d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
-        r = np.load(os.path.join(ROOT, "tests", "golden", "rec_golden.npz"))
-        with tsd_b200.Context(device=local_rank, flavour="rec") as rc:
-            rc.set_lda(r["lda_W"], r["lda_b"])
-            st = torch.cuda.ExternalStream(rc.stream, device=dev)
-            ms = _time_steps(torch, st, rc, lambda: rc.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]),
-                                                                      mode=tsd_b200.RUN_RECOGNIZE, max_boxes_per_frame=NBOX))
-            _, cnt = rc.fetch_detections(int(off[-1]))
-        out["recognize_chain"] = {"windows_per_s": F * NBOX / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms, "frames": F,
-                                  "stage_counts": [int(v) for v in cnt], "config": "synthetic 1360x800, 200 candidates/frame, x1.15 / 32x32, HOG + 6 LDA (f64)"}
-        del d_frames
-    except Exception as e:                                   # secondary numbers never break the bench line
-        out["recognize_chain"] = {"error": str(e)[:200]}
-    try:
-        import cv2
-        g = np.load(os.path.join(ROOT, "tests", "golden", "det_frames.npz"))
-        names = ["00604", "00639", "00719"]
-        imgs = np.stack([cv2.imread(os.path.join(ROOT, "tests", "golden", "det_frame_%s.png" % k)) for k in names])
-        bl = [g[k + "_boxes"].astype(np.int32) for k in names]
-        boxes = np.concatenate([bl[f % 3] for f in range(F)])
-        off = np.concatenate([[0], np.cumsum([len(bl[f % 3]) for f in range(F)])]).astype(np.int32)
-        d_frames = torch.from_numpy(imgs).to(dev)[torch.arange(F, device=dev) % 3].contiguous()
-        d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
-        mb = int(max(len(b) for b in bl))
-        ms = _time_steps(torch, stream_det, ctx_det, lambda: ctx_det.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]),
-                                                                                    max_boxes_per_frame=mb))
-        _, cnt = ctx_det.fetch_detections(int(off[-1]))
-        out["real_mser_frames"] = {"windows_per_s": int(off[-1]) / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms, "frames": F,
-                                   "boxes_per_frame_mean": float(off[-1]) / F, "stage_counts": [int(v) for v in cnt],
-                                   "config": "3 real GTSDB test frames + the boxes cv2.MSER(7,200,2000,0.15) gives for them, tiled to 1024 frames"}
-    except Exception as e:
-        out["real_mser_frames"] = {"error": str(e)[:200]}
+    uniq = tsd_b200.synth.make_frames(16, seed=tsd_b200.synth.FRAME_SEED + 500 + rank)
+    boxes, off = tsd_b200.synth.make_boxes(F, NBOX, seed=tsd_b200.synth.BOX_SEED + 500 + rank, enlarge=1.15, D=32)
+    d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(F, device=dev) % 16].contiguous()
+    d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+    r = np.load(os.path.join(ROOT, "tests", "golden", "rec_golden.npz"))
+    with tsd_b200.Context(device=local_rank, flavour="rec") as rc:
+        rc.set_lda(r["lda_W"], r["lda_b"])
+        st = torch.cuda.ExternalStream(rc.stream, device=dev)
+
+        def step():
+            rc.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), mode=tsd_b200.RUN_RECOGNIZE,
+                              max_boxes_per_frame=NBOX)
+        for _ in range(3):
+            step()
+        rc.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10):
+            step()
+        rc.flush()
+        e1.record(st)
+        rc.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        stages = _staged(torch, rc, st, step, 5)
+        _, cnt = rc.fetch_detections(int(off[-1]))
+        nnz = rc.stat_hist_entries()
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    alg, _ = algorithmic_bytes(boxes, off, cnt, nnz, (NBOX + 31) // 32, enlarge=1.15, D=32, recognize=True)
+    rec_only = {k: stages.get(k) for k in ("k6_gray", "k7_hog", "k8_lda") if stages.get(k)}
+    dom = max(rec_only, key=rec_only.get) if rec_only else None
+    out = {"windows_per_s": world * F * NBOX / (ms * 1e-3), "frames_per_s": world * F / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": F, "n_gpus": world,
+           "stage_counts": [int(v) for v in cnt], "stages_ms_per_step": stages,
+           "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in stages.items() if v > 0 and alg.get(k)},
+           "config": "synthetic 1360x800, 200 candidates/frame, x1.15 / 32x32, HOG + 6 LDA (f64) (BASELINE configs[3])"}
+    if dom:
+        ach = alg[dom] / (rec_only[dom] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "algorithmic_bytes_per_launch": alg[dom], "kernel_ms_per_launch": rec_only[dom], "traffic": None,
+                           "note": "dominant kernel of the recognition branch (K6/K7/K8); the K1/K2/K5 stages are shared with detection"}
     return out
+
+
+def sweep_4k(torch, tsd_b200, dev, local_rank, peak):
+    """BASELINE configs[4]: candidate-window sweep at 4K frames (3840x2160), 50 .. 2000 candidates per frame, device-resident
+    detection chain.  Frames: 8 distinct synthetic 4K frames tiled to the batch; candidates: 16 distinct per-frame lists tiled."""
+    H4, W4, U, UB = 2160, 3840, 8, 16
+    red6, blue6 = templates()
+    uniq = tsd_b200.synth.make_frames(U, H4, W4, seed=tsd_b200.synth.FRAME_SEED + 900)
+    d_uniq = torch.from_numpy(uniq).to(dev)
+    rows = []
+    with tsd_b200.Context(device=local_rank, flavour="det") as ctx:
+        ctx.set_templates(red6, blue6)
+        st = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        for N in (50, 200, 500, 1000, 2000):
+            F = 256
+            d_frames = d_uniq[torch.arange(F, device=dev) % U].contiguous()       # 256 resident 4K frames = 6.4 GB
+            bu, _ = tsd_b200.synth.make_boxes(UB, N, H4, W4, seed=tsd_b200.synth.BOX_SEED + 900 + N)
+            boxes = np.ascontiguousarray(bu.reshape(UB, N, 4)[np.arange(F) % UB].reshape(-1, 4))
+            off = (np.arange(F + 1) * N).astype(np.int32)
+            d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+
+            def step():
+                ctx.enqueue_frames(d_frames.data_ptr(), F, H4, W4, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=N)
+            for _ in range(3):
+                step()
+            ctx.synchronize()
+            steps = 10 if N <= 500 else 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(steps):
+                step()
+            ctx.flush()
+            e1.record(st)
+            ctx.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            stages = _staged(torch, ctx, st, step, 3)
+            _, cnt = ctx.fetch_detections(int(off[-1]))
+            nnz = ctx.stat_hist_entries()
+            alg, _ = algorithmic_bytes(boxes, off, cnt, nnz, (min(N, 1024) + 31) // 32, Hf=H4, Wf=W4)
+            tot = sum(alg.values())
+            rows.append({"candidates_per_frame": N, "frames": F, "windows_per_s": F * N / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms,
+                         "stage_counts": [int(v) for v in cnt], "stages_ms_per_step": stages,
+                         "chain_alg_gbs": tot / (ms * 1e-3) / 1e9, "chain_frac_of_peak": tot / (ms * 1e-3) / 1e9 / peak})
+            del d_frames
+    return {"config": "synthetic 3840x2160 BGR frames, 256 resident frames (6.4 GB), detection chain, device-resident (BASELINE configs[4])", "rows": rows}
+
+
+def real_mser_run(torch, tsd_b200, dev, ctx_det, stream_det):
+    """The detection chain on REAL frames with REAL cv2.MSER boxes: the three stored test frames and the boxes the
+    reference's MSER produced for them, tiled to 1024 frames."""
+    import cv2
+    F = 1024
+    g = np.load(os.path.join(ROOT, "tests", "golden", "det_frames.npz"))
+    names = ["00604", "00639", "00719"]
+    imgs = np.stack([cv2.imread(os.path.join(ROOT, "tests", "golden", "det_frame_%s.png" % k)) for k in names])
+    bl = [g[k + "_boxes"].astype(np.int32) for k in names]
+    boxes = np.concatenate([bl[f % 3] for f in range(F)])
+    off = np.concatenate([[0], np.cumsum([len(bl[f % 3]) for f in range(F)])]).astype(np.int32)
+    d_frames = torch.from_numpy(imgs).to(dev)[torch.arange(F, device=dev) % 3].contiguous()
+    d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+    mb = int(max(len(b) for b in bl))
+    l0 = ctx_det.launch_count
+    ms = _time_steps(torch, stream_det, ctx_det, lambda: ctx_det.enqueue_frames(d_frames.data_ptr(), F, H, W, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]),
+                                                                                max_boxes_per_frame=mb))
+    launches = (ctx_det.launch_count - l0) / 13.0            # 3 warm + 10 timed steps
+    _, cnt = ctx_det.fetch_detections(int(off[-1]))
+    return {"windows_per_s": int(off[-1]) / (ms * 1e-3), "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms, "frames": F, "launches_per_step": launches,
+            "boxes_per_frame_mean": float(off[-1]) / F, "stage_counts": [int(v) for v in cnt],
+            "config": "3 real GTSDB test frames + the boxes cv2.MSER(7,200,2000,0.15) gives for them, tiled to 1024 frames"}
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -394,37 +490,70 @@ def run_b200(args, rank, world, local_rank):
         ndet_total = len(det)
     value = world * F * NBOX * args.steps / (ms * 1e-3)
 
-    # ---- e2e: public host-buffer API, pinned host frames, H2D + D2H inside the timed region --------------------------
+    # ---- e2e: public host-buffer API, host frames, H2D + D2H inside the timed region ----------------------------------------
     Fe = min(args.e2e_frames, F) if not args.no_e2e else 1
     h_frames = torch.empty((Fe, H, W, 3), dtype=torch.uint8).pin_memory()
     for f0 in range(0, Fe, 256):
         h_frames[f0:min(f0 + 256, Fe)].copy_(d_frames[f0:min(f0 + 256, Fe)])
     hf = h_frames.numpy()
     hb, ho = boxes[:off[Fe]], off[:Fe + 1]
-    for _ in range(2):
-        edet, ecounts = ctx.detect_frames(hf, hb, ho)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        edet, ecounts = ctx.detect_frames(hf, hb, ho)
-    ctx.synchronize()
-    e_dt = (time.perf_counter() - t0) / args.e2e_steps
-    if dist is not None:
-        t = torch.tensor([e_dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_dt = float(t.item())
-    e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(hf.nbytes + hb.nbytes + ho.nbytes),
-           "d2h_bytes_per_step": int(len(edet) * 32 + 12), "frames_per_step": Fe, "ms_per_step": e_dt * 1e3,
-           "frames_per_sec": world * Fe / e_dt,
-           "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST): page-locked host frames are read in place by K2 over PCIe "
-                  "(only candidate ROIs cross the bus), boxes H2D, detection records D2H; h2d_bytes_per_step counts the whole "
-                  "host input (frames + boxes) the call consumes"}
 
+    def e2e_leg(frames_np, steps):
+        for _ in range(2):
+            ctx.detect_frames(frames_np, hb, ho)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            edet, ecounts = ctx.detect_frames(frames_np, hb, ho)
+        ctx.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, edet, ecounts
+    e_dt, edet, ecounts = e2e_leg(hf, args.e2e_steps)
+    alg_e, _ = algorithmic_bytes(hb, ho, ecounts)
+    roi_bytes = int(alg_e["k2_crop_resize"] - int(ecounts[1]) * 3 * D * D)      # source bytes of the candidate ROIs (section 8(d) formula)
+    e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(roi_bytes + hb.nbytes + ho.nbytes),
+           "d2h_bytes_per_step": int(len(edet) * 32 + 16), "frames_per_step": Fe, "ms_per_step": e_dt * 1e3,
+           "frames_per_sec": world * Fe / e_dt, "host_input_bytes_per_step": int(hf.nbytes + hb.nbytes + ho.nbytes),
+           "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST) on PAGE-LOCKED host frames: K2 reads them in place over PCIe, so "
+                  "only the candidate ROIs cross the bus -- h2d_bytes_per_step = algorithmic ROI bytes (SURVEY 8(d)) + boxes; 32-byte "
+                  "sector granularity and re-fetches of overlapping ROIs add to it (profiles/README.md); detection records D2H"}
+    if not args.no_e2e and world == 1:
+        # the same call on PAGEABLE frames (what cv2.imread returns): whole frames are copied in double-buffered chunks
+        pg = np.array(hf[:min(Fe, 256)], copy=True)
+        hb_s, ho_s = hb, ho
+        hb, ho = boxes[:off[len(pg)]], off[:len(pg) + 1]
+        p_dt, pdet, _ = e2e_leg(pg, 3)
+        e2e["pageable"] = {"value": len(pg) * NBOX / p_dt, "unit": "windows/s", "frames_per_step": len(pg), "ms_per_step": p_dt * 1e3,
+                           "h2d_bytes_per_step": int(pg.nbytes + hb.nbytes + ho.nbytes), "d2h_bytes_per_step": int(len(pdet) * 32 + 16),
+                           "api": "same call, pageable numpy frames: 32-frame chunks copied whole (cudaMemcpyAsync from pageable memory), chain of chunk k under the copy of chunk k+1"}
+        hb, ho = hb_s, ho_s
+
+    peak, peak_src = load_peaks()
     secondary = None
-    if rank == 0 and not args.no_secondary:
-        secondary = secondary_runs(torch, tsd_b200, dev, local_rank, ctx, stream)
+    if not args.no_secondary:
+        secondary = {}
+        try:                                                 # every rank (collective timing inside); never breaks the bench line
+            secondary["recognize_chain"] = recognize_run(torch, tsd_b200, dev, local_rank, rank, world, dist, peak)
+        except Exception as e:
+            secondary["recognize_chain"] = {"error": str(e)[:300]}
+            if dist is not None:
+                raise
+        if rank == 0:
+            try:
+                secondary["real_mser_frames"] = real_mser_run(torch, tsd_b200, dev, ctx, stream)
+            except Exception as e:
+                secondary["real_mser_frames"] = {"error": str(e)[:300]}
+            if world == 1 and not args.no_sweep:
+                del d_frames                                 # the sweep needs 6.4 GB of its own
+                try:
+                    secondary["sweep_4k"] = sweep_4k(torch, tsd_b200, dev, local_rank, peak)
+                except Exception as e:
+                    secondary["sweep_4k"] = {"error": str(e)[:300]}
     if rank == 0:
-        peak, peak_src = load_peaks()
         alg, npass = algorithmic_bytes(boxes, off, counts, hist_entries, (NBOX + 31) // 32)
         traffic = load_traffic()
         per_stage = {k: v / args.steps for k, v in stage_ms.items()}
@@ -435,10 +564,8 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "frames_per_sec": world * F * args.steps / (ms * 1e-3),
-            "config": {"workload": "synthetic 1360x800 BGR frames, 200 MSER-like candidates/frame, detection-only scoring (BASELINE configs[2])",
-                       "frames_per_gpu": F, "boxes_per_frame": NBOX, "window": D, "parallelism": "frames sharded by image, dp%d" % world,
-                       "l2": "inputs larger than L2: %d resident frames (%.1f GB) per GPU, ROI bytes touched per step %.0f MB"
-                             % (F, F * H * W * 3 / 1e9, alg["k2_crop_resize"] / 1e6)},
+            "config": bench_config(world), "frames_per_step": F * world, "frames_per_gpu": F,
+            "resident": "%d frames (%.1f GB) per GPU, ROI bytes touched per step %.0f MB" % (F, F * H * W * 3 / 1e9, alg["k2_crop_resize"] / 1e6),
             "stage_counts": {"raw": int(counts[0]), "aspect_passing": int(counts[1]), "survivors": int(counts[2]), "detections": int(counts[3])},
             "detections_all_ranks": int(ndet_total),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -474,6 +601,7 @@ def main():
     ap.add_argument("--cpu-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (recognition chain, real-MSER frames) measurements")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 4K candidate sweep (BASELINE configs[4]) of the secondary measurements")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used for the ncu launch list of the device-resident step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
