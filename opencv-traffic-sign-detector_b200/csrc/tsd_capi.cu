@@ -55,7 +55,7 @@ struct tsd_ctx {
     // fold of one batch runs under the throughput-bound kernels of the next.  tsd_stream() is ordered after a batch only once the
     // NEXT call, tsd_flush, tsd_synchronize or tsd_fetch_detections has been issued (the join is deferred by one call).
     int overlap = 1, slot = 0, pending_join = -1;
-    size_t slot_cap = 0, slot_fcap = 0;      // windows / per-frame entries per slot
+    size_t slot_cap = 0, slot_fcap = 0, slot_todo = 0;   // windows / per-frame entries / k5_pairs work-list entries per slot
     int slot_rw = 1;                         // words per bit row of the pair-class matrix the slot layout is sized for (sticky maximum)
     cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     cudaStream_t os[2] = {nullptr, nullptr};                                // per slot: the chain's stream
@@ -553,34 +553,53 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
 // K5: both (or one) passes of cleanDuplicatedDetections.  max_n = upper bound of windows per frame (host-known), ncap = total
 // windows (rows of the pair-class bit matrix).  max_n <= 1024: all-pairs classification (k5_gram / k5_pairs) + one warp per frame
 // (k5_fold_warp); larger frames: the general block-synchronous fold (k5_fold_kernel).
-template <int RMAX, int CAP>
-static int launch_fold_warp(tsd_ctx* c, int variant, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost) {
-    const int warps = RMAX <= 256 ? kFoldWarps : 2;
-    const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<RMAX, CAP>);
+// The fold of one batch: frames of up to kFoldCtaMin windows by one warp each (k5_fold_warp), larger ones (<= 1024) by one CTA each
+// (k5_fold_cta); both walk the same longest-first order list with their own work counter.
+template <int CAP>
+static int launch_folds(tsd_ctx* c, int variant, const FoldParams& P, int nframes, uint32_t* M, int RW, int cut, const int32_t* cost, int max_n) {
+    const int warps = kFoldWarps;
+    const size_t smem = ((sizeof(HsvLut) + 15) & ~(size_t)15) + (size_t)warps * sizeof(FoldWarpSmem<256, CAP>);
+    const size_t smem_cta = sizeof(FoldCtaSmem<CAP>);
     int& per_sm = c->fold_per_sm[variant];
+    int& per_sm_cta = c->fold_per_sm[2 + variant];
     if (!per_sm) {
-        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<RMAX, CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_fold_warp_kernel<RMAX, CAP>, warps * 32, smem));
+        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<256, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k5_fold_warp_kernel<256, CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_fold_warp_kernel<256, CAP>, warps * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        if (getenv("TSD_DEBUG")) fprintf(stderr, "[tsd] k5_fold_warp<%d,%d>: %zu B shared memory per CTA, %d CTAs per SM\n", RMAX, CAP, smem, per_sm);
+        CU(cudaFuncSetAttribute(k5_fold_cta_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+        CU(cudaFuncSetAttribute(k5_fold_cta_kernel<CAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cta, k5_fold_cta_kernel<CAP>, kFoldCtaWarps * 32, smem_cta));
+        if (per_sm_cta < 1) per_sm_cta = 1;
+        if (getenv("TSD_DEBUG")) fprintf(stderr, "[tsd] k5_fold_warp<256,%d>: %zu B shared memory per CTA, %d CTAs per SM; k5_fold_cta: %zu B, %d per SM\n", CAP, smem, per_sm, smem_cta, per_sm_cta);
     }
-    // longest-first frame order + work counter (context scratch: [nframes] order, [1] counter)
-    TRY(ensure(c, c->b_order, (c->order_off + nframes + 1) * 4));
+    // longest-first frame order + the two work counters (context scratch: [nframes] order, [2] counters)
     int32_t* order = (int32_t*)c->b_order.p + c->order_off;
     int32_t* counter = order + nframes;
     k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter);
     TRY(check_launch(c, "k5_order"));
     int grid = cdiv(nframes, warps);
     if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
-    k5_fold_warp_kernel<RMAX, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter);
-    return check_launch(c, "k5_fold_warp");
+    k5_fold_warp_kernel<256, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter, kFoldCtaMin);
+    TRY(check_launch(c, "k5_fold_warp"));
+    if (max_n > kFoldCtaMin) {
+        grid = nframes < per_sm_cta * c->sm_count ? nframes : per_sm_cta * c->sm_count;
+        k5_fold_cta_kernel<CAP><<<grid, kFoldCtaWarps * 32, smem_cta, c->cur>>>(P, nframes, M, RW, cut, order, counter + 1);
+        TRY(check_launch(c, "k5_fold_cta"));
+    }
+    return TSD_OK;
 }
 
-// M = the batch's rows of the pair-class bit matrix (2 * RW words per window, RW = words per bit row for max_n windows per frame).
+// M = the batch's rows of the pair-class bit matrix (2 * RW words per window, RW = words per bit row for max_n windows per frame);
+// todo = the batch's work list for k5_pairs ([count, items ...], todo_capacity(nframes, max_n) ints).
+static inline size_t todo_capacity(int nframes, int max_n) {
+    const int nbk = (std::min(max_n, 1024) + kGramBM - 1) / kGramBM;
+    return (size_t)nframes * std::max(1, nbk * (nbk + 1) / 2) + 2;
+}
+
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, uint32_t* M, float* E_T, int64_t e_stride) {
+                    int max_n, uint32_t* M, int32_t* todo, float* E_T, int64_t e_stride) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
@@ -606,24 +625,33 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     if (do_hist) {
         cost = out_count;                                    // [nframes] scratch until the fold writes the survivor counts (order is built first)
         CU(cudaMemsetAsync(cost, 0, (size_t)nframes * 4, c->cur));
-        // frames of up to kGramBM windows: Gram matrix on the tensor cores; larger frames (and TSD_GRAM=0): CUDA-core pair kernel
+        // frames of up to kGramBM windows: Gram matrix on the tensor cores, one CTA per frame (k5_gram); larger frames (<= 1024): one
+        // CTA per pair of 128-row blocks (k5_gram_big); what they leave over (flat frames), and everything with TSD_GRAM=0: k5_pairs
         int32_t* gram_done = nullptr;
         if (c->use_gram) {
             if (!c->attr_gram) {
                 CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem)));
                 CU(cudaFuncSetAttribute(k5_gram_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CU(cudaFuncSetAttribute(k5_gram_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramBigSmem)));
+                CU(cudaFuncSetAttribute(k5_gram_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 c->attr_gram = true;
             }
-            gram_done = (int32_t*)c->b_gramdone.p + 2 * c->order_off;                            // [count, frames ...] of this batch
+            gram_done = todo;
             CU(cudaMemsetAsync(gram_done, 0, 4, c->cur));
             k5_gram_kernel<<<nframes, kGramWarps * 32, sizeof(GramSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, P.hist_tol,
                                                                                    P.hist_lo, M, cost, gram_done, 2 * c->sm_count);
             TRY(check_launch(c, "k5_gram"));
+            if (max_n > kGramBM) {
+                const int nbk = (max_n + kGramBM - 1) / kGramBM, ppf = nbk * (nbk + 1) / 2;
+                k5_gram_big_kernel<<<nframes * ppf, kBigWarps * 32, sizeof(GramBigSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, ppf,
+                                                                                                  P.hist_tol, P.hist_lo, M, cost, gram_done);
+                TRY(check_launch(c, "k5_gram_big"));
+            }
         }
         {
             const int tiles = (max_n + kPairWarps - 1) / kPairWarps;
             const size_t psm = kPairWarps * kDenseLen * 2;
-            // with a todo list (the frames k5_gram left over) a grid of resident CTAs walks it; else one CTA per (frame, tile)
+            // with a todo list (what the Gram kernels left over) a grid of resident CTAs walks it; else one CTA per (frame, tile)
             const int pgrid = gram_done ? (int)std::min<int64_t>((int64_t)nframes * tiles, (int64_t)c->sm_count * 16) : nframes * tiles;
             if (!c->attr_pairs) {
                 CU(cudaFuncSetAttribute(k5_pairs_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
@@ -635,12 +663,7 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         }
         mark(c, "k5_pairs");
     }
-    {
-        int rc;
-        if (max_n <= 256) rc = npx <= 640 ? launch_fold_warp<256, 640>(c, 0, P, nframes, M, RW, cut, cost) : launch_fold_warp<256, 1024>(c, 1, P, nframes, M, RW, cut, cost);
-        else rc = npx <= 640 ? launch_fold_warp<1024, 640>(c, 2, P, nframes, M, RW, cut, cost) : launch_fold_warp<1024, 1024>(c, 3, P, nframes, M, RW, cut, cost);
-        if (rc != TSD_OK) return rc;
-    }
+    TRY(npx <= 640 ? launch_folds<640>(c, 0, P, nframes, M, RW, cut, cost, max_n) : launch_folds<1024>(c, 1, P, nframes, M, RW, cut, cost, max_n));
     // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
     k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
@@ -767,9 +790,10 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
     c->order_off = 0;
     TRY(ensure(c, c->b_pairs, (size_t)(n > 0 ? n : 1) * 2 * pair_row_words(max_n) * sizeof(uint32_t)));
-    TRY(ensure(c, c->b_gramdone, (size_t)(2 * nframes + 2) * 4));
+    TRY(ensure(c, c->b_gramdone, todo_capacity(nframes, max_n) * 4));
+    TRY(ensure(c, c->b_order, (size_t)(nframes + 2) * 4));
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (float*)den, n));
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (int32_t*)c->b_gramdone.p, (float*)den, n));
     TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
     if (nframes) {
         k5_gather_kernel<<<nframes, 128, 0, c->cur>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
@@ -1169,7 +1193,7 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 // B.fo = first entry in the per-frame scratch arrays (nframes + 1 entries), B.nbcap = upper bound of the batch's windows;
 // M = the batch's rows of the pair-class bit matrix.
 static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-                         const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M) {
+                         const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo) {
     const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
     const int cf = B.nframes, nb = B.nbcap, fo = B.fo;
@@ -1198,7 +1222,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 list, flags, survcnt, maxb, M, energy, (int64_t)cap));
+                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap));
     TRY(dev_scan(c, survcnt, cf, survoff));
     k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
     TRY(check_launch(c, "k5_gather"));
@@ -1282,12 +1306,13 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     tsd_ctx::Batch B;
     B.nframes = nframes; B.nbcap = nb; B.nboxes = nb;
     const size_t need_w = (((size_t)(nb > 0 ? nb : 1) + 3) & ~(size_t)3);
-    size_t cap = need_w, fcap = (size_t)nframes + 1, mwords = need_w * 2 * RW, m_off = 0;
+    const size_t need_todo = todo_capacity(nframes, max_boxes_per_frame);
+    size_t cap = need_w, fcap = (size_t)nframes + 2, mwords = need_w * 2 * RW, m_off = 0, todo_words = need_todo, todo_off = 0;
     const bool ov = c->overlap && !c->profiling;
     if (ov) {                                                // this batch lives in slot `slot` of doubled scratch buffers
         c->slot ^= 1;
         const size_t sw = (need_w + 63) & ~(size_t)63, sf = ((size_t)nframes + 2 + 63) & ~(size_t)63;
-        if (sw > c->slot_cap || sf > c->slot_fcap || RW > c->slot_rw) {
+        if (sw > c->slot_cap || sf > c->slot_fcap || RW > c->slot_rw || need_todo > c->slot_todo) {
             // The slot layout changes (slot 1 starts at slot_cap windows, slot_fcap frames, slot_cap * 2 * slot_rw pair-class
             // words): nothing may be in flight in either slot.  All three are sticky maxima, so a batch never reaches into the
             // other slot whatever its own RW is.
@@ -1297,6 +1322,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
             if (sw > c->slot_cap) c->slot_cap = sw;
             if (sf > c->slot_fcap) c->slot_fcap = sf;
             if (RW > c->slot_rw) c->slot_rw = RW;
+            if (need_todo > c->slot_todo) c->slot_todo = need_todo;
         }
         B.wo = (size_t)c->slot * c->slot_cap;
         B.fo = (int)((size_t)c->slot * c->slot_fcap);
@@ -1304,6 +1330,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         cap = 2 * c->slot_cap; fcap = 2 * c->slot_fcap;
         mwords = 2 * c->slot_cap * 2 * (size_t)c->slot_rw;
         m_off = (size_t)c->slot * c->slot_cap * 2 * (size_t)c->slot_rw;
+        todo_words = 2 * c->slot_todo; todo_off = (size_t)c->slot * c->slot_todo;
     } else {
         TRY(join_pending(c));
         c->prev.valid = false;
@@ -1316,7 +1343,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     TRY(ensure(c, c->b_detoff, fcap * 4));
     TRY(ensure(c, c->b_summary, 2 * 16));
     TRY(ensure(c, c->b_order, (fcap + 2) * 4));
-    TRY(ensure(c, c->b_gramdone, (2 * fcap + 4) * 4));
+    TRY(ensure(c, c->b_gramdone, todo_words * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));
     TRY(ensure(c, c->b_windows, cap * ws));
@@ -1340,6 +1367,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     }
     TRY(ensure(c, c->b_pairs, mwords * sizeof(uint32_t)));
     uint32_t* M = (uint32_t*)c->b_pairs.p + m_off;
+    int32_t* todo = (int32_t*)c->b_gramdone.p + todo_off;
     int rc = TSD_OK;
     if (ov) {
         const int sl = c->slot;
@@ -1347,12 +1375,12 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         CU(cudaStreamWaitEvent(c->os[sl], c->ev_slot_fork[sl], 0));
         TRY(join_pending(c));                                // the PREVIOUS batch: the context's stream waits for it only now, after this batch's fork
         c->cur = c->os[sl];
-        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M);
+        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
         CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
         c->pending_join = sl;
     } else {
         c->cur = c->stream;
-        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M);
+        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
     }
     c->cur = c->stream;
     if (rc != TSD_OK) { c->prev.valid = false; return rc; }

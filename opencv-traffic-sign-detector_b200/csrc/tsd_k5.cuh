@@ -35,6 +35,7 @@ constexpr int kGramCbWords = (kGramChunks + 1) / 2;
 constexpr int kEnergyRows = kHistGroups + kGramCbWords;   // rows of the [rows][windows] energy block
 static_assert(kGramKC % 32 == 0 && kEnergyRows <= 32, "chunk boundaries");
 constexpr int kClsUnsure = 3;
+constexpr int kGramBM = 128;                           // windows per frame k5_gram handles / rows per block of k5_gram_big
 // Statistics: pairs whose integer-dot classification came within 2e-6 of a threshold and were decided by the exact f64 evaluation
 // (tsd_stat_unsure_pairs; the tests use it to prove that path is exercised).  Rare, so the atomic costs nothing.
 __device__ unsigned long long g_unsure_pairs = 0;
@@ -317,15 +318,17 @@ __device__ __forceinline__ double exact_s12_warp(const uint16_t* dense, float a_
     return warp_sum(s12);
 }
 
+// Items jl0 .. jl0 + kPairWarps - 1 of frame f against the earlier items in [i_lo, i_hi) (i_lo a multiple of 32).
 template <int G>
 __device__ __forceinline__ void k5_pairs_tile(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
                                               const float* __restrict__ E_T, int64_t e_stride, const int32_t* __restrict__ offsets, int es, int RW,
-                                              double tol, double lo, uint32_t* __restrict__ M, int32_t* __restrict__ frame_cost, int f, int tile) {
+                                              double tol, double lo, uint32_t* __restrict__ M, int32_t* __restrict__ frame_cost, int f, int jl0,
+                                              int i_lo, int i_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int base = offsets[f], n = offsets[f + 1] - base;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jl = tile * kPairWarps + wid;
-    if (jl >= n || jl == 0 || n > RW * 32) return;          // warps are independent: no block barrier below
+    const int jl = jl0 + wid;
+    if (jl >= n || jl == 0 || n > RW * 32 || i_lo >= jl) return;          // warps are independent: no block barrier below
     uint16_t* dense = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)wid * kDenseLen;
     for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(dense)[b] = 0;
     __syncwarp();
@@ -337,9 +340,10 @@ __device__ __forceinline__ void k5_pairs_tile(const uint32_t* __restrict__ entri
     const float Ej = lane < kHistGroups ? __ldg(E_T + (int64_t)lane * e_stride + base + jl) : 0.f;
     __syncwarp();
     uint32_t* Mrow = M + (int64_t)(base + jl) * 2 * RW;
-    for (int i0 = 0; i0 < jl; i0 += 32) {
+    const int i_end = min(jl, i_hi);
+    for (int i0 = i_lo; i0 < i_end; i0 += 32) {
         const int il = i0 + lane;
-        const bool valid = il < jl;
+        const bool valid = il < i_end;
         const int wi = base + (valid ? il : 0);
         // lane-parallel bound for 32 earlier windows at once
         float ub = 0.f;
@@ -476,10 +480,21 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
                                                                    const int32_t* __restrict__ offsets, int nframes, int es, int RW,
                                                                    int tiles_per_frame, double tol, double lo, uint32_t* __restrict__ M,
                                                                    int32_t* __restrict__ frame_cost, const int32_t* __restrict__ todo) {
-    const int nf = todo ? min(todo[0], nframes) : nframes;
-    for (int item = blockIdx.x; item < nf * tiles_per_frame; item += gridDim.x) {
-        const int fi = item / tiles_per_frame, tile = item - fi * tiles_per_frame;
-        k5_pairs_tile<G>(entries, meta, E_T, e_stride, offsets, es, RW, tol, lo, M, frame_cost, todo ? todo[1 + fi] : fi, tile);
+    // todo items: (frame << 8) | (I << 4) | J = items of the 128-row block I against those of block J; I = J = 15 = the whole frame
+    const int nf = todo ? todo[0] : nframes;
+    for (int64_t item = blockIdx.x; item < (int64_t)nf * tiles_per_frame; item += gridDim.x) {
+        const int fi = (int)(item / tiles_per_frame), tile = (int)(item - (int64_t)fi * tiles_per_frame);
+        int f = fi, jl0 = tile * kPairWarps, i_lo = 0, i_hi = 0x7fffffff;
+        if (todo) {
+            const int t = todo[1 + fi];
+            f = t >> 8;
+            const int I = (t >> 4) & 15, J = t & 15;
+            if (I != 15) {
+                if (tile >= kGramBM / kPairWarps) continue;  // (CTA-uniform) a block has 128 items
+                jl0 += I * kGramBM; i_lo = J * kGramBM; i_hi = i_lo + kGramBM;
+            }
+        }
+        k5_pairs_tile<G>(entries, meta, E_T, e_stride, offsets, es, RW, tol, lo, M, frame_cost, f, jl0, i_lo, i_hi);
         __syncwarp();
     }
 }
@@ -498,7 +513,6 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
 // blocks than warps, one slice of K; the integer partial sums meet in shared memory, where the lane-per-pair classification
 // (classify_from_int, f64 fallback within 2e-6 of a threshold) reads them.
 // =====================================================================================================================
-constexpr int kGramBM = 128;                           // windows per frame handled here
 constexpr int kGramWarps = 12;                         // 96 four-lane groups; 6 lower-triangle 32 x 32 blocks x 2 K slices for n <= 96
 constexpr int kGramGroups = kGramWarps * 8;
 constexpr int kGramPitch = kGramKC + 16;               // bytes per tile row: an odd number of 16-byte units -> conflict-free ldmatrix
@@ -594,9 +608,8 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
     if (f >= nframes) return;
     const int base = offsets[f], n = offsets[f + 1] - base;
     if (n < 2 || n > RW * 32) return;                       // (CTA-uniform) nothing to classify / the general fold's frame
-    if (n > kGramBM) {                                      // left to k5_pairs: todo = [count, frames ...]
-        if (threadIdx.x == 0) todo[1 + atomicAdd(todo, 1)] = f;
-        return;
+    if (n > kGramBM) {
+        return;                                              // k5_gram_big's frame (block pairs)
     }
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     // scatter role: group = tid / 4 owns row `group` and (frames of more than 96 windows, groups 0..31) row group + 96
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
     }
     __syncthreads();
     if (S.nbig > kGramMaxBig) {                              // (CTA-uniform) left to k5_pairs
-        if (tid == 0) todo[1 + atomicAdd(todo, 1)] = f;
+        if (tid == 0) todo[1 + atomicAdd(todo, 1)] = (f << 8) | 0xff;
         return;
     }
     const uint16_t* const cb0 = S.cb[act0 ? row0 : 0];
@@ -806,6 +819,240 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
     }
 }
 
+// =====================================================================================================================
+// k5_gram_big: frames of 129 .. 1024 windows.  The Gram matrix C C^T of such a frame does not fit one CTA's shared memory, so it is
+// cut into 128-row blocks and ONE CTA computes one block pair (I, J), J <= I: the classes of the items of block I against the
+// (earlier) items of block J -- 128 x 128 pairs, 16 warps, each one 32 x 32 block of u8 IMMA (m16n8k32) accumulators.  Per chunk of
+// kGramKC bins the rows of both blocks are scattered from their sparse lists into two dense u8 tiles (A = block I, B = block J;
+// the same tile when I == J); the entries of the NEXT chunk are loaded into registers before the tensor-core phase of the current
+// one (every load address is known from the chunk boundaries k5_hist recorded), so the L2 latency hides under the MMAs.
+// Rows holding a count above 255 (flat windows; the tiles hold count & 255) are corrected exactly from the sparse lists, like in
+// k5_gram; a block pair with more than kBigMaxRows such rows is appended to the todo list of the CUDA-core kernel (k5_pairs).
+// Todo items (shared with k5_gram): (frame << 8) | (I << 4) | J, I = J = 15 standing for "the whole frame".
+// =====================================================================================================================
+constexpr int kBigWarps = 16;
+constexpr int kBigRowsPerWarp = 2 * kGramBM / kBigWarps;                 // 256 rows (two blocks) over 16 warps
+constexpr int kBigMaxRows = 32;
+__host__ __device__ inline int todo_item(int f, int I, int J) { return (f << 8) | (I << 4) | J; }
+
+struct __align__(16) GramBigSmem {
+    unsigned char tile[2][kGramBM * kGramPitch];            // [0] = block I rows, [1] = block J rows; later the int32 result [128][kGramIPitch]
+    double A[2 * kGramBM], rA[2 * kGramBM], s1[2 * kGramBM];
+    float a[2 * kGramBM];
+    int32_t nnz[2 * kGramBM];
+    uint16_t cb[2 * kGramBM][kGramChunks + 2];
+    int32_t nbig;
+    int32_t bigrow[kBigMaxRows];                            // local row index 0..255 (>= 128: block J)
+};
+static_assert(kGramBM * kGramIPitch * 4 <= 2 * kGramBM * kGramPitch, "result matrix aliases the tiles");
+
+__global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
+                                                                       const float* __restrict__ E_T, int64_t e_stride,
+                                                                       const int32_t* __restrict__ offsets, int nframes, int es, int RW, int pairs_per_frame,
+                                                                       double tol, double lo, uint32_t* __restrict__ M,
+                                                                       int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GramBigSmem& S = *reinterpret_cast<GramBigSmem*>(smem_raw);
+    const int f = blockIdx.x / pairs_per_frame;
+    int q = blockIdx.x - f * pairs_per_frame;
+    if (f >= nframes) return;
+    int I = 0;
+    while (q > I) { q -= I + 1; I++; }                       // pair index -> (I, J), J <= I: 0:(0,0) 1:(1,0) 2:(1,1) 3:(2,0) ...
+    const int J = q;
+    const int base = offsets[f], n = offsets[f + 1] - base;
+    if (n <= kGramBM || n > RW * 32 || I * kGramBM >= n) return;             // (CTA-uniform) k5_gram's frame / the general fold's / no such block
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const bool diag = I == J;
+    const int rowsI = min(kGramBM, n - I * kGramBM), rowsJ = min(kGramBM, n - J * kGramBM);
+    // local row r: 0..127 = item I*128 + r, 128..255 = item J*128 + (r - 128) (unused when I == J)
+    auto item_of = [&](int r) { return r < kGramBM ? I * kGramBM + r : J * kGramBM + (r - kGramBM); };
+    auto row_ok = [&](int r) { return r < kGramBM ? r < rowsI : (!diag && r - kGramBM < rowsJ); };
+    if (tid == 0) S.nbig = 0;
+    __syncthreads();
+    if (tid < 2 * kGramBM && row_ok(tid)) {
+        const int r = tid, w = base + item_of(r);
+        const WinMeta m = meta[w];
+        S.A[r] = m.A; S.rA[r] = m.rA; S.s1[r] = m.s1; S.a[r] = m.a; S.nnz[r] = m.nnz;
+        if (m.nnz > 0 && m.a < 1.0f / 255.5f) {              // a = (float)(1 / max count): max count >= 256
+            const int k = atomicAdd(&S.nbig, 1);
+            if (k < kBigMaxRows) S.bigrow[k] = r;
+        }
+        uint16_t* cbr = S.cb[r];
+        cbr[0] = 0;
+#pragma unroll
+        for (int k = 0; k < kGramCbWords; k++) {
+            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(E_T) + (int64_t)(kHistGroups + k) * e_stride + w);
+            cbr[2 * k + 1] = (uint16_t)(wv & 0xffffu);
+            if (2 * k + 2 <= kGramChunks) cbr[2 * k + 2] = (uint16_t)(wv >> 16);
+        }
+    }
+    __syncthreads();
+    if (S.nbig > kBigMaxRows) {                              // (CTA-uniform) flat frames: this block pair goes to k5_pairs
+        if (tid == 0) todo[1 + atomicAdd(todo, 1)] = todo_item(f, I, J);
+        return;
+    }
+    // scatter role: warp w owns local rows w, w + 16, ... (16 rows); lane = entry within the row's chunk range
+    uint32_t pre[kBigRowsPerWarp];
+    auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int k = 0; k < kBigRowsPerWarp; k++) {
+            const int r = wid + kBigWarps * k;
+            pre[k] = 0xffffffffu;
+            if (row_ok(r)) {
+                const int e = (int)S.cb[r][c] + lane;
+                if (e < (int)S.cb[r][c + 1]) pre[k] = __ldg(entries + (int64_t)(base + item_of(r)) * es + e);
+            }
+        }
+    };
+    // MMA role: warp (bi, bj) = 32 x 32 block of the 128 x 128 pair matrix: rows bi*32.. of tile A x rows bj*32.. of tile B
+    const int bi = wid >> 2, bj = wid & 3;
+    const bool mma_on = !diag || bj <= bi;                   // diagonal block pair: lower triangle only
+    int acc[2][4][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[mi][ni][k] = 0;
+    const uint32_t tA = (uint32_t)__cvta_generic_to_shared(S.tile[0]);
+    const uint32_t tB = diag ? tA : (uint32_t)__cvta_generic_to_shared(S.tile[1]);
+    const uint32_t a_addr = tA + (uint32_t)((bi * 32 + (lane & 7) + ((lane >> 3) & 1) * 8) * kGramPitch + (lane >> 4) * 16);
+    const uint32_t b_addr = tB + (uint32_t)((bj * 32 + (lane & 7) + (lane >> 4) * 8) * kGramPitch + ((lane >> 3) & 1) * 16);
+    load_chunk(0);
+#pragma unroll 1
+    for (int ch = 0; ch < kGramChunks; ch++) {
+        const int k0 = ch * kGramKC;
+        {                                                    // wipe both tiles (rows beyond n stay zero)
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint4* t4 = reinterpret_cast<uint4*>(S.tile[0]);
+            const int n16 = (diag ? 1 : 2) * kGramBM * kGramPitch / 16;
+            for (int i = tid; i < n16; i += kBigWarps * 32) t4[i] = z;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBigRowsPerWarp; k++) {
+            const int r = wid + kBigWarps * k;
+            const uint32_t v = pre[k];
+            unsigned char* trow = S.tile[r >> 7] + (size_t)(r & (kGramBM - 1)) * kGramPitch;
+            if (v != 0xffffffffu) trow[(int)(v >> 16) - k0] = (unsigned char)v;
+            if (row_ok(r)) {                                 // (rare) more than 32 entries of this row in the chunk
+                const uint32_t* er = entries + (int64_t)(base + item_of(r)) * es;
+                for (int e = (int)S.cb[r][ch] + 32 + lane; e < (int)S.cb[r][ch + 1]; e += 32) {
+                    const uint32_t u = __ldg(er + e);
+                    trow[(int)(u >> 16) - k0] = (unsigned char)u;
+                }
+            }
+        }
+        if (ch + 1 < kGramChunks) load_chunk(ch + 1);        // in flight during the tensor-core phase below
+        __syncthreads();
+        if (mma_on) {
+#pragma unroll 2
+            for (int kk = 0; kk < kGramKC; kk += 32) {
+                uint32_t a[2][4], b[2][4];
+                ldmatrix_x4(a[0], a_addr + kk);
+                ldmatrix_x4(a[1], a_addr + 16 * kGramPitch + kk);
+                ldmatrix_x4(b[0], b_addr + kk);
+                ldmatrix_x4(b[1], b_addr + 16 * kGramPitch + kk);
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int nj = 0; nj < 2; nj++) {
+                        mma_u8_16832(acc[mi][nj * 2], a[mi], b[nj][0], b[nj][1]);
+                        mma_u8_16832(acc[mi][nj * 2 + 1], a[mi], b[nj][2], b[nj][3]);
+                    }
+            }
+        }
+        __syncthreads();                                     // the tiles are wiped (or become the result matrix) next
+    }
+    int32_t* sI = reinterpret_cast<int32_t*>(S.tile[0]);     // [row of block I][row of block J]
+    if (mma_on) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int row = bi * 32 + mi * 16 + g, col = bj * 32 + ni * 8 + 2 * t;
+                int* d0 = &sI[row * kGramIPitch + col];
+                int* d1 = &sI[(row + 8) * kGramIPitch + col];
+                d0[0] = acc[mi][ni][0]; d0[1] = acc[mi][ni][1];
+                d1[0] = acc[mi][ni][2]; d1[1] = acc[mi][ni][3];
+            }
+    }
+    __syncthreads();
+    if (S.nbig > 0) {                                        // (CTA-uniform, rare) counts above 255: the tiles held count & 255
+        // every entry (row r, bin) with a count above 255 corrects its pairs with all rows of the OTHER block (all other rows of the
+        // same block when I == J); a pair big in the same bin on both sides is left to the entry of the lower item
+        for (int k = wid; k < S.nbig; k += kBigWarps) {
+            const int r = S.bigrow[k], ir = item_of(r);
+            const bool rI = r < kGramBM;
+            const uint32_t* erow = entries + (int64_t)(base + ir) * es;
+            const int nz = S.nnz[r];
+            const int o0 = (diag || !rI) ? 0 : kGramBM, on = (diag || !rI) ? rowsI : rowsJ;      // the other side's local rows o0 .. o0+on
+            for (int e0 = 0; e0 < nz; e0 += 32) {
+                const uint32_t v = e0 + lane < nz ? __ldg(erow + e0 + lane) : 0u;
+                unsigned mb = __ballot_sync(0xffffffffu, (v & 0xffffu) > 255u);
+                while (mb) {
+                    const int kb = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    const uint32_t vb = __shfl_sync(0xffffffffu, v, kb);
+                    const uint32_t bin = vb >> 16;
+                    const int cr = (int)(vb & 0xffffu);
+                    for (int x = lane; x < on; x += 32) {
+                        const int ro = o0 + x, io = item_of(ro);
+                        if (io == ir) continue;
+                        const uint32_t* ei = entries + (int64_t)(base + io) * es;
+                        int lo_ = 0, hi_ = S.nnz[ro];
+                        const int nzi = hi_;
+                        while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if ((__ldg(ei + mid) >> 16) < bin) lo_ = mid + 1; else hi_ = mid; }
+                        if (lo_ >= nzi) continue;
+                        const uint32_t u = __ldg(ei + lo_);
+                        if ((u >> 16) != bin) continue;
+                        const int ci = (int)(u & 0xffffu);
+                        if (ci > 255 && io < ir) continue;
+                        // result cell: [local row in I][local row in J]; for I == J the lower triangle [later][earlier]
+                        int cI, cJ;
+                        if (diag) { cI = max(r, ro); cJ = min(r, ro); }
+                        else { cI = rI ? r : ro; cJ = (rI ? ro : r) - kGramBM; }
+                        atomicAdd(&sI[cI * kGramIPitch + cJ], cr * ci - (cr & 255) * (ci & 255));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // classification: one warp per item j of block I, one earlier item of block J per lane
+    for (int rj = wid; rj < rowsI; rj += kBigWarps) {
+        const int jl = I * kGramBM + rj;
+        const double Aj = S.A[rj], rAj = S.rA[rj], s1j = S.s1[rj];
+        const float aj = S.a[rj];
+        uint32_t* Mrow = M + (int64_t)(base + jl) * 2 * RW;
+        for (int i0 = 0; i0 < rowsJ; i0 += 32) {
+            const int ri = i0 + lane, il = J * kGramBM + ri;
+            const bool valid = ri < rowsJ && il < jl;
+            if (J * kGramBM + i0 >= jl) break;               // (warp-uniform) nothing earlier than j in this word
+            const int rs = diag ? (valid ? ri : 0) : kGramBM + (valid ? ri : 0);      // the earlier item's local row (metadata index)
+            int c = 0;
+            if (valid) c = classify_from_int_s(sI[rj * kGramIPitch + ri], Aj, rAj, s1j, aj, S.A[rs], S.rA[rs], S.s1[rs], S.a[rs], tol, lo);
+            unsigned unsure = __ballot_sync(0xffffffffu, valid && c == kClsUnsure);
+            if (unsure && lane == 0) atomicAdd(&g_unsure_pairs, (unsigned long long)__popc(unsure));
+            while (unsure) {                                // rare: within 2e-6 of a threshold -> exact f64 evaluation
+                const int k = __ffs(unsure) - 1;
+                unsure &= unsure - 1;
+                const int rk = diag ? i0 + k : kGramBM + i0 + k, ik = J * kGramBM + i0 + k;
+                const double s12 = exact_s12_sparse_warp(entries + (int64_t)(base + jl) * es, S.nnz[rj], aj,
+                                                         entries + (int64_t)(base + ik) * es, S.nnz[rk], S.a[rk]);
+                if (lane == k) c = classify(correl_from(s12, s1j, Aj, S.s1[rk], S.A[rk]), tol, lo);
+            }
+            const unsigned bd = __ballot_sync(0xffffffffu, valid && c == 1), bm = __ballot_sync(0xffffffffu, valid && c == 2);
+            if (lane == 0) {
+                const int word = (J * kGramBM + i0) >> 5;
+                Mrow[word] = bd; Mrow[RW + word] = bm;
+                if (bm && frame_cost) atomicAdd(frame_cost + f, __popc(bm));
+            }
+        }
+    }
+}
+
 // Longest-processing-time-first order of the frames for the fold: key = 32 * (merge-band pairs) + windows, counting sort,
 // descending.  One CTA.  Also resets the fold's work counter.
 __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restrict__ frame_cost, const int32_t* __restrict__ offsets, int nframes,
@@ -822,7 +1069,7 @@ __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restric
     if (threadIdx.x == 0) {                                  // exclusive prefix over 2048 buckets (tiny)
         int run = 0;
         for (int i = 0; i < NB; i++) { const int c = hist[i]; hist[i] = run; run += c; }
-        *counter = 0;
+        counter[0] = 0; counter[1] = 0;                      // work counters of k5_fold_warp / k5_fold_cta
     }
     __syncthreads();
     for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
@@ -1047,9 +1294,78 @@ __device__ __forceinline__ unsigned fold_apply_deletions(unsigned A, unsigned D,
     return A;
 }
 
+
+// Pass 2 of the fold (corner similarity, DET:209-213) of one frame by one warp: A1 = survivors of pass 1 (bit set, lane w = items
+// 32w .. 32w+31, list order = item order).  Coordinates live in shared memory (overlaying the pass-1 workspace).  Returns the survivors.
+template <int RMAX, int CAP>
+__device__ __forceinline__ unsigned fold_coord_pass(unsigned A1, FoldWarpSmem<RMAX, CAP>& sm, const FoldParams& P, int base, int n, int sim_cut) {
+    const int lane = threadIdx.x & 31;
+    const int nwords = (n + 31) >> 5;
+    const int ws = P.ws;
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) sm.coords[p] = P.coords[base + p];      // overlays the pass-1 workspace
+    __syncwarp();
+    unsigned A2 = 0;
+    const double tol = P.coord_tol, lo = P.coord_lo;
+    for (int tj = 0; tj < nwords; tj++) {
+        unsigned wj = __shfl_sync(0xffffffffu, A1, tj);
+        while (wj) {
+            const int j = 32 * tj + __ffs(wj) - 1;
+            wj &= wj - 1;
+            int4 ic = sm.coords[j];
+            unsigned D = 0;
+            bool dirty = false;
+            int start = 0;                           // first list position still to scan
+            int t = 0;
+            while (t <= tj) {
+                unsigned aw = __shfl_sync(0xffffffffu, A2, t);
+                if (t == (start >> 5)) aw &= ~((1u << (start & 31)) - 1);
+                if (!aw) { t++; continue; }
+                int c = 0;
+                if ((aw >> lane) & 1u) c = classify(coord_sim(ic, sm.coords[32 * t + lane], P.simtab, sim_cut), tol, lo);
+                const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
+                if (!bmm) { if (lane == t) D |= bd; t++; continue; }
+                // ---- merge (DET:217-221): pixels, coords; later comparisons use the updated item ----
+                const int bit = __ffs(bmm) - 1, fm = 32 * t + bit;
+                if (lane == t) D |= (bd & ((1u << bit) - 1)) | (1u << bit);
+                const uint32_t hsh = merge_pixels_warp<true>(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                const int4 kc = sm.coords[fm];
+                ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);
+                if (lane == 0) sm.hash[j] = hsh;
+                dirty = true;
+                start = fm + 1;
+                t = start >> 5;
+                __syncwarp();
+            }
+            if (dirty) {
+                if (lane == 0) { sm.coords[j] = ic; P.coords[base + j] = ic; P.meta[base + j].hash = sm.hash[j]; }
+                __syncwarp();
+            }
+            if (__any_sync(0xffffffffu, D != 0)) A2 = fold_apply_deletions<RMAX, CAP>(A2, D, sm, P.windows, base, ws);
+            if (lane == (j >> 5)) A2 |= 1u << (j & 31);
+        }
+    }
+    return A2;
+}
+
+// survivors -> list (slots in list order) + count of frame f.  One warp.
+__device__ __forceinline__ void fold_emit_survivors(unsigned A, const FoldParams& P, int f, int base) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = __popc(A);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    int o = incl - cnt;
+    unsigned w = A;
+    while (w) { const int bit = __ffs(w) - 1; w &= w - 1; P.list[base + o++] = base + 32 * lane + bit; }
+    if (lane == 31) P.out_count[f] = incl;
+    __syncwarp();
+}
+
+// n_skip: frames with more windows than this belong to k5_fold_cta (launched beside this kernel on the same order list).
 template <int RMAX, int CAP>
 __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
-                                                                       const int32_t* __restrict__ order, int32_t* counter) {
+                                                                       const int32_t* __restrict__ order, int32_t* counter, int n_skip) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HsvLut& lut = *reinterpret_cast<HsvLut*>(smem_raw);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1067,6 +1383,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
         if (idx >= nframes) break;
         const int f = order[idx];
         const int base = P.offsets[f], n = P.offsets[f + 1] - base;
+        if (n > n_skip && n <= RW * 32) continue;            // k5_fold_cta's frame
         if (n > RMAX || n > RW * 32) { if (lane == 0) P.out_count[f] = -1; continue; }    // host picks RMAX / RW large enough
         for (int p = lane; p < n; p += 32) sm.hash[p] = P.meta[base + p].hash;
         for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;   // (the previous frame's pass 2 overlaid it)
@@ -1153,63 +1470,271 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
         } else {
             if (lane < nwords) A = (lane == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1) : 0xffffffffu;
         }
-        if (P.do_coords) {
-            __syncwarp();
-            for (int p = lane; p < n; p += 32) sm.coords[p] = P.coords[base + p];      // overlays the pass-1 workspace
-            __syncwarp();
-            const unsigned A1 = A;
-            unsigned A2 = 0;
-            const double tol = P.coord_tol, lo = P.coord_lo;
-            for (int tj = 0; tj < nwords; tj++) {
-                unsigned wj = __shfl_sync(0xffffffffu, A1, tj);
-                while (wj) {
-                    const int j = 32 * tj + __ffs(wj) - 1;
-                    wj &= wj - 1;
-                    int4 ic = sm.coords[j];
-                    unsigned D = 0;
-                    bool dirty = false;
-                    int start = 0;                           // first list position still to scan
-                    int t = 0;
-                    while (t <= tj) {
-                        unsigned aw = __shfl_sync(0xffffffffu, A2, t);
-                        if (t == (start >> 5)) aw &= ~((1u << (start & 31)) - 1);
-                        if (!aw) { t++; continue; }
-                        int c = 0;
-                        if ((aw >> lane) & 1u) c = classify(coord_sim(ic, sm.coords[32 * t + lane], P.simtab, sim_cut), tol, lo);
-                        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
-                        if (!bmm) { if (lane == t) D |= bd; t++; continue; }
-                        // ---- merge (DET:217-221): pixels, coords; later comparisons use the updated item ----
-                        const int bit = __ffs(bmm) - 1, fm = 32 * t + bit;
-                        if (lane == t) D |= (bd & ((1u << bit) - 1)) | (1u << bit);
-                        const uint32_t hsh = merge_pixels_warp<true>(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
-                        const int4 kc = sm.coords[fm];
-                        ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);
-                        if (lane == 0) sm.hash[j] = hsh;
-                        dirty = true;
-                        start = fm + 1;
-                        t = start >> 5;
-                        __syncwarp();
-                    }
-                    if (dirty) {
-                        if (lane == 0) { sm.coords[j] = ic; P.coords[base + j] = ic; P.meta[base + j].hash = sm.hash[j]; }
-                        __syncwarp();
-                    }
-                    if (__any_sync(0xffffffffu, D != 0)) A2 = fold_apply_deletions<RMAX, CAP>(A2, D, sm, P.windows, base, ws);
-                    if (lane == (j >> 5)) A2 |= 1u << (j & 31);
-                }
-            }
-            A = A2;
-        }
-        // survivors -> list (slots in list order) + count
-        const int cnt = __popc(A);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        int o = incl - cnt;
-        unsigned w = A;
-        while (w) { const int bit = __ffs(w) - 1; w &= w - 1; P.list[base + o++] = base + 32 * lane + bit; }
-        if (lane == 31) P.out_count[f] = incl;
+        if (P.do_coords) A = fold_coord_pass<RMAX, CAP>(A, sm, P, base, n, sim_cut);
+        fold_emit_survivors(A, P, f, base);
         __syncwarp();
+    }
+}
+
+
+// =====================================================================================================================
+// The fold of a LARGE frame (more than kFoldCtaMin windows, at most 1024): one CTA per frame.  Warp 0 is the sequencer -- it runs
+// exactly the item loop of k5_fold_warp (bit set of survivors, delete / merge bit rows, pop-by-pixel-equality) -- and the other
+// warps join it for the only expensive step, the re-classification of a merged item against hundreds of other items
+// (Cauchy-Schwarz pruning of 32 items per warp step, then the exact integer dots of the surviving candidates, one candidate per
+// warp step) and for the rewrite of the item's column in the later items' bit rows.  A 4K frame with 2000 candidates keeps ~800
+// windows after the aspect filter and merges ~100 times; with one warp per frame each merge cost ~100 us of exposed L2 latency.
+// =====================================================================================================================
+constexpr int kFoldCtaWarps = 8;
+constexpr int kFoldCtaMin = 256;                        // frames above this size come here (the warp fold keeps the smaller ones: 126 registers x 256 threads allow only 2 such CTAs per SM)
+
+template <int CAP>
+struct FoldCtaSmem {
+    HsvLut lut;
+    FoldWarpSmem<1024, CAP> w;
+    WinMeta mj;                  // the merged item's moments
+    uint32_t cmask[32];          // items to classify against (word t = items 32t .. 32t+31)
+    int32_t cmd, w0, w1, ncand, frame, rewrite_j;
+};
+enum { kCtaCmdClassify = 1, kCtaCmdNextFrame = 2, kCtaCmdExit = 3 };
+
+// All warps of the CTA.  Classes of the merged item (dense histogram in w.p1.dense, moments S.mj, energies w.p1.eg) against the items
+// in S.cmask words [S.w0, S.w1] -> bit words w.p1.rowd / w.p1.rowm.  With S.rewrite_j >= 0 the bits then replace column rewrite_j of
+// the later items' rows of M.  Four block barriers, the same for every warp.
+template <int CAP>
+__device__ __forceinline__ void fold_cta_classify(FoldCtaSmem<CAP>& S, const FoldParams& P, uint32_t* M, int RW, int base, int n) {
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    FoldWarpSmem<1024, CAP>& sm = S.w;
+    if (tid < 32) { sm.p1.rowd[tid] = 0; sm.p1.rowm[tid] = 0; }
+    if (tid == 0) S.ncand = 0;
+    __syncthreads();
+    const WinMeta mj = S.mj;
+    const int w0 = S.w0, w1 = S.w1;
+    uint32_t* cand = sm.p1.cand();
+    for (int t = w0 + wid; t <= w1; t += kFoldCtaWarps) {
+        const unsigned aw = S.cmask[t];
+        if (!aw) continue;
+        const bool mine = (aw >> lane) & 1u;
+        const int q = base + 32 * t + lane;
+        int c = 0, nnz_q = 0;
+        bool need = false;
+        if (mine) {
+            float ub = 0.f;
+#pragma unroll
+            for (int g = 0; g < kHistGroups; g++) ub += sm.p1.eg[g] * P.E_T[(int64_t)g * P.e_stride + q];
+            const WinMeta mq = load_meta_cg(P.meta + q);
+            nnz_q = mq.nnz;
+            const double den2 = mj.A * mq.A;
+            if (!(fabs(den2) > DBL_EPSILON)) c = classify(1.0, P.hist_tol, P.hist_lo);      // compareHist's degenerate branch
+            else need = !prunable(ub, mj, mq.s1, mq.A, mq.rA, P.hist_lo);
+        }
+        const unsigned nb = __ballot_sync(0xffffffffu, need);
+        int pos = 0;
+        if (nb && lane == 0) pos = atomicAdd(&S.ncand, __popc(nb));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (need) cand[pos + __popc(nb & ((1u << lane) - 1))] = (uint32_t)(32 * t + lane) | ((uint32_t)nnz_q << 16);
+        const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bm = __ballot_sync(0xffffffffu, c == 2);
+        if (lane == 0) { if (bd) atomicOr(&sm.p1.rowd[t], bd); if (bm) atomicOr(&sm.p1.rowm[t], bm); }
+    }
+    __syncthreads();
+    // exact integer dots: candidate k of a round goes to warp k % kFoldCtaWarps, slot k / kFoldCtaWarps of that warp (two in flight)
+    const int ncand = S.ncand;
+    const uint16_t* dense = sm.p1.dense;
+    const uint4* ent4 = reinterpret_cast<const uint4*>(P.entries) + (int64_t)base * (P.es >> 2);
+    const int es4 = P.es >> 2;
+    for (int r0 = 0; r0 < ncand; r0 += 32 * kFoldCtaWarps) {
+        const int left = ncand - r0 - wid;
+        const int nr = left <= 0 ? 0 : min(32, (left + kFoldCtaWarps - 1) / kFoldCtaWarps);       // this warp's candidates of the round
+        int Ik = 0;
+        int cA = 0, cB = 0, nA = 0, nB = 0;
+        const uint4 *eA = ent4, *eB = ent4;
+        uint4 a0, a1, b0, b1;
+#define CTA_FETCH(CI, N, E, V0, V1)                                                                          \
+        do {                                                                                                 \
+            const uint32_t info = cand[r0 + (CI) * kFoldCtaWarps + wid];                                     \
+            N = (int)((info >> 16) + 3) >> 2;                                                                \
+            E = ent4 + (int64_t)(info & 0xffffu) * es4;                                                      \
+            V0 = lane < N ? E[lane] : make_uint4(0, 0, 0, 0);                                                \
+            V1 = lane + 32 < N ? E[lane + 32] : make_uint4(0, 0, 0, 0);                                      \
+        } while (0)
+#define CTA_DOT(V) ((int)dense[(V).x >> 16] * (int)((V).x & 0xffffu) + (int)dense[(V).y >> 16] * (int)((V).y & 0xffffu) + \
+                    (int)dense[(V).z >> 16] * (int)((V).z & 0xffffu) + (int)dense[(V).w >> 16] * (int)((V).w & 0xffffu))
+#define CTA_COMPUTE(CI, N, E, V0, V1)                                                                        \
+        do {                                                                                                 \
+            int acc = CTA_DOT(V0) + CTA_DOT(V1);                                                             \
+            for (int e = lane + 64; e < N; e += 32) { const uint4 v = E[e]; acc += CTA_DOT(v); }             \
+            acc = warp_sum_i(acc);                                                                           \
+            if (lane == (CI)) Ik = acc;                                                                      \
+        } while (0)
+        if (nr > 0) {
+            CTA_FETCH(cA, nA, eA, a0, a1);
+            while (cA < nr) {
+                cB = cA + 1;
+                if (cB < nr) CTA_FETCH(cB, nB, eB, b0, b1);
+                CTA_COMPUTE(cA, nA, eA, a0, a1);
+                if (cB >= nr) break;
+                cA = cB + 1;
+                if (cA < nr) CTA_FETCH(cA, nA, eA, a0, a1);
+                CTA_COMPUTE(cB, nB, eB, b0, b1);
+            }
+        }
+#undef CTA_FETCH
+#undef CTA_DOT
+#undef CTA_COMPUTE
+        if (lane < nr) {                                     // lane-parallel classification (exact f64 only within 2e-6 of a threshold)
+            const int ql = (int)(cand[r0 + lane * kFoldCtaWarps + wid] & 0xffffu), q = base + ql;
+            const WinMeta mq = load_meta_cg(P.meta + q);
+            int c = classify_from_int(Ik, mj, mq, P.hist_tol, P.hist_lo);
+            if (c == kClsUnsure) {
+                atomicAdd(&g_unsure_pairs, 1ull);
+                const uint32_t* eo = P.entries + (int64_t)q * P.es;
+                double s12 = 0;
+                for (int i = 0; i < mq.nnz; i++) {
+                    const uint32_t v = eo[i];
+                    s12 += (double)((float)dense[v >> 16] * mj.a) * (double)((float)(v & 0xffffu) * mq.a);
+                }
+                c = classify(correl_from(s12, mj.s1, mj.A, mq.s1, mq.A), P.hist_tol, P.hist_lo);
+            }
+            if (c == 1) atomicOr(&sm.p1.rowd[ql >> 5], 1u << (ql & 31));
+            else if (c == 2) atomicOr(&sm.p1.rowm[ql >> 5], 1u << (ql & 31));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const int j = S.rewrite_j;
+    if (j >= 0) {                                            // the item is final: its column in the bit rows of every LATER item
+        const unsigned bitj = 1u << (j & 31);
+        const int nwords = (n + 31) >> 5;
+        for (int t = (j >> 5) + wid; t < nwords; t += kFoldCtaWarps) {
+            const int q2 = 32 * t + lane;
+            if (q2 > j && q2 < n) {
+                uint32_t* r = M + (int64_t)(base + q2) * 2 * RW + (j >> 5);
+                r[0] = (r[0] & ~bitj) | (((sm.p1.rowd[t] >> lane) & 1u) ? bitj : 0u);      // (this CTA is the only writer of the frame's rows)
+                r[RW] = (r[RW] & ~bitj) | (((sm.p1.rowm[t] >> lane) & 1u) ? bitj : 0u);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
+                                                                          const int32_t* __restrict__ order, int32_t* counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FoldCtaSmem<CAP>& S = *reinterpret_cast<FoldCtaSmem<CAP>*>(smem_raw);
+    FoldWarpSmem<1024, CAP>& sm = S.w;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    load_hsv_lut(S.lut, P.tab);
+    const int ws = P.ws, es = P.es;
+    while (true) {
+        __syncthreads();                                     // (the previous frame is complete; lut loaded)
+        if (tid == 0) {
+            int f = -1;
+            while (true) {                                   // next frame of this kernel's size class, longest first
+                const int idx = atomicAdd(counter, 1);
+                if (idx >= nframes) break;
+                const int fc = order[idx], nc = P.offsets[fc + 1] - P.offsets[fc];
+                if (nc > kFoldCtaMin && nc <= 1024 && nc <= RW * 32) { f = fc; break; }
+            }
+            S.frame = f;
+        }
+        __syncthreads();
+        const int f = S.frame;
+        if (f < 0) break;
+        const int base = P.offsets[f], n = P.offsets[f + 1] - base;
+        for (int p = tid; p < n; p += blockDim.x) sm.hash[p] = P.meta[base + p].hash;
+        for (int b = tid; b < kDenseLen / 2; b += blockDim.x) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;
+        __syncthreads();
+        if (wid != 0) {                                      // helper warps: wait for the sequencer's orders
+            while (true) {
+                __syncthreads();
+                const int cmd = S.cmd;
+                if (cmd != kCtaCmdClassify) break;
+                fold_cta_classify<CAP>(S, P, M, RW, base, n);
+            }
+            continue;
+        }
+        // ---- warp 0: the sequencer (same item loop as k5_fold_warp) ----
+        const int nwords = (n + 31) >> 5;
+        unsigned A = 0;
+        if (P.do_hist) {
+            const uint32_t* Mf = M + (int64_t)base * 2 * RW;
+            unsigned nd = 0, nm = 0;
+            if (n > 1 && lane < RW) { nd = __ldcg(Mf + 2 * RW + lane); nm = __ldcg(Mf + 3 * RW + lane); }
+            if (n > 0 && lane == 0) A = 1u;
+            for (int j = 1; j < n; j++) {
+                unsigned vd = nd, vm = nm;
+                if (j + 1 < n && lane < RW) { nd = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + lane); nm = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + RW + lane); }
+                unsigned D = 0, scan = 0xffffffffu;
+                bool dirty = false;
+                int4 ic = make_int4(0, 0, 0, 0);
+                WinMeta mj;
+                mj.nnz = 0;
+                const int slot = base + j;
+                while (true) {
+                    const unsigned m = vm & A & scan, d = vd & A & scan;
+                    const unsigned bm = __ballot_sync(0xffffffffu, m != 0);
+                    if (!bm) { D |= d; break; }
+                    // ---- merge with the first survivor (list order) in the merge band (DET:217-221) ----
+                    const int L = __ffs(bm) - 1;
+                    const int bit = __ffs(__shfl_sync(0xffffffffu, m, L)) - 1;
+                    const int fm = 32 * L + bit;
+                    if (lane < L) D |= d;
+                    else if (lane == L) D |= (d & ((1u << bit) - 1)) | (1u << bit);
+                    uint8_t* ipx = P.windows + (int64_t)slot * ws;
+                    uint32_t* ient = P.entries + (int64_t)slot * es;
+                    if (!dirty) ic = P.coords[slot];
+                    else {                                   // clear the previous dense copy of this item (hs still holds its bins)
+                        for (int r = lane; r < mj.nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = 0;
+                        __syncwarp();
+                    }
+                    merge_pixels_warp<false>(ipx, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                    const int4 kc = P.coords[base + fm];
+                    ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);   // Python // (coords >= 0)
+                    __syncwarp();
+                    const int nnz = hist_build_warp<CAP>(ipx, P.npx, S.lut, sm.p1.hs, ient, P.meta + slot, sm.p1.eg, 1);
+                    for (int r = lane; r < nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = (uint16_t)sm.p1.hs.cnt[r];
+                    __syncwarp();
+                    mj = load_meta_cg(P.meta + slot);
+                    if (lane == 0) sm.hash[j] = mj.hash;
+                    if (lane < kHistGroups) P.E_T[(int64_t)lane * P.e_stride + slot] = sm.p1.eg[lane];   // later merges prune against the NEW histogram
+                    // re-classify the updated item against the survivors after the merge position (all warps)
+                    scan = lane < L ? 0u : (lane == L ? (bit == 31 ? 0u : ~((2u << bit) - 1)) : 0xffffffffu);
+                    S.cmask[lane] = A & scan;
+                    if (lane == 0) { S.mj = mj; S.w0 = L; S.w1 = (j - 1) >> 5; S.rewrite_j = -1; S.cmd = kCtaCmdClassify; }
+                    __syncthreads();
+                    fold_cta_classify<CAP>(S, P, M, RW, base, n);
+                    if (lane >= L && lane <= ((j - 1) >> 5)) { vd = sm.p1.rowd[lane]; vm = sm.p1.rowm[lane]; }
+                    __syncwarp();
+                    dirty = true;
+                }
+                if (dirty) {
+                    if (lane == 0) P.coords[slot] = ic;
+                    // the item is final: its class against every LATER item (their bit rows described the un-merged histogram)
+                    unsigned later = 0;                      // items after j: lane w covers 32w..32w+31
+                    if (lane >= (j >> 5) && lane < nwords) {
+                        later = 0xffffffffu;
+                        if (lane == (j >> 5)) later = (j & 31) == 31 ? 0u : ~((2u << (j & 31)) - 1);
+                        if (lane == nwords - 1 && (n & 31)) later &= (1u << (n & 31)) - 1;
+                    }
+                    S.cmask[lane] = later;
+                    if (lane == 0) { S.mj = mj; S.w0 = j >> 5; S.w1 = nwords - 1; S.rewrite_j = j; S.cmd = kCtaCmdClassify; }
+                    __syncthreads();
+                    fold_cta_classify<CAP>(S, P, M, RW, base, n);
+                    for (int r = lane; r < mj.nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = 0;
+                    __syncwarp();
+                    if (j + 1 < n && lane < RW) { nd = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + lane); nm = __ldcg(Mf + (int64_t)(j + 1) * 2 * RW + RW + lane); }
+                }
+                if (__any_sync(0xffffffffu, D != 0)) A = fold_apply_deletions<1024, CAP>(A, D, sm, P.windows, base, ws);
+                if (lane == (j >> 5)) A |= 1u << (j & 31);
+            }
+        } else {
+            if (lane < nwords) A = (lane == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1) : 0xffffffffu;
+        }
+        if (lane == 0) S.cmd = kCtaCmdNextFrame;             // the helpers leave their command loop (pass 2 is cheap: warp 0 alone)
+        __syncthreads();
+        if (P.do_coords) A = fold_coord_pass<1024, CAP>(A, sm, P, base, n, sim_cut);
+        fold_emit_survivors(A, P, f, base);
     }
 }
 

@@ -177,6 +177,8 @@ def test_slot_layout_independent_of_row_words(tsd, oracle, templates):
 
         def enqueue(b):
             ctx.enqueue_frames(b[0].data_ptr(), b[3], 800, 1360, b[1].data_ptr(), b[2].data_ptr(), b[4], max_boxes_per_frame=b[5])
+        enqueue(batches[0]); enqueue(batches[1]); enqueue(batches[0])       # the slot layout grows to its final size (a growth synchronises)
+        ctx.synchronize()
         for first, second in ((0, 1), (1, 0), (0, 1), (1, 0)):
             enqueue(batches[first]); enqueue(batches[second])
             prev, _ = ctx.fetch_detections(batches[first][4], previous=True)
