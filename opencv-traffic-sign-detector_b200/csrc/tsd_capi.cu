@@ -636,15 +636,16 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
                 CU(cudaFuncSetAttribute(k5_gram_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 c->attr_gram = true;
             }
-            gram_done = todo;
+            gram_done = todo;                                // [count, items ...] for k5_pairs; behind it the same for k5_gram_big
+            int32_t* big = todo + todo_capacity(nframes, max_n);
             CU(cudaMemsetAsync(gram_done, 0, 4, c->cur));
+            CU(cudaMemsetAsync(big, 0, 4, c->cur));
             k5_gram_kernel<<<nframes, kGramWarps * 32, sizeof(GramSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, P.hist_tol,
-                                                                                   P.hist_lo, M, cost, gram_done, 2 * c->sm_count);
+                                                                                   P.hist_lo, M, cost, gram_done, big, 2 * c->sm_count);
             TRY(check_launch(c, "k5_gram"));
-            if (max_n > kGramBM) {
-                const int nbk = (max_n + kGramBM - 1) / kGramBM, ppf = nbk * (nbk + 1) / 2;
-                k5_gram_big_kernel<<<nframes * ppf, kBigWarps * 32, sizeof(GramBigSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW, ppf,
-                                                                                                  P.hist_tol, P.hist_lo, M, cost, gram_done);
+            if (max_n > kGramBM) {                           // persistent CTAs (one per SM: 148 KB of shared memory) walk the list k5_gram wrote
+                k5_gram_big_kernel<<<c->sm_count, kBigWarps * 32, sizeof(GramBigSmem), c->cur>>>(entries, meta, E_T, e_stride, offsets, nframes, P.es, RW,
+                                                                                                 P.hist_tol, P.hist_lo, M, cost, gram_done, big);
                 TRY(check_launch(c, "k5_gram_big"));
             }
         }
@@ -790,7 +791,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     for (int f = 0; f < nframes; f++) max_n = offsets[f + 1] - offsets[f] > max_n ? offsets[f + 1] - offsets[f] : max_n;
     c->order_off = 0;
     TRY(ensure(c, c->b_pairs, (size_t)(n > 0 ? n : 1) * 2 * pair_row_words(max_n) * sizeof(uint32_t)));
-    TRY(ensure(c, c->b_gramdone, todo_capacity(nframes, max_n) * 4));
+    TRY(ensure(c, c->b_gramdone, 2 * todo_capacity(nframes, max_n) * 4));
     TRY(ensure(c, c->b_order, (size_t)(nframes + 2) * 4));
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
                  tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (int32_t*)c->b_gramdone.p, (float*)den, n));
@@ -1306,7 +1307,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     tsd_ctx::Batch B;
     B.nframes = nframes; B.nbcap = nb; B.nboxes = nb;
     const size_t need_w = (((size_t)(nb > 0 ? nb : 1) + 3) & ~(size_t)3);
-    const size_t need_todo = todo_capacity(nframes, max_boxes_per_frame);
+    const size_t need_todo = 2 * todo_capacity(nframes, max_boxes_per_frame);      // work lists of k5_pairs and k5_gram_big
     size_t cap = need_w, fcap = (size_t)nframes + 2, mwords = need_w * 2 * RW, m_off = 0, todo_words = need_todo, todo_off = 0;
     const bool ov = c->overlap && !c->profiling;
     if (ov) {                                                // this batch lives in slot `slot` of doubled scratch buffers

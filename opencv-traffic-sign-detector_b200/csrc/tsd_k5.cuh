@@ -601,15 +601,25 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
                                                                     const float* __restrict__ E_T, int64_t e_stride,
                                                                     const int32_t* __restrict__ offsets, int nframes, int es, int RW,
                                                                     double tol, double lo, uint32_t* __restrict__ M,
-                                                                    int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo, int prefetch_ahead) {
+                                                                    int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo, int32_t* __restrict__ big,
+                                                                    int prefetch_ahead) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GramSmem& S = *reinterpret_cast<GramSmem*>(smem_raw);
     const int f = blockIdx.x;
     if (f >= nframes) return;
     const int base = offsets[f], n = offsets[f + 1] - base;
     if (n < 2 || n > RW * 32) return;                       // (CTA-uniform) nothing to classify / the general fold's frame
-    if (n > kGramBM) {
-        return;                                              // k5_gram_big's frame (block pairs)
+    if (n > kGramBM) {                                      // k5_gram_big's frame: its block pairs (I, J), J <= I, go to that kernel's work list
+        const int nbk = (n + kGramBM - 1) / kGramBM, np = nbk * (nbk + 1) / 2;
+        __shared__ int s_pos;
+        if (threadIdx.x == 0) s_pos = atomicAdd(big, np);
+        __syncthreads();
+        for (int q = threadIdx.x; q < np; q += blockDim.x) {
+            int I = 0, r = q;
+            while (r > I) { r -= I + 1; I++; }
+            big[1 + s_pos + q] = (f << 8) | (I << 4) | r;
+        }
+        return;
     }
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     // scatter role: group = tid / 4 owns row `group` and (frames of more than 96 windows, groups 0..31) row group + 96
@@ -848,19 +858,17 @@ static_assert(kGramBM * kGramIPitch * 4 <= 2 * kGramBM * kGramPitch, "result mat
 
 __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
                                                                        const float* __restrict__ E_T, int64_t e_stride,
-                                                                       const int32_t* __restrict__ offsets, int nframes, int es, int RW, int pairs_per_frame,
+                                                                       const int32_t* __restrict__ offsets, int nframes, int es, int RW,
                                                                        double tol, double lo, uint32_t* __restrict__ M,
-                                                                       int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo) {
+                                                                       int32_t* __restrict__ frame_cost, int32_t* __restrict__ todo, const int32_t* __restrict__ big) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GramBigSmem& S = *reinterpret_cast<GramBigSmem*>(smem_raw);
-    const int f = blockIdx.x / pairs_per_frame;
-    int q = blockIdx.x - f * pairs_per_frame;
-    if (f >= nframes) return;
-    int I = 0;
-    while (q > I) { q -= I + 1; I++; }                       // pair index -> (I, J), J <= I: 0:(0,0) 1:(1,0) 2:(1,1) 3:(2,0) ...
-    const int J = q;
+    const int nitems = big[0];                               // written by k5_gram (the launch before this one)
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    __syncthreads();                                         // (the previous item is complete: shared memory is free)
+    const int item = big[1 + it];
+    const int f = item >> 8, I = (item >> 4) & 15, J = item & 15;
     const int base = offsets[f], n = offsets[f + 1] - base;
-    if (n <= kGramBM || n > RW * 32 || I * kGramBM >= n) return;             // (CTA-uniform) k5_gram's frame / the general fold's / no such block
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const bool diag = I == J;
     const int rowsI = min(kGramBM, n - I * kGramBM), rowsJ = min(kGramBM, n - J * kGramBM);
@@ -889,7 +897,7 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const ui
     __syncthreads();
     if (S.nbig > kBigMaxRows) {                              // (CTA-uniform) flat frames: this block pair goes to k5_pairs
         if (tid == 0) todo[1 + atomicAdd(todo, 1)] = todo_item(f, I, J);
-        return;
+        continue;
     }
     // scatter role: warp w owns local rows w, w + 16, ... (16 rows); lane = entry within the row's chunk range
     uint32_t pre[kBigRowsPerWarp];
@@ -1050,6 +1058,7 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const ui
                 if (bm && frame_cost) atomicAdd(frame_cost + f, __popc(bm));
             }
         }
+    }
     }
 }
 
