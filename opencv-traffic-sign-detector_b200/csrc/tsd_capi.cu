@@ -60,6 +60,8 @@ struct tsd_ctx {
     cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     cudaStream_t os[2] = {nullptr, nullptr};                                // per slot: the chain's stream
     DevBuf b_summary, b_order, b_gramdone;
+    unsigned* d_tickets = nullptr;           // zero-initialised counters of the last-CTA-done scans: [slot 0 | slot 1 | stage calls] x 8
+    int ticket_base = 16;
     size_t order_off = 0;                    // offset (ints) of the current batch inside b_order
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -97,11 +99,20 @@ struct tsd_ctx {
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
     int ev_used = 0;
+    // CUDA graphs of the chain (TSD_GRAPH=0 turns them off): a batch shape seen twice in a row is captured once and replayed from then
+    // on -- the chains of small batches (real MSER frames) are bound by launch latency.  `gen` counts every event that changes a
+    // pointer baked into a captured kernel argument (scratch reallocation, slot layout, model state) and is part of the key.
+    struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t stamp = 0; };
+    std::vector<GraphEntry> graphs;
+    std::vector<uint64_t> seen_key;
+    uint64_t gen = 0, graph_clock = 0;
+    int use_graph = 1;
 };
 
 static int ensure(tsd_ctx* c, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return TSD_OK;
     if (b.p) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    c->gen++;                                                // captured graphs hold the old pointer
     size_t want = bytes + bytes / 4 + 256;
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
@@ -180,6 +191,7 @@ static int create_impl(tsd_ctx* c, int device) {
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
+    { const char* e = getenv("TSD_GRAPH"); if (e) c->use_graph = atoi(e) != 0; }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -206,6 +218,8 @@ static int create_impl(tsd_ctx* c, int device) {
     CU(cudaMalloc(&c->d_tab, sizeof(Tables)));
     CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tmpl, sizeof(ScoreTemplates)));
+    CU(cudaMalloc(&c->d_tickets, 24 * sizeof(unsigned)));
+    CU(cudaMemset(c->d_tickets, 0, 24 * sizeof(unsigned)));
     {   // default gamma table: ((i / 255) ** (1 / 2)) * 255 truncated to uint8 (DET:602-603); the Python wrapper overrides it with the
         // table the reference's own expression gives in-process
         uint8_t gt[256];
@@ -290,9 +304,10 @@ int tsd_destroy(tsd_ctx* c) {
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    void* ptrs[] = {c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    void* ptrs[] = {c->d_tickets, c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TSD_OK;
@@ -419,6 +434,7 @@ int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
     CU(cudaMemcpy(c->d_simtab, f, sizeof(double) * n, cudaMemcpyHostToDevice));
     c->simtab_n = n;
     c->h_simtab.assign(f, f + n);
+    c->gen++;
     return TSD_OK;
 }
 
@@ -434,6 +450,7 @@ int tsd_set_lda(tsd_ctx* c, const double* W, const double* b, int nfeat) {
     CU(cudaMemcpy(c->d_ldaW, W, sizeof(double) * nfeat * 6, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_ldab, b, sizeof(double) * 6, cudaMemcpyHostToDevice));
     c->lda_nfeat = nfeat;
+    c->gen++;
     return TSD_OK;
 }
 
@@ -455,6 +472,7 @@ int tsd_set_knn(tsd_ctx* c, const double* xbar, const double* scalings, int nfea
     CU(cudaMemcpy(c->d_Zt, Ztrain, sizeof(double) * (size_t)ntrain * 6, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_yt, ytrain, sizeof(int32_t) * ntrain, cudaMemcpyHostToDevice));
     c->knn_nfeat = nfeat; c->knn_ntrain = ntrain; c->knn_k = k;
+    c->gen++;
     return TSD_OK;
 }
 
@@ -518,18 +536,13 @@ static inline int pair_row_words(int max_n) {
     return ((max_n > 1 ? max_n : 1) + 31) / 32;
 }
 
-static int dev_scan(tsd_ctx* c, const int32_t* counts, int n, int32_t* offsets) {
-    scan_offsets_kernel<<<1, 1024, 0, c->cur>>>(counts, n, offsets);
-    return check_launch(c, "scan_offsets");
-}
-
-// K1 count + scan + compact -> coords/win_frame/win_offsets in context scratch or caller buffers
+// K1 count (+ scan by its last CTA) + compact -> coords/win_frame/win_offsets in context scratch or caller buffers
 static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* box_offsets, int nframes, int H, int W, double enlarge,
                              int32_t* counts, int32_t* win_offsets, int32_t* coords, int32_t* win_frame) {
     const double pm1 = enlarge - 1.0;
-    k1_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->cur>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, counts);
+    k1_count_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->cur>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, counts,
+                                                                           win_offsets, c->d_tickets + c->ticket_base);
     TRY(check_launch(c, "k1_count"));
-    TRY(dev_scan(c, counts, nframes, win_offsets));
     k1_compact_kernel<<<cdiv((int64_t)nframes * 32, 128), 128, 0, c->cur>>>((const int4*)boxes, box_offsets, nframes, H, W, pm1, c->cfg.aspect_lo, c->cfg.aspect_hi, win_offsets, (int4*)coords, win_frame);
     return check_launch(c, "k1_compact");
 }
@@ -599,7 +612,7 @@ static inline size_t todo_capacity(int nframes, int max_n) {
 
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, uint32_t* M, int32_t* todo, float* E_T, int64_t e_stride) {
+                    int max_n, uint32_t* M, int32_t* todo, float* E_T, int64_t e_stride, int32_t* surv_offsets) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
@@ -607,7 +620,7 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     P.E_T = E_T; P.e_stride = e_stride;
     P.hist_tol = hist_tol; P.hist_lo = hist_tol * c->cfg.merge_factor;      // tolerance * 0.8823 in f64 (DET:217)
     P.coord_tol = coord_tol; P.coord_lo = coord_tol * c->cfg.merge_factor;
-    if (nframes == 0) return TSD_OK;
+    if (nframes == 0) { if (surv_offsets) CU(cudaMemsetAsync(surv_offsets, 0, 4, c->cur)); return TSD_OK; }
     // max_n is only an upper bound (raw boxes per frame); frames with more than 1024 aspect-passing windows are flagged by
     // the warp-per-frame fold (out_count = -1) and redone by the general block-synchronous fold below
     const int RW = pair_row_words(max_n);
@@ -667,7 +680,7 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     TRY(npx <= 640 ? launch_folds<640>(c, 0, P, nframes, M, RW, cut, cost, max_n) : launch_folds<1024>(c, 1, P, nframes, M, RW, cut, cost, max_n));
     // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
-    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1);
+    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1, surv_offsets, c->d_tickets + c->ticket_base + 1);
     return check_launch(c, "k5_fold");
 }
 
@@ -794,8 +807,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     TRY(ensure(c, c->b_gramdone, 2 * todo_capacity(nframes, max_n) * 4));
     TRY(ensure(c, c->b_order, (size_t)(nframes + 2) * 4));
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
-                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (int32_t*)c->b_gramdone.p, (float*)den, n));
-    TRY(dev_scan(c, (int32_t*)dcnt, nframes, (int32_t*)dooff));
+                 tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (int32_t*)c->b_gramdone.p, (float*)den, n, (int32_t*)dooff));
     if (nframes) {
         k5_gather_kernel<<<nframes, 128, 0, c->cur>>>((uint8_t*)dw, (int4*)dc, (int32_t*)doff, (int32_t*)dlist, (int32_t*)dooff, nframes, nbytes, ws,
                                                          (uint8_t*)dow, (int4*)doc, nullptr);
@@ -1223,8 +1235,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap));
-    TRY(dev_scan(c, survcnt, cf, survoff));
+                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap, survoff));
     k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
     TRY(check_launch(c, "k5_gather"));
     mark(c, "k5_fold");
@@ -1274,13 +1285,58 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
         label_emit_kernel<<<cdiv(cap, 256), 256, 0, c->cur>>>(id, d_nsurv, nb, emit);
         TRY(check_launch(c, "label_emit"));
     }
-    det_count_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, survoff, cf, detcnt);
+    det_count_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, survoff, cf, detcnt, detoff, c->d_tickets + c->ticket_base + 2);
     TRY(check_launch(c, "det_count"));
-    TRY(dev_scan(c, detcnt, cf, detoff));
     det_write_kernel<<<cdiv((int64_t)cf * 32, 128), 128, 0, c->cur>>>(emit, id, hund, (int4*)coords, slots, survoff, detoff, cf, (int)cap, det,
                                                                         winoff + cf, survoff + cf, (int32_t*)c->b_summary.p + 4 * B.sidx);
     TRY(check_launch(c, "det_write"));
     mark(c, "detections");
+    return TSD_OK;
+}
+
+// One batch through the chain on c->cur: eagerly the first time a batch shape is seen, captured into a CUDA graph the second time,
+// replayed from then on (at most 8 graphs are kept, least recently used goes first).
+static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+                     const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo) {
+    if (!c->use_graph || c->profiling)
+        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+    const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
+                                       (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
+                                       (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram};
+    c->graph_clock++;
+    for (auto& g : c->graphs)
+        if (g.key == key) {
+            CU(cudaGraphLaunch(g.exec, c->cur));
+            g.stamp = c->graph_clock;
+            c->launches += g.launches;
+            return TSD_OK;
+        }
+    if (c->seen_key != key) {                                // first sighting: run it eagerly (one-off calls never pay for an instantiation)
+        c->seen_key = key;
+        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+    }
+    c->seen_key.clear();
+    const int64_t l0 = c->launches;
+    CU(cudaStreamBeginCapture(c->cur, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(c->cur, &graph);
+    if (rc != TSD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ee != cudaSuccess) return fail(TSD_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
+    tsd_ctx::GraphEntry g;
+    g.key = key; g.launches = c->launches - l0; g.stamp = c->graph_clock;
+    const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(TSD_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+    if (c->graphs.size() >= 8) {
+        size_t lru = 0;
+        for (size_t i = 1; i < c->graphs.size(); i++) if (c->graphs[i].stamp < c->graphs[lru].stamp) lru = i;
+        cudaGraphExecDestroy(c->graphs[lru].exec);
+        c->graphs.erase(c->graphs.begin() + lru);
+    }
+    c->graphs.push_back(g);
+    CU(cudaGraphLaunch(g.exec, c->cur));
     return TSD_OK;
 }
 
@@ -1324,6 +1380,7 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
             if (sf > c->slot_fcap) c->slot_fcap = sf;
             if (RW > c->slot_rw) c->slot_rw = RW;
             if (need_todo > c->slot_todo) c->slot_todo = need_todo;
+            c->gen++;
         }
         B.wo = (size_t)c->slot * c->slot_cap;
         B.fo = (int)((size_t)c->slot * c->slot_fcap);
@@ -1376,14 +1433,16 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         CU(cudaStreamWaitEvent(c->os[sl], c->ev_slot_fork[sl], 0));
         TRY(join_pending(c));                                // the PREVIOUS batch: the context's stream waits for it only now, after this batch's fork
         c->cur = c->os[sl];
-        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
+        c->ticket_base = 8 * sl;
+        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
         CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
         c->pending_join = sl;
     } else {
         c->cur = c->stream;
-        rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
+        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
     }
     c->cur = c->stream;
+    c->ticket_base = 16;
     if (rc != TSD_OK) { c->prev.valid = false; return rc; }
     B.valid = true;
     c->last = B;

@@ -93,6 +93,47 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// ---- exclusive scan of per-frame counts by the LAST CTA of a grid to finish -----------------------------------------------------
+// The per-frame counts of a stage (aspect-passing windows, survivors, detections) are turned into CSR offsets by whichever CTA of
+// the producing kernel retires last, instead of by a separate single-CTA launch: the chains of small batches (real MSER frames:
+// ~35 boxes per frame) are bound by launch latency, not by work.  `ticket` is a zero-initialised counter that is reset on the way out.
+__device__ __forceinline__ void block_scan_offsets(const int32_t* counts, int n, int32_t* offsets) {
+    __shared__ int32_t s_wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b = min(n, tid * per), e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += __ldcg(counts + i);   // (written by other SMs in this launch: not through L1)
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int v = lane < nw ? s_wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+        s_wsum[lane] = v;
+    }
+    __syncthreads();
+    int run = (wid ? s_wsum[wid - 1] : 0) + x - sum;
+    for (int i = b; i < e; i++) { offsets[i] = run; run += __ldcg(counts + i); }
+    if (tid == (int)blockDim.x - 1) offsets[n] = s_wsum[nw - 1];
+}
+
+// Call at the very end of a kernel, by all threads of every CTA (after the CTA's counts are written).
+__device__ __forceinline__ void scan_by_last_block(const int32_t* counts, int n, int32_t* offsets, unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    block_scan_offsets(counts, n, offsets);
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 // =====================================================================================================
 // K1  makeWindowBiggerOrDiscardFakeDetections  (DET:155-174 = REC:88-107), SURVEY A.1.  f64, no FMA.
 // =====================================================================================================
@@ -120,47 +161,21 @@ __global__ void k1_expand_kernel(const int4* __restrict__ boxes, int n, double p
 }
 
 // per frame: count of aspect-passing boxes whose (frame-clipped) crop is not empty.  One warp per frame.
+// The last CTA to finish turns the counts into the CSR offsets of the windows (win_offsets [nframes + 1]).
 __global__ void k1_count_kernel(const int4* __restrict__ boxes, const int32_t* __restrict__ box_offsets, int nframes,
-                                int H, int W, double pm1, double alo, double ahi, int32_t* __restrict__ counts) {
+                                int H, int W, double pm1, double alo, double ahi, int32_t* __restrict__ counts,
+                                int32_t* __restrict__ win_offsets, unsigned* __restrict__ ticket) {
     int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (f >= nframes) return;
-    int b0 = box_offsets[f], b1 = box_offsets[f + 1], cnt = 0;
-    for (int i = b0 + lane; i < b1; i += 32) {
-        int4 c;
-        if (expand_box(boxes[i], pm1, alo, ahi, c) && min(c.z, W) > min(c.x, W) && min(c.w, H) > min(c.y, H)) cnt++;
-    }
-    cnt = warp_sum_i(cnt);
-    if (lane == 0) counts[f] = cnt;
-}
-
-// exclusive scan of counts[0..n) -> offsets[0..n]; single CTA (n = number of frames; small)
-__global__ void scan_offsets_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
-    __shared__ int32_t wsum[32];
-    __shared__ int32_t carry;
-    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int i = base + tid;
-        int v = i < n ? counts[i] : 0, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wsum[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int s = lane < nw ? wsum[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-            wsum[lane] = s;
+    if (f < nframes) {
+        int b0 = box_offsets[f], b1 = box_offsets[f + 1], cnt = 0;
+        for (int i = b0 + lane; i < b1; i += 32) {
+            int4 c;
+            if (expand_box(boxes[i], pm1, alo, ahi, c) && min(c.z, W) > min(c.x, W) && min(c.w, H) > min(c.y, H)) cnt++;
         }
-        __syncthreads();
-        int pre = carry + (wid ? wsum[wid - 1] : 0) + x - v;
-        if (i < n) offsets[i] = pre;
-        __syncthreads();
-        if (tid == blockDim.x - 1) carry = pre + v;
-        __syncthreads();
+        cnt = warp_sum_i(cnt);
+        if (lane == 0) counts[f] = cnt;
     }
-    if (tid == 0) offsets[n] = carry;
+    scan_by_last_block(counts, nframes, win_offsets, ticket);
 }
 
 // order-preserving compaction: coords of passing boxes -> coords[win_offsets[f] + rank], win_frame[...] = f.
@@ -808,7 +823,10 @@ __device__ void apply_deletions_block(FoldSmem& sm, const FoldParams& P, int32_t
 // One CTA per frame.  Sequential over the frame's items (the fold order is the semantics); each item is compared
 // with ALL current survivors in parallel, the classes are scanned in list order up to the first merge, the merge is
 // applied and only the survivors after it are re-evaluated with the updated item (speculate-then-scan).
-__global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int nframes, int only_flagged) {
+// surv_offsets (optional): the last CTA to finish turns out_count [nframes] (written by this kernel and by the per-warp / per-CTA
+// folds launched before it) into the CSR offsets of the survivors.
+__global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int nframes, int only_flagged, int32_t* __restrict__ surv_offsets,
+                                                               unsigned* __restrict__ ticket) {
     __shared__ FoldSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = kFoldThreads >> 5;
     const int nbytes = P.npx * 3;
@@ -950,6 +968,7 @@ __global__ void __launch_bounds__(kFoldThreads) k5_fold_kernel(FoldParams P, int
         if (tid == 0) P.out_count[f] = sm.S;
         __syncthreads();
     }
+    if (surv_offsets) scan_by_last_block(P.out_count, nframes, surv_offsets, ticket);
 }
 
 // gather survivors (list -> compact CSR output).  One CTA per frame.
@@ -1405,13 +1424,15 @@ struct DetRec { int32_t frame, x1, y1, x2, y2, id, hundredths, reserved; };
 
 // per-frame count of emitted survivors (survivors are CSR by surv_offsets); one warp per frame
 __global__ void det_count_kernel(const uint8_t* __restrict__ emit, const int32_t* __restrict__ surv_offsets, int nframes,
-                                 int32_t* __restrict__ counts) {
+                                 int32_t* __restrict__ counts, int32_t* __restrict__ det_offsets, unsigned* __restrict__ ticket) {
     int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (f >= nframes) return;
-    int c = 0;
-    for (int i = surv_offsets[f] + lane; i < surv_offsets[f + 1]; i += 32) c += emit[i] != 0;
-    c = warp_sum_i(c);
-    if (lane == 0) counts[f] = c;
+    if (f < nframes) {
+        int c = 0;
+        for (int i = surv_offsets[f] + lane; i < surv_offsets[f + 1]; i += 32) c += emit[i] != 0;
+        c = warp_sum_i(c);
+        if (lane == 0) counts[f] = c;
+    }
+    scan_by_last_block(counts, nframes, det_offsets, ticket);      // the last CTA to finish: CSR offsets of the records
 }
 
 __global__ void det_write_kernel(const uint8_t* __restrict__ emit, const int32_t* __restrict__ id, const int32_t* __restrict__ hundredths,
