@@ -512,15 +512,18 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         return dt, edet, ecounts
+    ctx.stat_staged_bytes(reset=True)
     e_dt, edet, ecounts = e2e_leg(hf, args.e2e_steps)
+    staged = ctx.stat_staged_bytes(reset=True) // (args.e2e_steps + 2)          # (2 warm-up calls inside e2e_leg): bytes per call, counted on the device
     alg_e, _ = algorithmic_bytes(hb, ho, ecounts)
     roi_bytes = int(alg_e["k2_crop_resize"] - int(ecounts[1]) * 3 * D * D)      # source bytes of the candidate ROIs (section 8(d) formula)
-    e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(roi_bytes + hb.nbytes + ho.nbytes),
+    e2e = {"value": world * Fe * NBOX / e_dt, "unit": "windows/s", "h2d_bytes_per_step": int(staged + hb.nbytes + ho.nbytes),
            "d2h_bytes_per_step": int(len(edet) * 32 + 16), "frames_per_step": Fe, "ms_per_step": e_dt * 1e3,
            "frames_per_sec": world * Fe / e_dt, "host_input_bytes_per_step": int(hf.nbytes + hb.nbytes + ho.nbytes),
-           "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST) on PAGE-LOCKED host frames: K2 reads them in place over PCIe, so "
-                  "only the candidate ROIs cross the bus -- h2d_bytes_per_step = algorithmic ROI bytes (SURVEY 8(d)) + boxes; 32-byte "
-                  "sector granularity and re-fetches of overlapping ROIs add to it (profiles/README.md); detection records D2H"}
+           "roi_bytes_algorithmic": roi_bytes, "h2d_gbs": (staged + hb.nbytes + ho.nbytes) / e_dt / 1e9,
+           "api": "Context.detect_frames (tsd_detect_frames, TSD_MEM_HOST) on PAGE-LOCKED host frames: every 32-byte sector the candidate ROIs "
+                  "touch is copied over PCIe once per batch into a device mirror (stage_mark + stage_copy kernels), then the chain runs on the "
+                  "mirror; h2d_bytes_per_step = those bytes (counted by the copy kernel) + boxes; detection records D2H"}
     if not args.no_e2e and world == 1:
         # the same call on PAGEABLE frames (what cv2.imread returns): whole frames are copied in double-buffered chunks
         pg = np.array(hf[:min(Fe, 256)], copy=True)

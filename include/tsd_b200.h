@@ -84,8 +84,8 @@ TSD_API int tsd_synchronize(tsd_ctx *ctx);
  * tsd_fetch_detections is called: tsd_flush makes tsd_stream() wait for everything enqueued so far without blocking the host. */
 TSD_API int tsd_flush(tsd_ctx *ctx);
 /* Page-lock a caller-owned host buffer (cudaHostRegister, mapped).  tsd_detect_frames with TSD_MEM_HOST reads page-locked
- * frames IN PLACE over PCIe (only the candidate ROIs are transferred); pageable frames are copied whole, in chunks that
- * overlap the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */
+ * frames IN PLACE over PCIe (only the 32-byte sectors the candidate ROIs touch are transferred, each once per batch, into a
+ * device-resident mirror of the frames); pageable frames are copied whole, in chunks that overlap the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */
 TSD_API int tsd_host_register(void *p, int64_t bytes);
 TSD_API int tsd_host_unregister(void *p);
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
@@ -250,6 +250,10 @@ TSD_API int tsd_stat_hist_entries(tsd_ctx *ctx, int64_t *total);
  * integer dot product -- cv2.compareHist's value within 2e-6 of a threshold of DET/source.py:203-217 -- and was therefore computed
  * with the exact float64 evaluation.  reset != 0 zeroes the counter.  Synchronises. */
 TSD_API int tsd_stat_unsure_pairs(tsd_ctx *ctx, int64_t *total, int reset);
+
+/* Measurement helper: bytes that crossed PCIe host -> device for the frames of tsd_detect_frames calls on page-locked host memory
+ * (every 32-byte sector the candidate ROIs of a batch touch is copied once), since process start / the last reset.  Synchronises. */
+TSD_API int tsd_stat_staged_bytes(tsd_ctx *ctx, int64_t *total, int reset);
 
 /* Device-side stage timing: CUDA events are recorded between the stages of every tsd_enqueue_frames call made after
  * tsd_set_profiling(ctx, 1); tsd_stage_times synchronises and returns, per stage name, the time summed over those

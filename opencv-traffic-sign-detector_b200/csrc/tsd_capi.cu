@@ -66,7 +66,11 @@ struct tsd_ctx {
     cudaStream_t copy_stream = nullptr;      // host-buffer calls: H2D of the next chunk of frames overlaps the chain on `stream`
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     DevBuf b_stage[2], b_hboxes, b_hoff;
-    int zero_copy = 1;                       // K2 reads page-locked host frames in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
+    int zero_copy = 1;                       // page-locked host frames are read in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
+    int stage_rois = 1;                      // ... by the mark + copy kernels, each touched 32-byte sector once, into a device mirror K2 reads
+                                             // (TSD_STAGE=0: K2 itself gathers from host memory, round 1's path)
+    DevBuf b_mirror, b_stagemap;
+    unsigned long long* d_staged = nullptr;  // bytes the staging copy moved over PCIe (tsd_stat_staged_bytes)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
     tsd_config cfg;
     int64_t launches = 0;
@@ -188,6 +192,7 @@ static int create_impl(tsd_ctx* c, int device) {
     }
     { const char* e = getenv("TSD_OVERLAP"); if (e) c->overlap = atoi(e) != 0; }
     { const char* e = getenv("TSD_ZEROCOPY"); if (e) c->zero_copy = e[0] != '0'; }
+    { const char* e = getenv("TSD_STAGE"); if (e) c->stage_rois = e[0] != '0'; }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
@@ -219,6 +224,8 @@ static int create_impl(tsd_ctx* c, int device) {
     CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tmpl, sizeof(ScoreTemplates)));
     CU(cudaMalloc(&c->d_tickets, 24 * sizeof(unsigned)));
+    CU(cudaMalloc(&c->d_staged, 8));
+    CU(cudaMemset(c->d_staged, 0, 8));
     CU(cudaMemset(c->d_tickets, 0, 24 * sizeof(unsigned)));
     {   // default gamma table: ((i / 255) ** (1 / 2)) * 255 truncated to uint8 (DET:602-603); the Python wrapper overrides it with the
         // table the reference's own expression gives in-process
@@ -294,7 +301,7 @@ int tsd_destroy(tsd_ctx* c) {
     DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores,
-                      &c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
+                      &c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_mirror, &c->b_stagemap, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
         if (c->ev_slot_fork[i]) cudaEventDestroy(c->ev_slot_fork[i]);
@@ -304,7 +311,7 @@ int tsd_destroy(tsd_ctx* c) {
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    void* ptrs[] = {c->d_tickets, c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
+    void* ptrs[] = {c->d_staged, c->d_tickets, c->d_tab, c->d_tmpl, c->d_mlut, c->d_gamma, c->d_simtab, c->d_ldaW, c->d_ldab, c->d_xbar, c->d_scal, c->d_Zt, c->d_yt};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -422,7 +429,7 @@ int tsd_set_templates(tsd_ctx* c, const uint8_t* red6, const uint8_t* blue6) {
 }
 
 int tsd_set_similarity_table(tsd_ctx* c, const double* f, int n) {
-    if (!c || !f || n < 2) return fail(TSD_E_INVALID, "bad argument");
+    if (!c || !f || n < 2 || n > (1 << 30)) return fail(TSD_E_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
     // the kernel treats d2 >= n as "no action": require f(n-1) small enough that sqrt(f) < tol*merge_factor for both passes
     if (sqrt(f[n - 1]) >= c->cfg.coord_tol * c->cfg.merge_factor) return fail(TSD_E_INVALID, "similarity table too short: f(%d)=%g", n - 1, f[n - 1]);
@@ -774,6 +781,8 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     CU(cudaSetDevice(c->device));
     const int n = offsets[nframes], npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     if (n && (!windows || !coords)) return fail(TSD_E_INVALID, "NULL argument");
+    for (int64_t i = 0; i < (int64_t)n * 4; i++)             // (the corner distances are evaluated in 32-bit arithmetic)
+        if (coords[i] < 0 || coords[i] >= (1 << 30)) return fail(TSD_E_INVALID, "coordinate %d of window %d out of range [0, 2^30)", coords[i], (int)(i / 4));
     Stage s(c);
     void *dw, *dc, *doff, *dent, *dmeta, *dlist, *dflags, *dcnt, *dooff, *dow, *doc, *den;
     TRY(s.alloc(&dw, (size_t)n * ws));                       // internal layout: 16-byte aligned windows, zero pad
@@ -1206,7 +1215,8 @@ int tsd_knn_predict(tsd_ctx* c, const float* X, int n, double* Z, int32_t* label
 // B.fo = first entry in the per-frame scratch arrays (nframes + 1 entries), B.nbcap = upper bound of the batch's windows;
 // M = the batch's rows of the pair-class bit matrix.
 static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-                         const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo) {
+                         const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo,
+                         const uint8_t* host_src = nullptr /* page-locked host frames (device pointer): staged into d_frames (the mirror) after K1 */) {
     const int D = c->cfg.window, npx = D * D, nbytes = npx * 3, ws = win_stride(npx, 3), es = ent_stride(npx);
     const int ms = (npx + 15) & ~15, NW = (npx + 31) >> 5;     // mask byte stride (padded), mask words
     const int cf = B.nframes, nb = B.nbcap, fo = B.fo;
@@ -1228,6 +1238,21 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
     TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
     mark(c, "k1_expand_filter");
+    if (host_src) {                                          // every 32-byte sector the ROIs touch crosses PCIe once, into the mirror
+        const int wpr = (cdiv((int64_t)W * 3, 32) + 31) / 32;
+        const int64_t nwords = (int64_t)cf * H * wpr;
+        CU(cudaMemsetAsync(c->b_stagemap.p, 0, (size_t)nwords * 4, c->cur));
+        if (nb > 0) {
+            stage_mark_kernel<<<cdiv((int64_t)nb * 32, 128), 128, 0, c->cur>>>((const int4*)coords, winframe, d_nwin, nb, H, W, D, wpr, (uint32_t*)c->b_stagemap.p);
+            TRY(check_launch(c, "stage_mark"));
+            int g = cdiv(nwords, 256);
+            if (g > c->sm_count * 8) g = c->sm_count * 8;
+            stage_copy_kernel<<<g, 256, 0, c->cur>>>(host_src, row_stride, frame_stride, H, W * 3, wpr, nwords, (const uint32_t*)c->b_stagemap.p,
+                                                     (uint8_t*)d_frames, c->d_staged);
+            TRY(check_launch(c, "stage_copy"));
+        }
+        mark(c, "stage_h2d");
+    }
     // K2 (DET:123-124)
     TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
     mark(c, "k2_crop_resize");
@@ -1297,13 +1322,14 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
 // One batch through the chain on c->cur: eagerly the first time a batch shape is seen, captured into a CUDA graph the second time,
 // replayed from then on (at most 8 graphs are kept, least recently used goes first).
 static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-                     const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo) {
+                     const int32_t* d_boxes, const int32_t* d_box_offsets, int maxb, const tsd_ctx::Batch& B, uint32_t* M, int32_t* todo,
+                     const uint8_t* host_src) {
     if (!c->use_graph || c->profiling)
-        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo, host_src);
     const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
                                        (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
                                        (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
-                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram};
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src};
     c->graph_clock++;
     for (auto& g : c->graphs)
         if (g.key == key) {
@@ -1314,12 +1340,12 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
         }
     if (c->seen_key != key) {                                // first sighting: run it eagerly (one-off calls never pay for an instantiation)
         c->seen_key = key;
-        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+        return enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo, host_src);
     }
     c->seen_key.clear();
     const int64_t l0 = c->launches;
     CU(cudaStreamBeginCapture(c->cur, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo);
+    const int rc = enqueue_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, maxb, B, M, todo, host_src);
     cudaGraph_t graph = nullptr;
     const cudaError_t ee = cudaStreamEndCapture(c->cur, &graph);
     if (rc != TSD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1340,8 +1366,11 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
     return TSD_OK;
 }
 
-int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
-                       const int32_t* d_boxes, const int32_t* d_box_offsets, int nb, int max_boxes_per_frame) {
+// host_src != NULL: d_frames is ignored, the frames are page-locked host memory (host_src = their device pointer) and are staged
+// ROI sector by ROI sector into the context's mirror, which the chain then reads.
+static int enqueue_impl(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                        const int32_t* d_boxes, const int32_t* d_box_offsets, int nb, int max_boxes_per_frame, const uint8_t* host_src) {
+    if (host_src) d_frames = host_src;                       // (argument checks below)
     if (!c || !d_frames || !d_box_offsets || nframes < 1 || nb < 0 || H < 1 || W < 1) return fail(TSD_E_INVALID, "bad argument");
     if (mode != TSD_RUN_DETECT && mode != TSD_RUN_RECOGNIZE) return fail(TSD_E_INVALID, "bad mode %d", mode);
     if (row_stride < (int64_t)W * 3 || frame_stride < row_stride * (H - 1) + (int64_t)W * 3) return fail(TSD_E_INVALID, "bad strides");
@@ -1424,6 +1453,12 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(ensure(c, c->b_hog, cap * TSD_HOG_LEN * 4));
     }
     TRY(ensure(c, c->b_pairs, mwords * sizeof(uint32_t)));
+    if (host_src) {
+        const int wpr = (cdiv((int64_t)W * 3, 32) + 31) / 32;
+        TRY(ensure(c, c->b_mirror, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3 + 64));
+        TRY(ensure(c, c->b_stagemap, (size_t)nframes * H * wpr * 4));
+        d_frames = (const uint8_t*)c->b_mirror.p;
+    }
     uint32_t* M = (uint32_t*)c->b_pairs.p + m_off;
     int32_t* todo = (int32_t*)c->b_gramdone.p + todo_off;
     int rc = TSD_OK;
@@ -1434,12 +1469,12 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
         TRY(join_pending(c));                                // the PREVIOUS batch: the context's stream waits for it only now, after this batch's fork
         c->cur = c->os[sl];
         c->ticket_base = 8 * sl;
-        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
+        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo, host_src);
         CU(cudaEventRecord(c->ev_join[sl], c->os[sl]));
         c->pending_join = sl;
     } else {
         c->cur = c->stream;
-        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo);
+        rc = run_chain(c, mode, d_frames, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, max_boxes_per_frame, B, M, todo, host_src);
     }
     c->cur = c->stream;
     c->ticket_base = 16;
@@ -1448,6 +1483,25 @@ int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframe
     c->last = B;
     c->last_mode = mode;
     if (!ov) c->prev.valid = false;
+    return TSD_OK;
+}
+
+int tsd_enqueue_frames(tsd_ctx* c, int mode, const uint8_t* d_frames, int nframes, int H, int W, int64_t row_stride, int64_t frame_stride,
+                       const int32_t* d_boxes, const int32_t* d_box_offsets, int nb, int max_boxes_per_frame) {
+    return enqueue_impl(c, mode, d_frames, nframes, H, W, row_stride, frame_stride, d_boxes, d_box_offsets, nb, max_boxes_per_frame, nullptr);
+}
+
+// Bytes the ROI staging of tsd_detect_frames (page-locked host frames) has copied over PCIe since process start / the last reset:
+// 32 bytes per distinct sector a batch's candidate ROIs touch.  Synchronises.
+int tsd_stat_staged_bytes(tsd_ctx* c, int64_t* total, int reset) {
+    if (!c || !total) return fail(TSD_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    TRY(join_pending(c));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long h = 0;
+    CU(cudaMemcpy(&h, c->d_staged, 8, cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(c->d_staged, 0, 8));
+    *total = (int64_t)h;
     return TSD_OK;
 }
 
@@ -1554,11 +1608,11 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
     const int32_t* d_off = (const int32_t*)c->b_hoff.p;
     int32_t tot[4] = {0, 0, 0, 0};
     int nd_total = 0;
-    auto run_chunk = [&](const uint8_t* d_frames, int f0, int cf) -> int {
+    auto run_chunk = [&](const uint8_t* d_frames, int f0, int cf, const uint8_t* host_src = nullptr) -> int {
         int max_n = 0;
         for (int f = f0; f < f0 + cf; f++) max_n = box_offsets[f + 1] - box_offsets[f] > max_n ? box_offsets[f + 1] - box_offsets[f] : max_n;
         // offsets stay absolute: the kernels index `boxes` with them, so the base pointer is the whole box array
-        return tsd_enqueue_frames(c, mode, d_frames, cf, H, W, row_stride, frame_stride, d_boxes, d_off + f0, box_offsets[f0 + cf] - box_offsets[f0], max_n > 0 ? max_n : 1);
+        return enqueue_impl(c, mode, d_frames, cf, H, W, row_stride, frame_stride, d_boxes, d_off + f0, box_offsets[f0 + cf] - box_offsets[f0], max_n > 0 ? max_n : 1, host_src);
     };
     auto fetch_chunk = [&](int f0) -> int {
         int32_t nd = 0, cnt[4];
@@ -1573,11 +1627,14 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
     };
     int rc_all = TSD_OK;
     if (c->zero_copy) {
-        // Page-locked (pinned / cudaHostRegister'ed) host frames are read IN PLACE by K2: only the ROI bytes cross PCIe
-        // (~0.5 MB of a 3.26 MB frame at 200 candidates), measured 3.3x faster than copying whole frames (profiles/).
+        // Page-locked (pinned / cudaHostRegister'ed) host frames are read IN PLACE: only the bytes of the candidate ROIs cross PCIe
+        // (~0.3 MB of a 3.26 MB frame at 200 candidates).  Default: the mark + copy kernels bring every touched 32-byte sector over
+        // once, coalesced, into a device mirror (needs 16-byte aligned frames and strides); TSD_STAGE=0: K2 gathers from host memory.
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            TRY(run_chunk((const uint8_t*)at.devicePointer, 0, nframes));
+            const uint8_t* hp = (const uint8_t*)at.devicePointer;
+            const bool stage = c->stage_rois && ((uintptr_t)hp % 16 == 0) && row_stride % 16 == 0 && frame_stride % 16 == 0 && ((int64_t)W * 3) % 16 == 0;
+            TRY(stage ? run_chunk(nullptr, 0, nframes, hp) : run_chunk(hp, 0, nframes));
             const int rc = fetch_chunk(0);
             *ndet = nd_total;
             if (counts) for (int i = 0; i < 4; i++) counts[i] = tot[i];

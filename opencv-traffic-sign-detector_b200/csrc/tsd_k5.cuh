@@ -853,8 +853,13 @@ struct __align__(16) GramBigSmem {
     uint16_t cb[2 * kGramBM][kGramChunks + 2];
     int32_t nbig;
     int32_t bigrow[kBigMaxRows];                            // local row index 0..255 (>= 128: block J)
+    uint32_t extra[2 * kGramBM][32];                        // entries 32 .. 63 of a row's range in the NEXT chunk (cp.async, lane-private slots)
 };
 static_assert(kGramBM * kGramIPitch * 4 <= 2 * kGramBM * kGramPitch, "result matrix aliases the tiles");
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 
 __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const uint32_t* __restrict__ entries, const WinMeta* __restrict__ meta,
                                                                        const float* __restrict__ E_T, int64_t e_stride,
@@ -907,8 +912,10 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const ui
             const int r = wid + kBigWarps * k;
             pre[k] = 0xffffffffu;
             if (row_ok(r)) {
-                const int e = (int)S.cb[r][c] + lane;
-                if (e < (int)S.cb[r][c + 1]) pre[k] = __ldg(entries + (int64_t)(base + item_of(r)) * es + e);
+                const int e = (int)S.cb[r][c] + lane, hi = (int)S.cb[r][c + 1];
+                const uint32_t* er = entries + (int64_t)(base + item_of(r)) * es;
+                if (e < hi) pre[k] = __ldg(er + e);
+                if (e + 32 < hi) cp_async4(&S.extra[r][lane], er + e + 32);     // a window has ~25-40 occupied bins per 512-bin chunk
             }
         }
     };
@@ -936,21 +943,24 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const ui
             const int n16 = (diag ? 1 : 2) * kGramBM * kGramPitch / 16;
             for (int i = tid; i < n16; i += kBigWarps * 32) t4[i] = z;
         }
+        cp_async_wait_all();                                 // this lane's own extra slots (written by its cp.async of the previous iteration)
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kBigRowsPerWarp; k++) {
             const int r = wid + kBigWarps * k;
             const uint32_t v = pre[k];
             unsigned char* trow = S.tile[r >> 7] + (size_t)(r & (kGramBM - 1)) * kGramPitch;
-            if (v != 0xffffffffu) trow[(int)(v >> 16) - k0] = (unsigned char)v;
-            if (row_ok(r)) {                                 // (rare) more than 32 entries of this row in the chunk
-                const uint32_t* er = entries + (int64_t)(base + item_of(r)) * es;
-                for (int e = (int)S.cb[r][ch] + 32 + lane; e < (int)S.cb[r][ch + 1]; e += 32) {
-                    const uint32_t u = __ldg(er + e);
-                    trow[(int)(u >> 16) - k0] = (unsigned char)u;
+            if (v != 0xffffffffu) {
+                trow[(int)(v >> 16) - k0] = (unsigned char)v;
+                const int e1 = (int)S.cb[r][ch] + 32 + lane, hi = (int)S.cb[r][ch + 1];
+                if (e1 < hi) { const uint32_t u = S.extra[r][lane]; trow[(int)(u >> 16) - k0] = (unsigned char)u; }
+                if (e1 + 32 < hi) {                          // (rare) more than 64 entries of this row in the chunk
+                    const uint32_t* er = entries + (int64_t)(base + item_of(r)) * es;
+                    for (int e = e1 + 32; e < hi; e += 32) { const uint32_t u = __ldg(er + e); trow[(int)(u >> 16) - k0] = (unsigned char)u; }
                 }
             }
         }
+        __syncwarp();                                        // the extra slots are free again
         if (ch + 1 < kGramChunks) load_chunk(ch + 1);        // in flight during the tensor-core phase below
         __syncthreads();
         if (mma_on) {
@@ -1502,8 +1512,11 @@ struct FoldCtaSmem {
     HsvLut lut;
     FoldWarpSmem<1024, CAP> w;
     WinMeta mj;                  // the merged item's moments
-    uint32_t cmask[32];          // items to classify against (word t = items 32t .. 32t+31)
+    uint32_t cmask[32];          // items to classify against (word t = items 32t .. 32t+31); pass 2: the survivors so far
     int32_t cmd, w0, w1, ncand, frame, rewrite_j;
+    uint32_t cd[32], cm[32];     // pass 2: delete / merge bits of the current item against survivor word t
+    int4 ic;                     // pass 2: the current item's (possibly merged) coordinates
+    int32_t start, go;           // pass 2: first list position still to scan / another round needed
 };
 enum { kCtaCmdClassify = 1, kCtaCmdNextFrame = 2, kCtaCmdExit = 3 };
 
@@ -1626,6 +1639,87 @@ __device__ __forceinline__ void fold_cta_classify(FoldCtaSmem<CAP>& S, const Fol
     __syncthreads();
 }
 
+
+// Pass 2 (corner similarity) of a large frame by the whole CTA: same semantics as fold_coord_pass, but the classes of the current
+// item against the survivors so far (up to 32 words of 32) are computed by all warps at once, one word per warp step, instead of
+// word after word by one warp -- with ~480 pass-1 survivors that scan was 40 % of the frame's fold time.  Warp 0 keeps the survivor
+// set A2, finds the first merge in list order, applies merges and deletions; returns the survivors (valid in warp 0).
+template <int CAP>
+__device__ __forceinline__ unsigned fold_cta_coord_pass(FoldCtaSmem<CAP>& S, const FoldParams& P, int base, int n, int sim_cut, unsigned A1) {
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    FoldWarpSmem<1024, CAP>& sm = S.w;
+    const int nwords = (n + 31) >> 5;
+    const int ws = P.ws;
+    const double tol = P.coord_tol, lo = P.coord_lo;
+    for (int p = tid; p < n; p += blockDim.x) sm.coords[p] = P.coords[base + p];      // overlays the pass-1 workspace
+    if (wid == 0) { S.cmask[lane] = 0; S.cd[lane] = A1; }   // cd doubles as the carrier of A1 for the other warps' item loop
+    __syncthreads();
+    const unsigned a1w = S.cd[lane];                         // every warp walks the same item sequence
+    unsigned A2 = 0;
+    __syncthreads();
+    for (int tj = 0; tj < nwords; tj++) {
+        unsigned wj = __shfl_sync(0xffffffffu, a1w, tj);
+        while (wj) {
+            const int j = 32 * tj + __ffs(wj) - 1;
+            wj &= wj - 1;
+            if (tid == 0) { S.ic = sm.coords[j]; S.start = 0; }
+            unsigned D = 0;
+            bool dirty = false;
+            __syncthreads();
+            while (true) {
+                const int4 ic = S.ic;
+                const int start = S.start;
+                for (int t = (start >> 5) + wid; t <= tj; t += kFoldCtaWarps) {
+                    unsigned aw = S.cmask[t];
+                    if (t == (start >> 5)) aw &= ~((1u << (start & 31)) - 1);
+                    int c = 0;
+                    if ((aw >> lane) & 1u) c = classify(coord_sim(ic, sm.coords[32 * t + lane], P.simtab, sim_cut), tol, lo);
+                    const unsigned bd = __ballot_sync(0xffffffffu, c == 1), bmm = __ballot_sync(0xffffffffu, c == 2);
+                    if (lane == 0) { S.cd[t] = bd; S.cm[t] = bmm; }
+                }
+                __syncthreads();
+                if (wid == 0) {
+                    const bool in_range = lane >= (start >> 5) && lane <= tj;
+                    const unsigned mw = in_range ? S.cm[lane] : 0u, dw = in_range ? S.cd[lane] : 0u;
+                    const unsigned any = __ballot_sync(0xffffffffu, mw != 0u);
+                    if (!any) {
+                        D |= dw;
+                        if (lane == 0) S.go = 0;
+                    } else {
+                        // ---- merge with the first survivor in the merge band (DET:217-221): pixels, coords; later comparisons use the updated item
+                        const int t = __ffs(any) - 1;
+                        const int bit = __ffs(__shfl_sync(0xffffffffu, mw, t)) - 1, fm = 32 * t + bit;
+                        if (lane < t) D |= dw;
+                        else if (lane == t) D |= (dw & ((1u << bit) - 1)) | (1u << bit);
+                        const uint32_t hsh = merge_pixels_warp<true>(P.windows + (int64_t)(base + j) * ws, P.windows + (int64_t)(base + fm) * ws, ws, P.npx);
+                        const int4 kc = sm.coords[fm];
+                        if (lane == 0) {
+                            S.ic = make_int4((ic.x + kc.x) >> 1, (ic.y + kc.y) >> 1, (ic.z + kc.z) >> 1, (ic.w + kc.w) >> 1);
+                            sm.hash[j] = hsh;
+                            S.start = fm + 1;
+                            S.go = 1;
+                        }
+                        dirty = true;
+                    }
+                }
+                __syncthreads();
+                if (!S.go) break;
+            }
+            if (wid == 0) {
+                if (dirty) {
+                    if (lane == 0) { const int4 icn = S.ic; sm.coords[j] = icn; P.coords[base + j] = icn; P.meta[base + j].hash = sm.hash[j]; }
+                    __syncwarp();
+                }
+                if (__any_sync(0xffffffffu, D != 0)) A2 = fold_apply_deletions<1024, CAP>(A2, D, sm, P.windows, base, ws);
+                if (lane == (j >> 5)) A2 |= 1u << (j & 31);
+                S.cmask[lane] = A2;
+            }
+            __syncthreads();
+        }
+    }
+    return A2;
+}
+
 template <int CAP>
 __global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
                                                                           const int32_t* __restrict__ order, int32_t* counter) {
@@ -1661,6 +1755,7 @@ __global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldPar
                 if (cmd != kCtaCmdClassify) break;
                 fold_cta_classify<CAP>(S, P, M, RW, base, n);
             }
+            if (P.do_coords) fold_cta_coord_pass<CAP>(S, P, base, n, sim_cut, 0u);
             continue;
         }
         // ---- warp 0: the sequencer (same item loop as k5_fold_warp) ----
@@ -1740,9 +1835,9 @@ __global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldPar
         } else {
             if (lane < nwords) A = (lane == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1) : 0xffffffffu;
         }
-        if (lane == 0) S.cmd = kCtaCmdNextFrame;             // the helpers leave their command loop (pass 2 is cheap: warp 0 alone)
+        if (lane == 0) S.cmd = kCtaCmdNextFrame;             // the helpers leave their command loop and join pass 2
         __syncthreads();
-        if (P.do_coords) A = fold_coord_pass<1024, CAP>(A, sm, P, base, n, sim_cut);
+        if (P.do_coords) A = fold_cta_coord_pass<CAP>(S, P, base, n, sim_cut, A);
         fold_emit_survivors(A, P, f, base);
     }
 }

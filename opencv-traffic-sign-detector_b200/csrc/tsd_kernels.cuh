@@ -87,6 +87,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -376,6 +381,90 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
         }
     }
     }
+}
+
+// =====================================================================================================
+// Host-frame staging (tsd_detect_frames on PAGE-LOCKED host frames).  The candidate ROIs cover ~10 % of a frame, so copying whole
+// frames wastes PCIe; letting K2 gather straight from host memory (round 1) fetched every 32-byte sector once per window that
+// touches it (nested / jittered MSER boxes overlap heavily) and in requests as the taps happen to fall.  Instead:
+//   stage_mark : one warp per window sets, in a per-frame bitmap over (row, 32-byte sector), every sector K2 will read -- the whole
+//                byte span [3 x1, 3 x2) of each source row the resize touches (all rows of the crop up to 2D rows, else the two rows
+//                per destination row, computed exactly like K2 does);
+//   stage_copy : walks the bitmaps; lane l of a warp copies sector 32 w + l of bitmap word w when its bit is set, so runs of set bits
+//                become coalesced 128-byte reads over PCIe, and every sector crosses the bus ONCE per batch; the copy lands in a
+//                device-resident mirror with the frame's own layout, which K2 then reads at HBM speed.
+// The mirror is never cleared: K2 only reads sectors that were marked (and therefore copied) in the same batch.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) stage_mark_kernel(const int4* __restrict__ coords, const int32_t* __restrict__ win_frame,
+                                                         const int32_t* __restrict__ n_ptr, int n_max, int H, int W, int D, int wpr,
+                                                         uint32_t* __restrict__ bitmap) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (w >= n) return;
+    const int4 c = coords[w];
+    const int cx = min(c.x, W), cy = min(c.y, H);
+    const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
+    if (cw <= 0 || ch <= 0) return;
+    const int s0 = (3 * cx) >> 5, s1 = (3 * (cx + cw) - 1) >> 5;           // first / last 32-byte sector of the row span
+    uint32_t* fb = bitmap + (int64_t)win_frame[w] * H * wpr;
+    int rows[2], nrows = 0;
+    if (ch <= 2 * D) {                                       // every row of the crop (copy / 2x2 AREA / down-scales up to 2)
+        if (lane < ch) rows[nrows++] = cy + lane;
+        if (lane + 32 < ch) rows[nrows++] = cy + lane + 32;
+    } else if (lane < D) {                                   // the two source rows of destination row `lane` (same float steps as K2)
+        const double scale = 1.0 / ((double)D / (double)ch);
+        float f = (float)(((double)lane + 0.5) * scale - 0.5);
+        const int sy = (int)floorf(f);
+        rows[nrows++] = cy + min(max(sy, 0), ch - 1);
+        rows[nrows++] = cy + min(max(sy + 1, 0), ch - 1);
+    }
+    for (int k = 0; k < nrows; k++) {
+        uint32_t* rb = fb + (int64_t)rows[k] * wpr;
+        for (int wd = s0 >> 5; wd <= (s1 >> 5); wd++) {
+            const int lo = max(s0, 32 * wd) & 31, hi = min(s1, 32 * wd + 31) & 31;
+            const uint32_t m = (hi == 31 ? 0xffffffffu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+            if ((rb[wd] & m) != m) atomicOr(rb + wd, m);     // (most windows re-mark sectors an overlapping window already set)
+        }
+    }
+}
+
+// total words = nframes * H * wpr.  src rows: row_bytes valid bytes, 16-byte aligned base and strides (host checks).
+__global__ void __launch_bounds__(256) stage_copy_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int H, int row_bytes,
+                                                         int wpr, int64_t nwords, const uint32_t* __restrict__ bitmap, uint8_t* __restrict__ mirror,
+                                                         unsigned long long* __restrict__ bytes_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long copied = 0;
+    for (int64_t base = warp * 32; base < nwords; base += nwarps * 32) {
+        const int64_t wi = base + lane;
+        const uint32_t mine = wi < nwords ? __ldg(bitmap + wi) : 0u;
+        unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+        while (nz) {
+            const int k = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t wv = __shfl_sync(0xffffffffu, mine, k);
+            const int64_t g = base + k;                      // global word index -> (frame, row, word of the row)
+            const int64_t fr = g / wpr;
+            const int wd = (int)(g - fr * wpr);
+            const int64_t f = fr / H;
+            const int row = (int)(fr - f * H);
+            const int off = (32 * wd + lane) * 32;           // byte offset of this lane's sector inside the row
+            if (((wv >> lane) & 1u) && off < row_bytes) {
+                const int64_t o = f * frame_stride + (int64_t)row * row_stride + off;
+                const int valid = min(32, row_bytes - off);
+                if (valid == 32) {
+                    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(src + o)), b = __ldcs(reinterpret_cast<const uint4*>(src + o + 16));
+                    *reinterpret_cast<uint4*>(mirror + o) = a;
+                    *reinterpret_cast<uint4*>(mirror + o + 16) = b;
+                } else {
+                    for (int i = 0; i < valid; i++) mirror[o + i] = src[o + i];
+                }
+                copied += (unsigned)valid;
+            }
+        }
+    }
+    copied = warp_sum_u64(copied);
+    if (lane == 0 && copied && bytes_out) atomicAdd(bytes_out, copied);
 }
 
 // =====================================================================================================
@@ -759,8 +848,10 @@ struct FoldSmem {
 };
 
 __device__ __forceinline__ double coord_sim(int4 a, int4 b, const double* __restrict__ simtab, int simtab_n) {
-    long long dx = (long long)a.x - b.x, dy = (long long)a.y - b.y, ex = (long long)a.z - b.z, ey = (long long)a.w - b.w;
-    long long d1 = dx * dx + dy * dy, d2 = ex * ex + ey * ey;
+    // 32-bit arithmetic: a corner more than 32767 px away in x or y is beyond every table (simtab_n <= 2^30) without squaring it
+    const int dx = a.x - b.x, dy = a.y - b.y, ex = a.z - b.z, ey = a.w - b.w;
+    if (max(max(abs(dx), abs(dy)), max(abs(ex), abs(ey))) > 32767) return 0.0;
+    const int d1 = dx * dx + dy * dy, d2 = ex * ex + ey * ey;
     if (d1 >= simtab_n || d2 >= simtab_n) return 0.0;      // f < 0.16 beyond the table: sqrt(f1 f2) < 0.4 < tol*0.8823
     return __dsqrt_rn(__dmul_rn(simtab[d1], simtab[d2]));
 }

@@ -313,6 +313,12 @@ class Context:
         check(self._L.tsd_stat_unsure_pairs(self._h, C.byref(t), int(bool(reset))))
         return int(t.value)
 
+    def stat_staged_bytes(self, reset=False):
+        """Bytes the ROI staging of detect_frames (page-locked host frames) moved over PCIe since process start / the last reset."""
+        t = C.c_int64()
+        check(self._L.tsd_stat_staged_bytes(self._h, C.byref(t), int(bool(reset))))
+        return int(t.value)
+
     def preprocess(self, frames, clip_limit=2.0, tiles=(8, 8), gamma=2):
         """grayAndEnhanceContrast (DET:135-152) for a batch: BGR2GRAY -> CLAHE -> GaussianBlur 3x3 -> gamma LUT.
         frames uint8 [F,H,W,3] or [H,W,3] -> uint8 [F,H,W] (or [H,W])."""

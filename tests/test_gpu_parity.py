@@ -438,8 +438,9 @@ def test_chain_properties_full_size(ctx_det, tsd):
 
 def test_host_paths_agree(tsd, templates, oracle, monkeypatch):
     """tsd_detect_frames with host buffers: pageable frames (copied whole, in chunks that overlap the chain; 3 frames per
-    chunk here so several chunks and a ragged tail are exercised), page-locked frames (read in place over PCIe by K2) and
-    the device-resident path must give identical records, equal to the oracle's."""
+    chunk here so several chunks and a ragged tail are exercised), page-locked frames (the sectors the ROIs touch staged once
+    into a device mirror; or, TSD_STAGE=0, gathered from host memory by K2 itself) and whole-frame copies (TSD_ZEROCOPY=0) must
+    give identical records, equal to the oracle's."""
     red6, blue6 = templates
     F = 10
     frames = tsd.synth.make_frames(F)
@@ -455,15 +456,28 @@ def test_host_paths_agree(tsd, templates, oracle, monkeypatch):
         pinned = np.ascontiguousarray(frames.copy())
         ctx.pin(pinned)
         try:
+            ctx.stat_staged_bytes(reset=True)
             d_pinned, c_pinned = ctx.detect_frames(pinned, boxes, off)
+            staged = ctx.stat_staged_bytes()
+        finally:
+            ctx.unpin(pinned)
+    # page-locked frames: only the sectors the ROIs touch cross the bus -- far fewer bytes than the frames, at least the ROIs' own
+    assert 0 < staged < pinned.nbytes // 3
+    monkeypatch.setenv("TSD_STAGE", "0")                                  # round 1's path: K2 itself gathers from host memory
+    with tsd.Context(0, "det") as ctx:
+        ctx.set_templates(red6, blue6)
+        ctx.pin(pinned)
+        try:
+            d_gather, c_gather = ctx.detect_frames(pinned, boxes, off)
+            assert ctx.stat_staged_bytes() == 0                           # (nothing staged on this path)
         finally:
             ctx.unpin(pinned)
     monkeypatch.setenv("TSD_ZEROCOPY", "0")
     with tsd.Context(0, "det") as ctx:
         ctx.set_templates(red6, blue6)
         d_copy, c_copy = ctx.detect_frames(frames, boxes, off)
-    assert _records(d_pageable) == exp and _records(d_pinned) == exp and _records(d_copy) == exp
-    assert c_pageable.tolist() == c_pinned.tolist() == c_copy.tolist()
+    assert _records(d_pageable) == exp and _records(d_pinned) == exp and _records(d_copy) == exp and _records(d_gather) == exp
+    assert c_pageable.tolist() == c_pinned.tolist() == c_copy.tolist() == c_gather.tolist()
 
 
 def test_back_to_back_batches_overlap_slots(tsd, templates, oracle, monkeypatch):

@@ -17,12 +17,25 @@ ap.add_argument("--H", type=int, default=800)
 ap.add_argument("--W", type=int, default=1360)
 ap.add_argument("--times", action="store_true")
 ap.add_argument("--wall", action="store_true", help="CUDA-event time of the steps enqueued back to back (no per-stage events)")
+ap.add_argument("--real", action="store_true", help="the three stored real test frames with their real cv2.MSER boxes, tiled to --frames (bench.py's real_mser_frames)")
 ap.add_argument("--mode", default="det", choices=["det", "rec"], help="det: K1 K2 K5 K3 K4 (x1.30, 25x25); rec: K1 K2 K5 K6 K7 K8 (x1.15, 32x32)")
 a = ap.parse_args()
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "det_templates.npz"))
-U = min(16, a.frames)
-uniq = tsd_b200.synth.make_frames(U, a.H, a.W)
-boxes, off = tsd_b200.synth.make_boxes(a.frames, a.boxes, a.H, a.W)
+if a.real:
+    import cv2
+    gd = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+    gf = np.load(os.path.join(gd, "det_frames.npz"))
+    names = ["00604", "00639", "00719"]
+    uniq = np.stack([cv2.imread(os.path.join(gd, "det_frame_%s.png" % k)) for k in names])
+    bl = [gf[k + "_boxes"].astype(np.int32) for k in names]
+    U = 3
+    boxes = np.concatenate([bl[f % 3] for f in range(a.frames)])
+    off = np.concatenate([[0], np.cumsum([len(bl[f % 3]) for f in range(a.frames)])]).astype(np.int32)
+    a.boxes = int(max(len(b) for b in bl))
+else:
+    U = min(16, a.frames)
+    uniq = tsd_b200.synth.make_frames(U, a.H, a.W)
+    boxes, off = tsd_b200.synth.make_boxes(a.frames, a.boxes, a.H, a.W)
 dev = torch.device("cuda", 0)
 d_frames = torch.from_numpy(uniq).to(dev)[torch.arange(a.frames, device=dev) % U].contiguous()
 d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
