@@ -70,6 +70,7 @@ struct tsd_ctx {
     int stage_rois = 1;                      // ... by the mark + copy kernels, each touched 32-byte sector once, into a device mirror K2 reads
                                              // (TSD_STAGE=0: K2 itself gathers from host memory, round 1's path)
     DevBuf b_mirror, b_stagemap;
+    int stage_gran = 1;                      // TSD_STAGE_GRAN = 32 | 64 | 128 bytes: unit the marked spans are widened to (sectors: 1, 2, 4)
     unsigned long long* d_staged = nullptr;  // bytes the staging copy moved over PCIe (tsd_stat_staged_bytes)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
     tsd_config cfg;
@@ -97,6 +98,7 @@ struct tsd_ctx {
     bool profiling = false;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int use_gram = 1;                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
+    int fold_cta_cost = 0;                   // TSD_FOLD_CTA_COST: frames with at least this many merge-band pairs go to the CTA fold (0 = by size only)
     // function attributes (dynamic shared memory opt-in) are set once per context: per-context flags, no process-wide statics
     int fold_per_sm[4] = {0, 0, 0, 0};       // resident CTAs per SM of the four k5_fold_warp instantiations (0 = not queried yet)
     bool attr_gram = false, attr_pairs = false;
@@ -193,10 +195,12 @@ static int create_impl(tsd_ctx* c, int device) {
     { const char* e = getenv("TSD_OVERLAP"); if (e) c->overlap = atoi(e) != 0; }
     { const char* e = getenv("TSD_ZEROCOPY"); if (e) c->zero_copy = e[0] != '0'; }
     { const char* e = getenv("TSD_STAGE"); if (e) c->stage_rois = e[0] != '0'; }
+    { const char* e = getenv("TSD_STAGE_GRAN"); if (e) { const int g = atoi(e); c->stage_gran = g >= 128 ? 4 : g >= 64 ? 2 : 1; } }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     { const char* e = getenv("TSD_GRAPH"); if (e) c->use_graph = atoi(e) != 0; }
+    { const char* e = getenv("TSD_FOLD_CTA_COST"); if (e) c->fold_cta_cost = atoi(e); }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -593,18 +597,22 @@ static int launch_folds(tsd_ctx* c, int variant, const FoldParams& P, int nframe
         if (per_sm_cta < 1) per_sm_cta = 1;
         if (getenv("TSD_DEBUG")) fprintf(stderr, "[tsd] k5_fold_warp<256,%d>: %zu B shared memory per CTA, %d CTAs per SM; k5_fold_cta: %zu B, %d per SM\n", CAP, smem, per_sm, smem_cta, per_sm_cta);
     }
-    // longest-first frame order + the two work counters (context scratch: [nframes] order, [2] counters)
-    int32_t* order = (int32_t*)c->b_order.p + c->order_off;
+    // longest-first frame order + the two work counters + the costs in that order (context scratch: [nframes] order, [2] counters,
+    // [nframes] costs)
+    int32_t* order = (int32_t*)c->b_order.p + 2 * c->order_off;
     int32_t* counter = order + nframes;
-    k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter);
+    int32_t* cost_sorted = counter + 2;
+    k5_order_kernel<<<1, 1024, 0, c->cur>>>(cost, P.offsets, nframes, order, counter, cost_sorted);
     TRY(check_launch(c, "k5_order"));
+    // frames predicted to merge often go to the CTA fold too (batches large enough for a straggler to matter)
+    const int cost_min = (cost && nframes >= 256) ? c->fold_cta_cost : 0;
     int grid = cdiv(nframes, warps);
     if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
-    k5_fold_warp_kernel<256, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter, kFoldCtaMin);
+    k5_fold_warp_kernel<256, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter, kFoldCtaMin, cost_sorted, cost_min);
     TRY(check_launch(c, "k5_fold_warp"));
-    if (max_n > kFoldCtaMin) {
+    if (max_n > kFoldCtaMin || cost_min > 0) {
         grid = nframes < per_sm_cta * c->sm_count ? nframes : per_sm_cta * c->sm_count;
-        k5_fold_cta_kernel<CAP><<<grid, kFoldCtaWarps * 32, smem_cta, c->cur>>>(P, nframes, M, RW, cut, order, counter + 1);
+        k5_fold_cta_kernel<CAP><<<grid, kFoldCtaWarps * 32, smem_cta, c->cur>>>(P, nframes, M, RW, cut, order, counter + 1, kFoldCtaMin, cost_sorted, cost_min);
         TRY(check_launch(c, "k5_fold_cta"));
     }
     return TSD_OK;
@@ -814,7 +822,7 @@ int tsd_dedup(tsd_ctx* c, const uint8_t* windows, const int32_t* coords, const i
     c->order_off = 0;
     TRY(ensure(c, c->b_pairs, (size_t)(n > 0 ? n : 1) * 2 * pair_row_words(max_n) * sizeof(uint32_t)));
     TRY(ensure(c, c->b_gramdone, 2 * todo_capacity(nframes, max_n) * 4));
-    TRY(ensure(c, c->b_order, (size_t)(nframes + 2) * 4));
+    TRY(ensure(c, c->b_order, (size_t)(2 * nframes + 4) * 4));
     TRY(dev_fold(c, (uint8_t*)dw, ws, (int32_t*)dc, (uint32_t*)dent, (WinMeta*)dmeta, (int32_t*)doff, nframes, npx, !by_coords, by_coords,
                  tol, tol, (int32_t*)dlist, (uint8_t*)dflags, (int32_t*)dcnt, max_n, (uint32_t*)c->b_pairs.p, (int32_t*)c->b_gramdone.p, (float*)den, n, (int32_t*)dooff));
     if (nframes) {
@@ -1243,7 +1251,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
         const int64_t nwords = (int64_t)cf * H * wpr;
         CU(cudaMemsetAsync(c->b_stagemap.p, 0, (size_t)nwords * 4, c->cur));
         if (nb > 0) {
-            stage_mark_kernel<<<cdiv((int64_t)nb * 32, 128), 128, 0, c->cur>>>((const int4*)coords, winframe, d_nwin, nb, H, W, D, wpr, (uint32_t*)c->b_stagemap.p);
+            stage_mark_kernel<<<cdiv((int64_t)nb * 32, 128), 128, 0, c->cur>>>((const int4*)coords, winframe, d_nwin, nb, H, W, D, wpr, c->stage_gran, (uint32_t*)c->b_stagemap.p);
             TRY(check_launch(c, "stage_mark"));
             int g = cdiv(nwords, 256);
             if (g > c->sm_count * 8) g = c->sm_count * 8;
@@ -1329,7 +1337,7 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
     const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
                                        (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
                                        (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
-                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src};
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->stage_gran};
     c->graph_clock++;
     for (auto& g : c->graphs)
         if (g.key == key) {
@@ -1429,7 +1437,7 @@ static int enqueue_impl(tsd_ctx* c, int mode, const uint8_t* d_frames, int nfram
     TRY(ensure(c, c->b_detcnt, fcap * 4));
     TRY(ensure(c, c->b_detoff, fcap * 4));
     TRY(ensure(c, c->b_summary, 2 * 16));
-    TRY(ensure(c, c->b_order, (fcap + 2) * 4));
+    TRY(ensure(c, c->b_order, (2 * fcap + 4) * 4));
     TRY(ensure(c, c->b_gramdone, todo_words * 4));
     TRY(ensure(c, c->b_coords, cap * 16));
     TRY(ensure(c, c->b_winframe, cap * 4));

@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, MINB) k5_pairs_kernel(const u
 // blocks than warps, one slice of K; the integer partial sums meet in shared memory, where the lane-per-pair classification
 // (classify_from_int, f64 fallback within 2e-6 of a threshold) reads them.
 // =====================================================================================================================
+constexpr int kGramTinyMax = 24;                       // frames of up to this many windows go straight to k5_pairs
 constexpr int kGramWarps = 12;                         // 96 four-lane groups; 6 lower-triangle 32 x 32 blocks x 2 K slices for n <= 96
 constexpr int kGramGroups = kGramWarps * 8;
 constexpr int kGramPitch = kGramKC + 16;               // bytes per tile row: an odd number of 16-byte units -> conflict-free ldmatrix
@@ -609,6 +610,10 @@ __global__ void __launch_bounds__(kGramWarps * 32, 2) k5_gram_kernel(const uint3
     if (f >= nframes) return;
     const int base = offsets[f], n = offsets[f + 1] - base;
     if (n < 2 || n > RW * 32) return;                       // (CTA-uniform) nothing to classify / the general fold's frame
+    if (n <= kGramTinyMax) {                                // a handful of windows (real MSER frames: ~4): a warp per item in k5_pairs costs a few
+        if (threadIdx.x == 0) todo[1 + atomicAdd(todo, 1)] = (f << 8) | 0xff;     // microseconds, this CTA's six chunk rounds ~40
+        return;
+    }
     if (n > kGramBM) {                                      // k5_gram_big's frame: its block pairs (I, J), J <= I, go to that kernel's work list
         const int nbk = (n + kGramBM - 1) / kGramBM, np = nbk * (nbk + 1) / 2;
         __shared__ int s_pos;
@@ -1074,8 +1079,9 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) k5_gram_big_kernel(const ui
 
 // Longest-processing-time-first order of the frames for the fold: key = 32 * (merge-band pairs) + windows, counting sort,
 // descending.  One CTA.  Also resets the fold's work counter.
+// cost_sorted[k] = frame_cost of order[k]: the folds route on it (frame_cost itself aliases the survivor counts they write).
 __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restrict__ frame_cost, const int32_t* __restrict__ offsets, int nframes,
-                                                        int32_t* __restrict__ order, int32_t* __restrict__ counter) {
+                                                        int32_t* __restrict__ order, int32_t* __restrict__ counter, int32_t* __restrict__ cost_sorted) {
     constexpr int NB = 2048;
     __shared__ int32_t hist[NB];
     for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
@@ -1085,15 +1091,32 @@ __global__ void __launch_bounds__(1024) k5_order_kernel(const int32_t* __restric
         atomicAdd(&hist[NB - 1 - key], 1);                   // bucket 0 = heaviest
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                                  // exclusive prefix over 2048 buckets (tiny)
-        int run = 0;
-        for (int i = 0; i < NB; i++) { const int c = hist[i]; hist[i] = run; run += c; }
-        counter[0] = 0; counter[1] = 0;                      // work counters of k5_fold_warp / k5_fold_cta
+    {                                                        // exclusive prefix over the 2048 buckets: two per thread + a block scan
+        __shared__ int32_t wsum[32];
+        const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+        const int c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+        int x = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int v = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+            wsum[lane] = v;
+        }
+        __syncthreads();
+        const int excl = (wid ? wsum[wid - 1] : 0) + x - (c0 + c1);
+        hist[2 * tid] = excl; hist[2 * tid + 1] = excl + c0;
+        if (tid == 0) { counter[0] = 0; counter[1] = 0; }   // work counters of k5_fold_warp / k5_fold_cta
     }
     __syncthreads();
     for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
         const int key = min(NB - 1, 32 * (frame_cost ? frame_cost[f] : 0) + (offsets[f + 1] - offsets[f]));
-        order[atomicAdd(&hist[NB - 1 - key], 1)] = f;
+        const int pos = atomicAdd(&hist[NB - 1 - key], 1);
+        order[pos] = f;
+        cost_sorted[pos] = frame_cost ? frame_cost[f] : 0;
     }
 }
 
@@ -1381,10 +1404,18 @@ __device__ __forceinline__ void fold_emit_survivors(unsigned A, const FoldParams
     __syncwarp();
 }
 
-// n_skip: frames with more windows than this belong to k5_fold_cta (launched beside this kernel on the same order list).
+// Which fold takes a frame: k5_fold_cta (one CTA) the frames of more than n_skip windows and -- cost_min > 0 -- the frames whose
+// merge-band pair count (frame_cost, the fold's cost predictor) reaches cost_min: a frame that merges a dozen times keeps one
+// warp busy for ~0.7 ms while the rest of the batch is long done; k5_fold_warp (one warp) everything else.
+__device__ __forceinline__ bool fold_goes_to_cta(int n, int cost, int n_skip, int cost_min) {
+    return n > n_skip || (cost_min > 0 && cost >= cost_min && n > 32);
+}
+
+// n_skip / cost_min: see fold_goes_to_cta (k5_fold_cta is launched beside this kernel on the same order list).
 template <int RMAX, int CAP>
 __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
-                                                                       const int32_t* __restrict__ order, int32_t* counter, int n_skip) {
+                                                                       const int32_t* __restrict__ order, int32_t* counter, int n_skip,
+                                                                       const int32_t* __restrict__ frame_cost_sorted, int cost_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HsvLut& lut = *reinterpret_cast<HsvLut*>(smem_raw);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1402,10 +1433,10 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
         if (idx >= nframes) break;
         const int f = order[idx];
         const int base = P.offsets[f], n = P.offsets[f + 1] - base;
-        if (n > n_skip && n <= RW * 32) continue;            // k5_fold_cta's frame
+        if (n <= RW * 32 && n <= 1024 && fold_goes_to_cta(n, frame_cost_sorted ? frame_cost_sorted[idx] : 0, n_skip, cost_min)) continue;   // k5_fold_cta's frame
         if (n > RMAX || n > RW * 32) { if (lane == 0) P.out_count[f] = -1; continue; }    // host picks RMAX / RW large enough
         for (int p = lane; p < n; p += 32) sm.hash[p] = P.meta[base + p].hash;
-        for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;   // (the previous frame's pass 2 overlaid it)
+        bool dense_clean = false;                            // the previous frame's pass 2 overlaid the dense scratch: wiped at the first merge
         __syncwarp();
         const int nwords = (n + 31) >> 5;
         unsigned A = 0;                                      // survivors, list order = item order
@@ -1435,6 +1466,11 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParam
                     else if (lane == L) D |= (d & ((1u << bit) - 1)) | (1u << bit);
                     uint8_t* ipx = P.windows + (int64_t)slot * ws;
                     uint32_t* ient = P.entries + (int64_t)slot * es;
+                    if (!dense_clean) {
+                        for (int b = lane; b < kDenseLen / 2; b += 32) reinterpret_cast<uint32_t*>(sm.p1.dense)[b] = 0;
+                        dense_clean = true;
+                        __syncwarp();
+                    }
                     if (!dirty) ic = P.coords[slot];          // (pass 1 keeps coordinates in global memory: only merges touch them)
                     else {                                   // clear the previous dense copy of this item (hs still holds its bins)
                         for (int r = lane; r < mj.nnz; r += 32) sm.p1.dense[sm.p1.hs.binof[r]] = 0;
@@ -1722,7 +1758,8 @@ __device__ __forceinline__ unsigned fold_cta_coord_pass(FoldCtaSmem<CAP>& S, con
 
 template <int CAP>
 __global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
-                                                                          const int32_t* __restrict__ order, int32_t* counter) {
+                                                                          const int32_t* __restrict__ order, int32_t* counter, int n_skip,
+                                                                          const int32_t* __restrict__ frame_cost_sorted, int cost_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FoldCtaSmem<CAP>& S = *reinterpret_cast<FoldCtaSmem<CAP>*>(smem_raw);
     FoldWarpSmem<1024, CAP>& sm = S.w;
@@ -1737,7 +1774,7 @@ __global__ void __launch_bounds__(kFoldCtaWarps * 32) k5_fold_cta_kernel(FoldPar
                 const int idx = atomicAdd(counter, 1);
                 if (idx >= nframes) break;
                 const int fc = order[idx], nc = P.offsets[fc + 1] - P.offsets[fc];
-                if (nc > kFoldCtaMin && nc <= 1024 && nc <= RW * 32) { f = fc; break; }
+                if (nc <= 1024 && nc <= RW * 32 && fold_goes_to_cta(nc, frame_cost_sorted ? frame_cost_sorted[idx] : 0, n_skip, cost_min)) { f = fc; break; }
             }
             S.frame = f;
         }

@@ -395,8 +395,10 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
 //                device-resident mirror with the frame's own layout, which K2 then reads at HBM speed.
 // The mirror is never cleared: K2 only reads sectors that were marked (and therefore copied) in the same batch.
 // =====================================================================================================
+// gran = sectors per PCIe request unit (1, 2 or 4): the span is widened to whole units of 32 * gran bytes (a read request that
+// fills a whole 128-byte line moves more payload per PCIe packet than four 32-byte ones).
 __global__ void __launch_bounds__(128) stage_mark_kernel(const int4* __restrict__ coords, const int32_t* __restrict__ win_frame,
-                                                         const int32_t* __restrict__ n_ptr, int n_max, int H, int W, int D, int wpr,
+                                                         const int32_t* __restrict__ n_ptr, int n_max, int H, int W, int D, int wpr, int gran,
                                                          uint32_t* __restrict__ bitmap) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(128) stage_mark_kernel(const int4* __restrict_
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
     if (cw <= 0 || ch <= 0) return;
-    const int s0 = (3 * cx) >> 5, s1 = (3 * (cx + cw) - 1) >> 5;           // first / last 32-byte sector of the row span
+    const int s0 = ((3 * cx) >> 5) & ~(gran - 1), s1 = min(((3 * (cx + cw) - 1) >> 5) | (gran - 1), ((3 * W + 31) >> 5) - 1);   // first / last 32-byte sector of the row span
     uint32_t* fb = bitmap + (int64_t)win_frame[w] * H * wpr;
     int rows[2], nrows = 0;
     if (ch <= 2 * D) {                                       // every row of the crop (copy / 2x2 AREA / down-scales up to 2)
@@ -426,6 +428,13 @@ __global__ void __launch_bounds__(128) stage_mark_kernel(const int4* __restrict_
             if ((rb[wd] & m) != m) atomicOr(rb + wd, m);     // (most windows re-mark sectors an overlapping window already set)
         }
     }
+}
+
+// 16-byte load from page-locked host memory with the 128-byte L2 fetch-size hint: neighbouring lanes' sectors travel as one request
+__device__ __forceinline__ uint4 ld_host_128(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
 // total words = nframes * H * wpr.  src rows: row_bytes valid bytes, 16-byte aligned base and strides (host checks).
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(256) stage_copy_kernel(const uint8_t* __restri
                 const int64_t o = f * frame_stride + (int64_t)row * row_stride + off;
                 const int valid = min(32, row_bytes - off);
                 if (valid == 32) {
-                    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(src + o)), b = __ldcs(reinterpret_cast<const uint4*>(src + o + 16));
+                    const uint4 a = ld_host_128(src + o), b = ld_host_128(src + o + 16);
                     *reinterpret_cast<uint4*>(mirror + o) = a;
                     *reinterpret_cast<uint4*>(mirror + o + 16) = b;
                 } else {
