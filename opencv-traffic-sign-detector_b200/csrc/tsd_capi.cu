@@ -4,6 +4,7 @@
 #include "../../include/tsd_b200.h"
 #include "tsd_kernels.cuh"
 #include "tsd_k5.cuh"
+#include "tsd_k2_tma.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -101,7 +102,8 @@ struct tsd_ctx {
     int fold_cta_cost = 0;                   // TSD_FOLD_CTA_COST: frames with at least this many merge-band pairs go to the CTA fold (0 = by size only)
     // function attributes (dynamic shared memory opt-in) are set once per context: per-context flags, no process-wide statics
     int fold_per_sm[4] = {0, 0, 0, 0};       // resident CTAs per SM of the four k5_fold_warp instantiations (0 = not queried yet)
-    bool attr_gram = false, attr_pairs = false;
+    bool attr_gram = false, attr_pairs = false, attr_k2tma = false;
+    int k2_tma = 0;                          // TSD_K2=tma: the TMA-staged resize kernel (tsd_k2_tma.cuh) instead of the direct gather
     std::vector<cudaEvent_t> ev;
     std::vector<std::string> ev_names;
     int ev_used = 0;
@@ -200,6 +202,7 @@ static int create_impl(tsd_ctx* c, int device) {
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     { const char* e = getenv("TSD_GRAPH"); if (e) c->use_graph = atoi(e) != 0; }
+    { const char* e = getenv("TSD_K2"); if (e) c->k2_tma = strcmp(e, "tma") == 0; }
     { const char* e = getenv("TSD_FOLD_CTA_COST"); if (e) c->fold_cta_cost = atoi(e); }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
@@ -525,12 +528,31 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
     return check_launch(c, "k1_expand");
 }
 
-// out_stride = bytes between output windows: D*D*ch (public packed layout) or win_stride() (internal, zero padded)
+// out_stride = bytes between output windows: D*D*ch (public packed layout) or win_stride() (internal, zero padded).
+// nframes = frames behind `frames` (the TMA variant's tensor map needs the extent; 0 = unknown: direct gather).
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
-                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride) {
+                           const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride, int nframes = 0) {
     if (n_max == 0) return TSD_OK;
     const int g4 = cdiv(n_max, 4);
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
+    // TSD_K2=tma: ROI staged by the Tensor Memory Accelerator (internal 16-byte window layout, BGR, D = 25 / 32, TMA-legal frame layout)
+    if (c->k2_tma && ch == 3 && (D == 25 || D == 32) && nframes > 0 && out_stride % 16 == 0 && ((uintptr_t)windows % 16) == 0) {
+        K2TensorMaps maps;
+        if (k2_build_tensor_maps(&maps, frames, nframes, H, W, rs, fs)) {
+            const size_t smem = (size_t)kTmaWarps * tma_warp_bytes(D) + 128;
+            if (!c->attr_k2tma) {
+                CU(cudaFuncSetAttribute(k2_crop_resize_tma_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaWarps * tma_warp_bytes(25) + 128)));
+                CU(cudaFuncSetAttribute(k2_crop_resize_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTmaWarps * tma_warp_bytes(32) + 128)));
+                CU(cudaFuncSetAttribute(k2_crop_resize_tma_kernel<25>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CU(cudaFuncSetAttribute(k2_crop_resize_tma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                c->attr_k2tma = true;
+            }
+            const int grid = std::min(g4, c->sm_count * 4);  // persistent warps: 4 CTAs of 4 warps per SM (shared memory bound)
+            if (D == 25) k2_crop_resize_tma_kernel<25><<<grid, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
+            else k2_crop_resize_tma_kernel<32><<<grid, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
+            return check_launch(c, "k2_crop_resize_tma");
+        }
+    }
     if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
     else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
@@ -1262,7 +1284,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
         mark(c, "stage_h2d");
     }
     // K2 (DET:123-124)
-    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws));
+    TRY(dev_crop_resize(c, d_frames, H, W, row_stride, frame_stride, 3, coords, winframe, d_nwin, nb, D, windows, ws, cf));
     mark(c, "k2_crop_resize");
     // K5 (DET:127-129)
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
@@ -1337,7 +1359,7 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
     const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
                                        (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
                                        (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
-                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->stage_gran};
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->stage_gran, (uint64_t)c->k2_tma};
     c->graph_clock++;
     for (auto& g : c->graphs)
         if (g.key == key) {

@@ -284,22 +284,19 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 // 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
 // (Variants that lost on B200 -- crop staged in shared memory with cp.async, row reuse + staged output, aligned 32-bit tap loads,
 // one CTA per frame -- are documented with their measurements in DESIGN.md section 8 and live in the git history of round 1.)
+// One window by one warp, taps gathered straight from the frame (the body of k2_crop_resize_v2; also the path k2_crop_resize_tma
+// takes for crops that do not fit its staging buffer).  s_y = the warp's 32 x int4 scratch.
 template <int C, int D>
-__global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
-    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
-    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride) {
-    __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {     // (the grid normally covers all windows: one trip)
+__device__ __forceinline__ void k2_window_gather(const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+                                                 const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, int w,
+                                                 uint8_t* __restrict__ windows, int out_stride, int4* s_y) {
+    const int lane = threadIdx.x & 31;
     const int4 c = coords[w];
     const int cx = min(c.x, W), cy = min(c.y, H);
     const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
     if (cw <= 0 || ch <= 0) {                                // empty crop (cv2.resize would raise; K1 never emits one): a defined, all-zero window
         for (int i = lane; i < out_stride; i += 32) windows[(int64_t)w * out_stride + i] = 0;
-        continue;
+        return;
     }
     const uint8_t* __restrict__ src = frames + (int64_t)win_frame[w] * frame_stride + (int64_t)cy * row_stride + (int64_t)cx * C;
     uint8_t* __restrict__ dst = windows + (int64_t)w * out_stride + lane * C;
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
                 for (int k = 0; k < C; k++) dst[dy * D * C + k] = v[k];
             }
         }
-        continue;
+        return;
     }
     if (cw == 2 * D && ch == 2 * D) {                       // INTER_AREA 2x2 fast path
         const uint8_t* p = src + 2 * li * C;
@@ -334,7 +331,7 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
                 for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
             }
         }
-        continue;
+        return;
     }
     // coefficient tables (float32 rounding as in OpenCV); lane doubles as dx (x tables) and as dy (y tables)
     int xs0, xd1, xa0, xa1, yr0, yr1, yb0, yb1;
@@ -360,11 +357,11 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
     }
     const uint8_t* px = src + xs0;
     __syncwarp();                                            // (the previous window's rows are consumed)
-    s_y[wl][lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
+    s_y[lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
     __syncwarp();
 #pragma unroll kK2Unroll
     for (int dy = 0; dy < D; dy++) {
-        const int4 yc = s_y[wl][dy];
+        const int4 yc = s_y[dy];
         const int r0 = yc.x, r1 = yc.y, b0 = yc.z, b1 = yc.w;
         const uint8_t* p0 = px + (int64_t)r0 * row_stride;
         const uint8_t* p1 = px + (int64_t)r1 * row_stride;
@@ -380,7 +377,19 @@ __global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
             for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
         }
     }
-    }
+}
+
+template <int C, int D>
+__global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
+    const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
+    const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
+    uint8_t* __restrict__ windows, int out_stride) {
+    __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
+    const int wl = threadIdx.x >> 5;
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps)       // (the grid normally covers all windows: one trip)
+        k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl]);
 }
 
 // =====================================================================================================
@@ -430,14 +439,10 @@ __global__ void __launch_bounds__(128) stage_mark_kernel(const int4* __restrict_
     }
 }
 
-// 16-byte load from page-locked host memory with the 128-byte L2 fetch-size hint: neighbouring lanes' sectors travel as one request
-__device__ __forceinline__ uint4 ld_host_128(const uint8_t* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-// total words = nframes * H * wpr.  src rows: row_bytes valid bytes, 16-byte aligned base and strides (host checks).
+// total words = nframes * H * wpr.  src rows: row_bytes valid bytes (a multiple of 16), 16-byte aligned base and strides (host checks).
+// Four non-empty bitmap words per trip: all their loads are issued before the first store, so a warp keeps up to 8 x 16 bytes per
+// lane in flight over PCIe (the copy is bound by the number of outstanding read requests, not by their size: a 128-byte L2 fetch
+// hint and spans widened to whole 128-byte lines both measured slower).
 __global__ void __launch_bounds__(256) stage_copy_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int H, int row_bytes,
                                                          int wpr, int64_t nwords, const uint32_t* __restrict__ bitmap, uint8_t* __restrict__ mirror,
                                                          unsigned long long* __restrict__ bytes_out) {
@@ -449,26 +454,38 @@ __global__ void __launch_bounds__(256) stage_copy_kernel(const uint8_t* __restri
         const uint32_t mine = wi < nwords ? __ldg(bitmap + wi) : 0u;
         unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
         while (nz) {
-            const int k = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t wv = __shfl_sync(0xffffffffu, mine, k);
-            const int64_t g = base + k;                      // global word index -> (frame, row, word of the row)
-            const int64_t fr = g / wpr;
-            const int wd = (int)(g - fr * wpr);
-            const int64_t f = fr / H;
-            const int row = (int)(fr - f * H);
-            const int off = (32 * wd + lane) * 32;           // byte offset of this lane's sector inside the row
-            if (((wv >> lane) & 1u) && off < row_bytes) {
-                const int64_t o = f * frame_stride + (int64_t)row * row_stride + off;
-                const int valid = min(32, row_bytes - off);
-                if (valid == 32) {
-                    const uint4 a = ld_host_128(src + o), b = ld_host_128(src + o + 16);
-                    *reinterpret_cast<uint4*>(mirror + o) = a;
-                    *reinterpret_cast<uint4*>(mirror + o + 16) = b;
-                } else {
-                    for (int i = 0; i < valid; i++) mirror[o + i] = src[o + i];
+            int64_t o[4];
+            int nb[4];                                       // bytes this lane copies for word u: 0, 16 or 32
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                nb[u] = 0; o[u] = 0;
+                if (nz) {                                    // (warp-uniform)
+                    const int k = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t wv = __shfl_sync(0xffffffffu, mine, k);
+                    const int64_t g = base + k;              // global word index -> (frame, row, word of the row)
+                    const int64_t fr = g / wpr;
+                    const int wd = (int)(g - fr * wpr);
+                    const int64_t f = fr / H;
+                    const int row = (int)(fr - f * H);
+                    const int off = (32 * wd + lane) * 32;   // byte offset of this lane's sector inside the row
+                    if (((wv >> lane) & 1u) && off < row_bytes) {
+                        o[u] = f * frame_stride + (int64_t)row * row_stride + off;
+                        nb[u] = min(32, row_bytes - off);
+                    }
                 }
-                copied += (unsigned)valid;
+            }
+            uint4 va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (nb[u] >= 16) va[u] = __ldcs(reinterpret_cast<const uint4*>(src + o[u]));
+                if (nb[u] >= 32) vb[u] = __ldcs(reinterpret_cast<const uint4*>(src + o[u] + 16));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (nb[u] >= 16) *reinterpret_cast<uint4*>(mirror + o[u]) = va[u];
+                if (nb[u] >= 32) *reinterpret_cast<uint4*>(mirror + o[u] + 16) = vb[u];
+                copied += (unsigned)(nb[u] & ~15);
             }
         }
     }

@@ -241,3 +241,43 @@ def test_exact_f64_fallback_is_taken(tsd, oracle, monkeypatch):
                     ow, oc = oracle.dedup(wins, coords, False, float(tol))
                     assert go[1] == len(oc) and np.array_equal(gc, oc) and np.array_equal(gw, ow), (gram, tol)
             assert ctx.stat_unsure_pairs() > 0, "the exact-f64 path was never taken (TSD_GRAM=%s)" % gram
+
+
+def test_k2_tma_variant_bit_identical(tsd, oracle, templates, det_full150, jpeg24, resultado150, monkeypatch):
+    """TSD_K2=tma: the resize kernel whose ROI is staged in shared memory by the Tensor Memory Accelerator (cp.async.bulk.tensor behind
+    an mbarrier, tsd_k2_tma.cuh) must give exactly the default kernel's windows: the whole chain on synthetic frames (crops of every
+    size class: staged ones of 64 / 128 / 192 / 256-byte boxes, the direct-gather fallback for wide crops, copy and 2x2-AREA paths,
+    ROIs clipped at the right / bottom frame edge where the TMA zero-fills) against the oracle, at 1360x800 and at 4K, and on the 24
+    real frames against the reference's resultado.txt lines."""
+    red6, blue6 = templates
+    monkeypatch.setenv("TSD_K2", "tma")
+    with tsd.Context(0, "det") as ctx:
+        ctx.set_templates(red6, blue6)
+        for (H, W, F, N, seed) in ((800, 1360, 48, 200, 81), (2160, 3840, 2, 700, 82)):
+            frames = tsd.synth.make_frames(F, H, W, seed=tsd.synth.FRAME_SEED + seed)
+            boxes, off = tsd.synth.make_boxes(F, N, H, W, seed=tsd.synth.BOX_SEED + seed)
+            det, counts = ctx.detect_frames(frames, boxes, off)
+            exp, tot = [], np.zeros(4, np.int64)
+            for f in range(F):
+                o = oracle.detect_frame(frames[f], boxes[off[f]:off[f + 1]], red6, blue6)
+                tot += o["stage_counts"]
+                exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+            got = [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
+            assert counts.tolist() == tot.tolist() and got == exp, (H, W)
+        g = det_full150
+        idx = jpeg24["index"]
+        boxes = np.concatenate([g["boxes"][g["box_offsets"][f]:g["box_offsets"][f + 1]] for f in idx])
+        off = np.concatenate([[0], np.cumsum([g["box_offsets"][f + 1] - g["box_offsets"][f] for f in idx])]).astype(np.int32)
+        det, _ = ctx.detect_frames(jpeg24["frames"], boxes, off)
+        assert _lines(jpeg24["files"], det) == [ln for ln in resultado150 if ln.split(";")[0] in set(jpeg24["files"])]
+    # recognition flavour (32x32 windows): survivors' labels through the chain equal the default kernel's
+    r = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "rec_golden.npz"))
+    frames = tsd.synth.make_frames(16, seed=tsd.synth.FRAME_SEED + 83)
+    boxes, off = tsd.synth.make_boxes(16, 200, seed=tsd.synth.BOX_SEED + 83, enlarge=1.15, D=32)
+    res = []
+    for k2 in ("tma", "v2"):
+        monkeypatch.setenv("TSD_K2", k2)
+        with tsd.Context(0, "rec") as ctx:
+            ctx.set_lda(r["lda_W"], r["lda_b"])
+            res.append(ctx.detect_frames(frames, boxes, off, mode=tsd.RUN_RECOGNIZE))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
