@@ -587,7 +587,7 @@ static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, in
     if (npx <= 640) {
         int grid = cdiv(n_max, 4);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
-        k5_hist_kernel<640, 4, 8><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<640, 4, TSD_HIST_MINB><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
     } else {
         int grid = cdiv(n_max, 3);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;

@@ -4,7 +4,7 @@
 // k2_crop_resize_v2 gathers every tap straight from the frame: 12 byte loads per destination pixel row and lane through L1, the
 // kernel is bound by the LSU / instruction issue.  Here ONE elected lane per window issues cp.async.bulk.tensor (TMA, SASS UTMALDG)
 // for the window's ROI -- boxes of P bytes x 8 rows out of a 3-D tensor map over the frames (uint8 [F][H][3W]; the x coordinate
-// is the byte offset 3*x1, so the unaligned ROI arrives left-aligned with pitch P) -- into the warp's staging buffer behind an
+// is the byte offset 3*x1 rounded down to 16, so the ROI arrives with pitch P and up to 15 bytes of slack in front) -- into the warp's staging buffer behind an
 // mbarrier, and the resize runs from shared memory with the SAME arithmetic (11-bit fixed point, x coefficient clamp, y row clip)
 // restructured so that the horizontal pass of a source row is computed once and reused by the next destination row when both touch
 // it (for the typical 1.4x down-scale 36 instead of 50 row passes).  The 1888-byte window is assembled in shared memory and
@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(kTmaWarps * 32) k2_crop_resize_tma_kernel(
         const int4 c = coords[w];
         const int cx = min(c.x, W), cy = min(c.y, H);
         const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
-        const int P = ((cw * C + 63) >> 6) << 6, nops = (ch + kTmaBoxRows - 1) / kTmaBoxRows;
+        // the box starts at the 16-byte boundary at or below the ROI's first byte (an x coordinate that is not a multiple of 16 bytes
+        // faulted with "illegal instruction" on B200): `rem` bytes of slack in front of every staged row
+        const int rem = (cx * C) & 15;
+        const int P = ((cw * C + rem + 63) >> 6) << 6, nops = (ch + kTmaBoxRows - 1) / kTmaBoxRows;
         const bool staged = cw > 0 && ch > 0 && P <= 256 && ch <= 64 && P * kTmaBoxRows * nops <= kTmaStageBytes;
         if (!staged) {                                       // (warp-uniform) wide / tall / empty crops: direct gather
             k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl]);
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32) k2_crop_resize_tma_kernel(
             const int fr = win_frame[w];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's reads of the previous ROI precede the new copy
             mbar_expect_tx(bar, (uint32_t)(P * kTmaBoxRows * nops));
-            for (int i = 0; i < nops; i++) tma_load_3d(sb + i * kTmaBoxRows * P, map, bar, cx * C, cy + i * kTmaBoxRows, fr);
+            for (int i = 0; i < nops; i++) tma_load_3d(sb + i * kTmaBoxRows * P, map, bar, cx * C - rem, cy + i * kTmaBoxRows, fr);
         }
         // coefficient tables while the copy is in flight (float32 rounding as in OpenCV); lane doubles as dx and as dy
         int xs0, xd1, xa0, xa1;
@@ -124,13 +127,13 @@ __global__ void __launch_bounds__(kTmaWarps * 32) k2_crop_resize_tma_kernel(
         if (cw == D && ch == D) {                           // same size: copy
 #pragma unroll 5
             for (int dy = 0; dy < D; dy++) {
-                const uint8_t* p = sb + dy * P + li * C;
+                const uint8_t* p = sb + rem + dy * P + li * C;
                 if (act) { od[dy * D * C] = p[0]; od[dy * D * C + 1] = p[1]; od[dy * D * C + 2] = p[2]; }
             }
         } else if (cw == 2 * D && ch == 2 * D) {            // INTER_AREA 2x2 fast path
 #pragma unroll 5
             for (int dy = 0; dy < D; dy++) {
-                const uint8_t* q0 = sb + (2 * dy) * P + 2 * li * C;
+                const uint8_t* q0 = sb + rem + (2 * dy) * P + 2 * li * C;
                 const uint8_t* q1 = q0 + P;
                 if (act) {
 #pragma unroll
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32) k2_crop_resize_tma_kernel(
         } else {
             // general path: the horizontal pass of a source row lives in registers and is reused by the next destination row when
             // both touch it (row indices are warp-uniform, so the branches are too)
-            const uint8_t* px = sb + xs0;
+            const uint8_t* px = sb + rem + xs0;
             int cur0 = -1, cur1 = -1, h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
 #pragma unroll 5
             for (int dy = 0; dy < D; dy++) {

@@ -29,6 +29,12 @@
 #define TSD_HIST_UNROLL 8        // pixels per lane in flight in the two histogram passes (measured: 2: .266, 4: .274, 5: .283, 7-8: .259, 10: .310, 20: .369 ms)
 #endif
 
+#ifndef TSD_HIST_MINB
+#define TSD_HIST_MINB 8          // min resident CTAs per SM of k5_hist (register budget: 8 -> 64 registers)
+#endif
+#ifndef TSD_K2_MINB
+#define TSD_K2_MINB 12           // min resident CTAs per SM of k2_crop_resize_v2 (12 -> 40 registers)
+#endif
 #ifndef TSD_HIST_GROUP_UNROLL
 #define TSD_HIST_GROUP_UNROLL 2  // groups of 4 pixels per lane in flight in the aligned histogram passes (measured at 4096 frames: 1: .922, 2: .921, 3: .934, 4: .953 ms)
 #endif
@@ -380,7 +386,7 @@ __device__ __forceinline__ void k2_window_gather(const uint8_t* __restrict__ fra
 }
 
 template <int C, int D>
-__global__ void __launch_bounds__(128, 12) k2_crop_resize_v2_kernel(
+__global__ void __launch_bounds__(128, TSD_K2_MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
     uint8_t* __restrict__ windows, int out_stride) {
