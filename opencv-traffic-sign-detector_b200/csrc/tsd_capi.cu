@@ -534,6 +534,7 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
                            const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride, int nframes = 0) {
     if (n_max == 0) return TSD_OK;
     const int g4 = cdiv(n_max, 4);
+    int skip_tma = 0;
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
     // TSD_K2=tma: ROI staged by the Tensor Memory Accelerator (internal 16-byte window layout, BGR, D = 25 / 32, TMA-legal frame layout)
     if (c->k2_tma && ch == 3 && (D == 25 || D == 32) && nframes > 0 && out_stride % 16 == 0 && ((uintptr_t)windows % 16) == 0) {
@@ -547,16 +548,17 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
                 CU(cudaFuncSetAttribute(k2_crop_resize_tma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 c->attr_k2tma = true;
             }
-            const int grid = std::min(g4, c->sm_count * 4);  // persistent warps: 4 CTAs of 4 warps per SM (shared memory bound)
-            if (D == 25) k2_crop_resize_tma_kernel<25><<<grid, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
-            else k2_crop_resize_tma_kernel<32><<<grid, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
-            return check_launch(c, "k2_crop_resize_tma");
+            // one window per warp; the crops that do not fit the staging buffer are left to the gather kernel launched right after
+            if (D == 25) k2_crop_resize_tma_kernel<25><<<g4, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
+            else k2_crop_resize_tma_kernel<32><<<g4, kTmaWarps * 32, smem, c->cur>>>(maps, K2_ARGS, windows, out_stride);
+            TRY(check_launch(c, "k2_crop_resize_tma"));
+            skip_tma = 1;
         }
     }
-    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride);
+    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0);
     else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
     else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS

@@ -16,11 +16,9 @@
 
 namespace tsd {
 
-constexpr int kTmaStageBytes = 10240;                 // per warp: P x 8 x (number of 8-row boxes) must fit
 constexpr int kTmaWarps = 4;
 __host__ __device__ constexpr int tma_out_bytes(int D) { return (D * D * 3 + 127) & ~127; }      // assembled window rounded up to 128
 __host__ __device__ constexpr int tma_warp_bytes(int D) { return kTmaStageBytes + tma_out_bytes(D); }
-constexpr int kTmaBoxRows = 8;
 
 struct alignas(64) K2TensorMaps { CUtensorMap m[4]; };   // box widths 64, 128, 192, 256 bytes x 8 rows x 1 frame
 
@@ -82,20 +80,16 @@ __global__ void __launch_bounds__(kTmaWarps * 32) k2_crop_resize_tma_kernel(
     const int li = act ? lane : 0;
     for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
         const int4 c = coords[w];
+        const int fr = win_frame[w];                         // (issued with the coords load, not behind it)
         const int cx = min(c.x, W), cy = min(c.y, H);
         const int cw = min(c.z, W) - cx, ch = min(c.w, H) - cy;
         // the box starts at the 16-byte boundary at or below the ROI's first byte (an x coordinate that is not a multiple of 16 bytes
         // faulted with "illegal instruction" on B200): `rem` bytes of slack in front of every staged row
+        if (!k2_tma_takes(cx, cw, ch)) continue;             // (warp-uniform) wide / tall / empty crops: k2_crop_resize_v2, launched beside this kernel
         const int rem = (cx * C) & 15;
         const int P = ((cw * C + rem + 63) >> 6) << 6, nops = (ch + kTmaBoxRows - 1) / kTmaBoxRows;
-        const bool staged = cw > 0 && ch > 0 && P <= 256 && ch <= 64 && P * kTmaBoxRows * nops <= kTmaStageBytes;
-        if (!staged) {                                       // (warp-uniform) wide / tall / empty crops: direct gather
-            k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl]);
-            continue;
-        }
         if (lane == 0) {                                     // the ROI travels as nops boxes of P bytes x 8 rows (rows past the frame: zero fill)
             const CUtensorMap* map = &maps.m[(P >> 6) - 1];
-            const int fr = win_frame[w];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's reads of the previous ROI precede the new copy
             mbar_expect_tx(bar, (uint32_t)(P * kTmaBoxRows * nops));
             for (int i = 0; i < nops; i++) tma_load_3d(sb + i * kTmaBoxRows * P, map, bar, cx * C - rem, cy + i * kTmaBoxRows, fr);

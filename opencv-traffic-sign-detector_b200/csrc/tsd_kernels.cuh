@@ -290,6 +290,15 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 // 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
 // (Variants that lost on B200 -- crop staged in shared memory with cp.async, row reuse + staged output, aligned 32-bit tap loads,
 // one CTA per frame -- are documented with their measurements in DESIGN.md section 8 and live in the git history of round 1.)
+// Which windows the TMA-staged resize kernel takes (tsd_k2_tma.cuh): crops whose byte span, widened to whole 16-byte units in front
+// and 64-byte units in total, and whose rows, in boxes of 8, fit the per-warp staging buffer.  cx = clipped x1, cw / ch = clipped size.
+constexpr int kTmaStageBytes = 10240;
+constexpr int kTmaBoxRows = 8;
+__device__ __forceinline__ bool k2_tma_takes(int cx, int cw, int ch) {
+    const int P = ((cw * 3 + ((cx * 3) & 15) + 63) >> 6) << 6, nops = (ch + kTmaBoxRows - 1) / kTmaBoxRows;
+    return cw > 0 && ch > 0 && P <= 256 && ch <= 64 && P * kTmaBoxRows * nops <= kTmaStageBytes;
+}
+
 // One window by one warp, taps gathered straight from the frame (the body of k2_crop_resize_v2; also the path k2_crop_resize_tma
 // takes for crops that do not fit its staging buffer).  s_y = the warp's 32 x int4 scratch.
 template <int C, int D>
@@ -389,13 +398,19 @@ template <int C, int D>
 __global__ void __launch_bounds__(128, TSD_K2_MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride) {
+    uint8_t* __restrict__ windows, int out_stride, int skip_tma) {
     __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
     const int wl = threadIdx.x >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps)       // (the grid normally covers all windows: one trip)
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {     // (the grid normally covers all windows: one trip)
+        if (skip_tma) {                                      // the TMA-staged kernel, launched beside this one, takes the crops that fit its buffer
+            const int4 c = coords[w];
+            const int cx = min(c.x, W), cy = min(c.y, H);
+            if (k2_tma_takes(cx, min(c.z, W) - cx, min(c.w, H) - cy)) continue;
+        }
         k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl]);
+    }
 }
 
 // =====================================================================================================
