@@ -226,6 +226,8 @@ static int create_impl(tsd_ctx* c, int device) {
         int hb = (int)floor(i * a_h + (-0. * a_h)), sb = (int)floor(i * a_s + (-0. * a_s));
         t.hbin[i] = (uint8_t)(hb < kHistH ? hb : kHistH - 1);
         t.sbin[i] = (uint8_t)(sb < kHistS ? sb : kHistS - 1);
+        // the histogram kernels compute both bins arithmetically (hue_bin, (S * 60) >> 8): they must agree with calcHist's float rule
+        if ((i < 180 && hue_bin(i) != t.hbin[i]) || ((i * kHistS) >> 8) != t.sbin[i]) return fail(TSD_E_STATE, "histogram bin arithmetic disagrees with the table at %d", i);
     }
     CU(cudaMalloc(&c->d_tab, sizeof(Tables)));
     CU(cudaMemcpy(c->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
@@ -533,6 +535,7 @@ static int dev_expand(tsd_ctx* c, const int32_t* boxes, int n, double enlarge, i
 static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int64_t rs, int64_t fs, int ch, const int32_t* coords,
                            const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride, int nframes = 0) {
     if (n_max == 0) return TSD_OK;
+    if (rs * (int64_t)H >= ((int64_t)1 << 31)) return fail(TSD_E_INVALID, "a frame must span less than 2 GiB (row offsets are 32-bit)");
     const int g4 = cdiv(n_max, 4);
     int skip_tma = 0;
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
@@ -555,10 +558,12 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
             skip_tma = 1;
         }
     }
-    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma);
-    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma);
-    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0);
-    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0);
+    // aligned 32-bit tap loads need 4-byte aligned frames and strides and the number of frames (the last row of the last frame keeps byte loads)
+    const int wide_last = (nframes > 0 && ((uintptr_t)frames % 4) == 0 && rs % 4 == 0 && fs % 4 == 0) ? nframes - 1 : -2;
+    if (ch == 3 && D == 25) k2_crop_resize_v2_kernel<3, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma, wide_last);
+    else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma, wide_last);
+    else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0, -2);
+    else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0, -2);
     else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
     else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
@@ -586,15 +591,17 @@ static int dev_windows_index(tsd_ctx* c, const int32_t* boxes, const int32_t* bo
 static int dev_hist(tsd_ctx* c, const uint8_t* windows, const int32_t* n_ptr, int n_max, int npx, int ws, uint32_t* entries, WinMeta* meta,
                     float* E_T, int64_t e_stride) {
     if (n_max == 0) return TSD_OK;
+#define HIST_ARGS windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride
     if (npx <= 640) {
         int grid = cdiv(n_max, 4);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
-        k5_hist_kernel<640, 4, TSD_HIST_MINB><<<grid, 128, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<640, 4, TSD_HIST_MINB, HsvLut><<<grid, 128, sizeof(HistKSmem<640, 4, HsvLut>), c->cur>>>(HIST_ARGS);
     } else {
         int grid = cdiv(n_max, 3);
         if (grid > c->sm_count * TSD_HIST_GRID) grid = c->sm_count * TSD_HIST_GRID;
-        k5_hist_kernel<1024, 3, 1><<<grid, 96, 0, c->cur>>>(windows, n_ptr, n_max, npx, ws, ent_stride(npx), c->d_tab, entries, meta, E_T, e_stride);
+        k5_hist_kernel<1024, 3, 1, HsvLut><<<grid, 96, sizeof(HistKSmem<1024, 3, HsvLut>), c->cur>>>(HIST_ARGS);
     }
+#undef HIST_ARGS
     return check_launch(c, "k5_hist");
 }
 
@@ -751,7 +758,7 @@ int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W
     CU(cudaSetDevice(c->device));
     // Device pointers: the kernel zero-fills a window whose clipped crop is empty (cv2.resize would raise; the chain never asks for
     // one: K1 drops such boxes).  Host pointers are checked here, like the reference's own exceptions.
-    if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows, D * D * channels);
+    if (mem == TSD_MEM_DEVICE) return dev_crop_resize(c, frames, H, W, row_stride, frame_stride, channels, coords, win_frame, nullptr, n, D, windows, D * D * channels, nframes);
     for (int i = 0; i < n; i++) {
         const int32_t* q = coords + 4 * (size_t)i;
         if (win_frame[i] < 0 || win_frame[i] >= nframes) return fail(TSD_E_INVALID, "window %d: frame %d not in [0,%d)", i, win_frame[i], nframes);
@@ -765,7 +772,7 @@ int tsd_crop_resize(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W
     TRY(s.in(coords, (size_t)n * 16, &dc));
     TRY(s.in(win_frame, (size_t)n * 4, &dwf));
     TRY(s.alloc(&dw, (size_t)n * D * D * channels));
-    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, channels, (int32_t*)dc, (int32_t*)dwf, nullptr, n, D, (uint8_t*)dw, D * D * channels));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, channels, (int32_t*)dc, (int32_t*)dwf, nullptr, n, D, (uint8_t*)dw, D * D * channels, nframes));
     TRY(s.out(windows, dw, (size_t)n * D * D * channels));
     CU(cudaStreamSynchronize(c->stream));
     return TSD_OK;
@@ -792,7 +799,7 @@ int tsd_windows(tsd_ctx* c, const uint8_t* frames, int nframes, int H, int W, in
     TRY(s.alloc(&dwf, (size_t)nb * 4));
     TRY(s.alloc(&dw, (size_t)nb * D * D * 3));
     TRY(dev_windows_index(c, (int32_t*)db, (int32_t*)dbo, nframes, H, W, enlarge, (int32_t*)dcnt, (int32_t*)dwo, (int32_t*)dc, (int32_t*)dwf));
-    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, 3, (int32_t*)dc, (int32_t*)dwf, (int32_t*)dwo + nframes, nb, D, (uint8_t*)dw, D * D * 3));
+    TRY(dev_crop_resize(c, (uint8_t*)df, H, W, row_stride, frame_stride, 3, (int32_t*)dc, (int32_t*)dwf, (int32_t*)dwo + nframes, nb, D, (uint8_t*)dw, D * D * 3, nframes));
     TRY(s.out(win_offsets, dwo, (size_t)(nframes + 1) * 4));
     CU(cudaStreamSynchronize(c->stream));
     const int tot = win_offsets[nframes];

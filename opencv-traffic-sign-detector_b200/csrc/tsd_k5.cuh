@@ -107,20 +107,42 @@ struct __align__(16) HistScratch {
     uint16_t binof[CAP];
 };
 
-struct HsvLut {                 // per CTA
-    int32_t sdiv[256], hdiv[256];
-    uint8_t hbin[256];
-};
-
-__device__ __forceinline__ void load_hsv_lut(HsvLut& t, const Tables* __restrict__ tab) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { t.sdiv[i] = tab->sdiv[i]; t.hdiv[i] = tab->hdiv[i]; t.hbin[i] = tab->hbin[i]; }
+// calcHist's hue bin floor(H * 50 / 180.0) for H in [0, 180) without a table: (H * 5) / 18 == (H * 18205) >> 16 (checked below for
+// every H; tsd_create checks the same expression against the host-built Tables::hbin and fails loudly if they ever differ)
+__host__ __device__ constexpr int hue_bin(int H) { return (H * 18205) >> 16; }
+constexpr bool hue_bin_ok() {
+    for (int H = 0; H < 180; H++) if (hue_bin(H) != (H * 5) / 18) return false;
+    return true;
 }
+static_assert(hue_bin_ok(), "hue_bin");
+
+struct HsvLut {                 // per CTA: OpenCV's two division tables (RGB2HSV_b)
+    int32_t sdiv[256], hdiv[256];
+    __device__ __forceinline__ int sd(int v, int) const { return sdiv[v]; }
+    __device__ __forceinline__ int hd(int d, int) const { return hdiv[d]; }
+};
+__device__ __forceinline__ void load_hsv_lut(HsvLut& t, const Tables* __restrict__ tab) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { t.sdiv[i] = tab->sdiv[i]; t.hdiv[i] = tab->hdiv[i]; }
+}
+// H-S histogram bin of one BGR pixel (cv2.cvtColor BGR2HSV + calcHist([0,1], [50,60], [0,180,0,256]), DET:577-580)
+template <class LUT>
+__device__ __forceinline__ int hs_bin(int b, int g, int r, const LUT& lut, int lane) {
+    const int v = max(b, max(g, r)), m = min(b, min(g, r));
+    const int d = v - m;
+    int h = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * d) : (r - g + 4 * d);
+    const int S = (d * lut.sd(v, lane) + (1 << 11)) >> 12;
+    h = (h * lut.hd(d, lane) + (1 << 11)) >> 12;
+    const int H = h < 0 ? h + 180 : h;
+    return hue_bin(H) * kHistS + ((S * kHistS) >> 8);        // floor(S*60/256.0) exactly (60/256 is a dyadic rational)
+}
+
+__device__ __forceinline__ void mark_bin(uint32_t* bitmap, int bin) { atomicOr(&bitmap[bin >> 5], 1u << (bin & 31)); }
 
 // px: window pixels (global; may have been rewritten by this warp -> plain loads), e: entries out (global, es words,
 // zero-padded to a multiple of 4), meta out, Eg: optional group energies (E_T + w, stride e_stride).
 // Returns nnz.  All 32 lanes must call.  On return sw.cnt / sw.binof hold the entries (used to fill a dense copy).
-template <int CAP>
-__device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const HsvLut& lut, HistScratch<CAP>& sw,
+template <int CAP, class LUT>
+__device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const LUT& lut, HistScratch<CAP>& sw,
                                                uint32_t* __restrict__ e, WinMeta* meta, float* Eg, int64_t e_stride, bool gram_aux = false) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < 96; i += 32) sw.bitmap[i] = 0;
@@ -142,13 +164,10 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int p = 4 * g + j;
-                const int b = (int)(col[j] & 255u), gg = (int)((col[j] >> 8) & 255u), r = (int)(col[j] >> 16);
-                int H, S, V;
-                bgr2hsv(b, gg, r, lut.sdiv, lut.hdiv, H, S, V);
-                const int bin = (int)lut.hbin[H] * kHistS + ((S * kHistS) >> 8);
+                const int bin = hs_bin((int)(col[j] & 255u), (int)((col[j] >> 8) & 255u), (int)(col[j] >> 16), lut, lane);
                 bins[j] = (uint32_t)bin;
                 if (p < npx) {
-                    atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
+                    mark_bin(sw.bitmap, bin);
                     hsh += pix_hash32(p, col[j]);
                 }
             }
@@ -158,11 +177,9 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
 #pragma unroll kHistUnroll
     for (int p = lane; p < npx; p += 32) {
         const int b = px[3 * p], g = px[3 * p + 1], r = px[3 * p + 2];
-        int H, S, V;
-        bgr2hsv(b, g, r, lut.sdiv, lut.hdiv, H, S, V);
-        const int bin = (int)lut.hbin[H] * kHistS + ((S * kHistS) >> 8);   // floor(S*60/256.0) exactly (60/256 is a dyadic rational)
+        const int bin = hs_bin(b, g, r, lut, lane);
         sw.binbuf[p] = (uint16_t)bin;
-        atomicOr(&sw.bitmap[bin >> 5], 1u << (bin & 31));
+        mark_bin(sw.bitmap, bin);
         hsh += pix_hash32(p, (uint32_t)(b | (g << 8) | (r << 16)));
     }
     }
@@ -250,24 +267,31 @@ __device__ __forceinline__ int hist_build_warp(const uint8_t* px, int npx, const
     return nnz;
 }
 
-template <int CAP, int kHistWarps, int MINB>      // warps per CTA: 4 for D=25, 3 for D=32 (static shared memory <= 48 KB)
+template <int CAP, int kHistWarps, class LUT>
+struct HistKSmem {
+    LUT lut;
+    HistScratch<CAP> w[kHistWarps];
+};
+template <int CAP, int kHistWarps, int MINB, class LUT>
 __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const uint8_t* __restrict__ windows, const int32_t* __restrict__ n_ptr,
                                                                   int n_max, int npx, int ws, int es, const Tables* __restrict__ tab,
                                                                   uint32_t* __restrict__ entries, WinMeta* __restrict__ meta,
                                                                   float* __restrict__ E_T, int64_t e_stride) {
     constexpr int NCH = (CAP * 3 / 16 + 31) / 32;            // 128-bit chunks per lane covering one window
     static_assert(sizeof(uint32_t) * CAP >= NCH * 32 * 16, "the pixel staging area must fit into HistScratch::cnt");
-    __shared__ HsvLut lut;
-    __shared__ HistScratch<CAP> s_w[kHistWarps];
-    load_hsv_lut(lut, tab);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HistKSmem<CAP, kHistWarps, LUT>& S = *reinterpret_cast<HistKSmem<CAP, kHistWarps, LUT>*>(smem_raw);
+    const LUT& lut = S.lut;
+    load_hsv_lut(S.lut, tab);
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    HistScratch<CAP>& sw = S.w[wid];
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
     const int nwarps = gridDim.x * kHistWarps;
     const bool staged = (ws & 15) == 0 && ((uintptr_t)windows & 15) == 0 && ws <= NCH * 32 * 16;
     if (!staged) {                                           // packed public layout: pixels straight from global memory
         for (int w = blockIdx.x * kHistWarps + wid; w < n; w += nwarps)
-            hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
+            hist_build_warp<CAP>(windows + (int64_t)w * ws, npx, lut, sw, entries + (int64_t)w * es, meta + w,
                                  E_T ? E_T + w : nullptr, e_stride, E_T != nullptr);
         return;
     }
@@ -276,8 +300,8 @@ __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const ui
     const int nch = ws >> 4;
     uint4 r[NCH];
     // pixels are staged in the warp's own count array: pass A (the only reader of the pixels) ends before the counts are zeroed,
-    // and the next window waits in registers until then -- 2 KB less shared memory per warp, 8 instead of 6 CTAs per SM
-    uint4* s_px_w = reinterpret_cast<uint4*>(s_w[wid].cnt);
+    // and the next window waits in registers until then
+    uint4* s_px_w = reinterpret_cast<uint4*>(sw.cnt);
     int w = blockIdx.x * kHistWarps + wid;
     if (w < n) {
         const uint4* g = reinterpret_cast<const uint4*>(windows + (int64_t)w * ws);
@@ -293,7 +317,7 @@ __global__ void __launch_bounds__(kHistWarps * 32, MINB) k5_hist_kernel(const ui
 #pragma unroll
             for (int k = 0; k < NCH; k++) if (lane + 32 * k < nch) r[k] = __ldg(g + lane + 32 * k);
         }
-        hist_build_warp<CAP>(reinterpret_cast<const uint8_t*>(s_px_w), npx, lut, s_w[wid], entries + (int64_t)w * es, meta + w,
+        hist_build_warp<CAP>(reinterpret_cast<const uint8_t*>(s_px_w), npx, lut, sw, entries + (int64_t)w * es, meta + w,
                              E_T ? E_T + w : nullptr, e_stride, E_T != nullptr);
     }
 }

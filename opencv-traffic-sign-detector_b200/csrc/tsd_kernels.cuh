@@ -11,7 +11,7 @@
 #include <float.h>
 
 #ifndef TSD_K2_UNROLL
-#define TSD_K2_UNROLL 5          // destination rows of the K2 general path unrolled together (loads in flight per lane = 12 x this)
+#define TSD_K2_UNROLL 3          // destination rows of the K2 general path per trip (all their loads in flight together; measured at 4096 frames, wide loads: 2: .780, 3: .758, 4: .821, 5: .98 ms with 40 registers)
 #endif
 #ifndef TSD_K3_UNROLL
 #define TSD_K3_UNROLL 4          // pixels per lane in flight in the mask kernel
@@ -34,6 +34,9 @@
 #endif
 #ifndef TSD_K2_MINB
 #define TSD_K2_MINB 12           // min resident CTAs per SM of k2_crop_resize_v2 (12 -> 40 registers)
+#endif
+#ifndef TSD_K2_WIDE
+#define TSD_K2_WIDE 1            // K2 general path: aligned 32-bit tap loads + IDP.2A horizontal pass (0: byte loads)
 #endif
 #ifndef TSD_HIST_GROUP_UNROLL
 #define TSD_HIST_GROUP_UNROLL 2  // groups of 4 pixels per lane in flight in the aligned histogram passes (measured at 4096 frames: 1: .922, 2: .921, 3: .934, 4: .953 ms)
@@ -299,12 +302,94 @@ __device__ __forceinline__ bool k2_tma_takes(int cx, int cw, int ch) {
     return cw > 0 && ch > 0 && P <= 256 && ch <= 64 && P * kTmaBoxRows * nops <= kTmaStageBytes;
 }
 
+// The D destination rows of one window in the general (two-pass 11-bit fixed point) case.  XDC: the second tap sits C bytes after the
+// first in every column (xd1 == C, true for every crop wider than D).  (v0 >> 16) + (v1 >> 16) + 2 is folded into one multiply-add:
+// ((v1 + (2 << 16)) >> 16) == (v1 >> 16) + 2.
+template <int C, int D, bool XDC>
+__device__ __forceinline__ void k2_rows(const uint8_t* __restrict__ px, const int4* s_y, int xd1, int xa0, int xa1, uint8_t* __restrict__ dst, bool act) {
+#pragma unroll kK2Unroll
+    for (int dy = 0; dy < D; dy++) {
+        const int4 yc = s_y[dy];
+        const int b0 = yc.z, b1 = yc.w;
+        const uint8_t* p0 = px + (uint32_t)yc.x;
+        const uint8_t* p1 = px + (uint32_t)yc.y;
+        const uint8_t* q0 = XDC ? p0 + C : p0 + xd1;
+        const uint8_t* q1 = XDC ? p1 + C : p1 + xd1;
+        int v[C];
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int t0 = __ldg(p0 + k) * xa0 + __ldg(q0 + k) * xa1;
+            const int t1 = __ldg(p1 + k) * xa0 + __ldg(q1 + k) * xa1;
+            v[k] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4) + (2 << 16)) >> 16)) >> 2;
+        }
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
+        }
+    }
+}
+
+// The same rows with WIDE loads (C = 3, 4-byte aligned frames and strides): the 6 consecutive bytes a lane needs of a source row (two
+// taps x three channels) come from 2-3 aligned 32-bit loads instead of 6 byte loads (the byte-load kernel keeps the L1 data pipe
+// ~70 % busy: 645 wavefronts per window), a funnel shift brings them to bit 0, two byte permutes pair each channel's taps and one
+// IDP.2A per channel (16-bit coefficients x 8-bit taps) is the horizontal pass.  The second tap is read at +3 bytes in every
+// column: where cv2 clamps it onto the first (x = 0 of an up-scale, the last column) its coefficient is 0.  An aligned word may reach
+// up to 6 bytes past the bytes needed, so a window on the last row of the last frame takes the byte loads.
+template <int D>
+__device__ __forceinline__ void k2_rows_wide(const uint8_t* __restrict__ px, const int4* s_y, int xa0, int xa1, uint8_t* dst, bool act) {
+    const unsigned o = (unsigned)(reinterpret_cast<uintptr_t>(px) & 3);
+    const unsigned o8 = o * 8;
+    const uint8_t* pa = px - o;
+    asm volatile("" : "+l"(pa), "+l"(dst));                  // both stay in registers: one 64-bit add per row pointer, immediate store offsets
+    const bool third = o == 3;                               // bytes o .. o+5 of the aligned words: a third word only from offset 3
+    const unsigned xa = (unsigned)xa0 | ((unsigned)xa1 << 16);
+    // kK2Unroll destination rows per trip: all their loads are issued before the first result is stored
+    for (int dy0 = 0; dy0 < D; dy0 += kK2Unroll) {
+        uint32_t a0[kK2Unroll], a1[kK2Unroll], a2[kK2Unroll], c0[kK2Unroll], c1[kK2Unroll], c2[kK2Unroll];
+        int b0[kK2Unroll], b1[kK2Unroll];
+#pragma unroll
+        for (int u = 0; u < kK2Unroll; u++) {
+            const int4 yc = s_y[min(dy0 + u, D - 1)];
+            b0[u] = yc.z; b1[u] = yc.w;
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(pa + (uint32_t)yc.x);
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(pa + (uint32_t)yc.y);
+            a0[u] = __ldg(q0); a1[u] = __ldg(q0 + 1); a2[u] = third ? __ldg(q0 + 2) : 0u;
+            c0[u] = __ldg(q1); c1[u] = __ldg(q1 + 1); c2[u] = third ? __ldg(q1 + 2) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kK2Unroll; u++) {
+            const int dy = dy0 + u;
+            const uint32_t lo0 = __funnelshift_r(a0[u], a1[u], o8), hi0 = __funnelshift_r(a1[u], a2[u], o8);      // bytes 0-3 / 4-7 counted from the first tap
+            const uint32_t lo1 = __funnelshift_r(c0[u], c1[u], o8), hi1 = __funnelshift_r(c1[u], c2[u], o8);
+            const uint32_t bg0 = __byte_perm(lo0, hi0, 0x4130), r0 = __byte_perm(lo0, hi0, 0x0052);               // [B0 B1 G0 G1], [R0 R1 . .]
+            const uint32_t bg1 = __byte_perm(lo1, hi1, 0x4130), r1 = __byte_perm(lo1, hi1, 0x0052);
+            int v[3];
+            {
+                const int t0 = (int)__dp2a_lo(xa, bg0, 0u), t1 = (int)__dp2a_lo(xa, bg1, 0u);
+                v[0] = (((b0[u] * (t0 >> 4)) >> 16) + ((b1[u] * (t1 >> 4) + (2 << 16)) >> 16)) >> 2;
+            }
+            {
+                const int t0 = (int)__dp2a_hi(xa, bg0, 0u), t1 = (int)__dp2a_hi(xa, bg1, 0u);
+                v[1] = (((b0[u] * (t0 >> 4)) >> 16) + ((b1[u] * (t1 >> 4) + (2 << 16)) >> 16)) >> 2;
+            }
+            {
+                const int t0 = (int)__dp2a_lo(xa, r0, 0u), t1 = (int)__dp2a_lo(xa, r1, 0u);
+                v[2] = (((b0[u] * (t0 >> 4)) >> 16) + ((b1[u] * (t1 >> 4) + (2 << 16)) >> 16)) >> 2;
+            }
+            if (act && dy < D) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) dst[dy * D * 3 + k] = (uint8_t)v[k];
+            }
+        }
+    }
+}
+
 // One window by one warp, taps gathered straight from the frame (the body of k2_crop_resize_v2; also the path k2_crop_resize_tma
 // takes for crops that do not fit its staging buffer).  s_y = the warp's 32 x int4 scratch.
 template <int C, int D>
 __device__ __forceinline__ void k2_window_gather(const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
                                                  const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, int w,
-                                                 uint8_t* __restrict__ windows, int out_stride, int4* s_y) {
+                                                 uint8_t* __restrict__ windows, int out_stride, int4* s_y, int wide_last = -2) {
     const int lane = threadIdx.x & 31;
     const int4 c = coords[w];
     const int cx = min(c.x, W), cy = min(c.y, H);
@@ -372,33 +457,21 @@ __device__ __forceinline__ void k2_window_gather(const uint8_t* __restrict__ fra
     }
     const uint8_t* px = src + xs0;
     __syncwarp();                                            // (the previous window's rows are consumed)
-    s_y[lane] = make_int4(yr0, yr1, yb0, yb1);           // one 128-bit broadcast read per destination row instead of 4 shuffles
+    // one 128-bit broadcast read per destination row instead of 4 shuffles; the rows travel as 32-bit BYTE offsets (the host checks
+    // that a frame spans less than 2 GiB), so a tap address is one 64-bit add instead of a 64-bit multiply-add per row
+    s_y[lane] = make_int4(yr0 * (int)row_stride, yr1 * (int)row_stride, yb0, yb1);
     __syncwarp();
-#pragma unroll kK2Unroll
-    for (int dy = 0; dy < D; dy++) {
-        const int4 yc = s_y[dy];
-        const int r0 = yc.x, r1 = yc.y, b0 = yc.z, b1 = yc.w;
-        const uint8_t* p0 = px + (int64_t)r0 * row_stride;
-        const uint8_t* p1 = px + (int64_t)r1 * row_stride;
-        int v[C];
-#pragma unroll
-        for (int k = 0; k < C; k++) {
-            const int t0 = __ldg(p0 + k) * xa0 + __ldg(p0 + xd1 + k) * xa1;
-            const int t1 = __ldg(p1 + k) * xa0 + __ldg(p1 + xd1 + k) * xa1;
-            v[k] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;       // (IMAD.HI variant measured slower)
-        }
-        if (act) {
-#pragma unroll
-            for (int k = 0; k < C; k++) dst[dy * D * C + k] = (uint8_t)v[k];
-        }
-    }
+    // every down-scale (cw > D) has its second tap exactly one pixel to the right in every column: the tap offsets are immediates
+    if (C == 3 && TSD_K2_WIDE && wide_last >= -1 && !(win_frame[w] == wide_last && cy + ch == H)) k2_rows_wide<D>(px, s_y, xa0, xa1, dst, act);
+    else if (__all_sync(0xffffffffu, xd1 == C)) k2_rows<C, D, true>(px, s_y, C, xa0, xa1, dst, act);
+    else k2_rows<C, D, false>(px, s_y, xd1, xa0, xa1, dst, act);
 }
 
 template <int C, int D>
 __global__ void __launch_bounds__(128, TSD_K2_MINB) k2_crop_resize_v2_kernel(
     const uint8_t* __restrict__ frames, int H, int W, int64_t row_stride, int64_t frame_stride,
     const int4* __restrict__ coords, const int32_t* __restrict__ win_frame, const int32_t* __restrict__ n_ptr, int n_max,
-    uint8_t* __restrict__ windows, int out_stride, int skip_tma) {
+    uint8_t* __restrict__ windows, int out_stride, int skip_tma, int wide_last) {
     __shared__ int4 s_y[4][32];                              // per warp: (row0, row1, weight0, weight1) of every destination row
     const int wl = threadIdx.x >> 5;
     const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
@@ -409,7 +482,7 @@ __global__ void __launch_bounds__(128, TSD_K2_MINB) k2_crop_resize_v2_kernel(
             const int cx = min(c.x, W), cy = min(c.y, H);
             if (k2_tma_takes(cx, min(c.z, W) - cx, min(c.w, H) - cy)) continue;
         }
-        k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl]);
+        k2_window_gather<C, D>(frames, H, W, row_stride, frame_stride, coords, win_frame, w, windows, out_stride, s_y[wl], wide_last);
     }
 }
 
