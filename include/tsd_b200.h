@@ -260,6 +260,9 @@ TSD_API int tsd_stat_staged_bytes(tsd_ctx *ctx, int64_t *total, int reset);
  * calls (names[i] / ms[i] for i < returned count). */
 TSD_API int tsd_set_profiling(tsd_ctx *ctx, int on);
 TSD_API int tsd_stage_times(tsd_ctx *ctx, const char **names, float *ms, int cap);
+/* tsd_set_profiling(ctx, 2) keeps consecutive tsd_enqueue_frames calls overlapped (two scratch slots, two streams) and
+ * tsd_timeline returns every stage boundary recorded since then, in enqueue order, as milliseconds after the first one. */
+TSD_API int tsd_timeline(tsd_ctx *ctx, const char **names, float *ms, int cap);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "tsd_fetch_previous": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tsd_set_profiling": (_i, [_vp, _i]),
     "tsd_stage_times": (_i, [_vp, _vp, _vp, _i]),
+    "tsd_timeline": (_i, [_vp, _vp, _vp, _i]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -59,6 +59,8 @@ struct tsd_ctx {
     size_t slot_cap = 0, slot_fcap = 0, slot_todo = 0;   // windows / per-frame entries / k5_pairs work-list entries per slot
     int slot_rw = 1;                         // words per bit row of the pair-class matrix the slot layout is sized for (sticky maximum)
     cudaEvent_t ev_slot_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_w1[2] = {nullptr, nullptr};   // slot's batch has finished its throughput-bound front half (K1 .. pair classes)
+    int stagger = 1;                         // TSD_STAGGER: the front half of a batch starts only when the previous batch's has ended
     cudaStream_t os[2] = {nullptr, nullptr};                                // per slot: the chain's stream
     DevBuf b_summary, b_order, b_gramdone;
     unsigned* d_tickets = nullptr;           // zero-initialised counters of the last-CTA-done scans: [slot 0 | slot 1 | stage calls] x 8
@@ -96,9 +98,10 @@ struct tsd_ctx {
     DevBuf b_coords, b_winframe, b_windows, b_entries, b_meta, b_list, b_flags, b_cnt, b_winoff, b_survcnt, b_survoff,
         b_slots, b_pairs, b_energy, b_red, b_blue, b_bits, b_id, b_hund, b_emit, b_detcnt, b_detoff, b_det, b_gray, b_hog, b_labels, b_scores;
     int last_mode = 0;
-    bool profiling = false;
+    int profiling = 0;
     int keep_masks = 0;                      // TSD_KEEP_MASKS=1: the chain also writes K3's byte masks (nobody reads them there)
     int use_gram = 1;                        // TSD_GRAM=0: pair classes of every frame from the CUDA-core kernel (k5_pairs)
+    int fold_per_sm_cap = 2;                 // TSD_FOLD_PER_SM: cap of resident k5_fold_warp CTAs per SM (0 = as many as fit; measured with the staggered overlap at 4096 frames: 0: 3.22, 1: 3.20, 2: 3.09, 3: 3.18 ms per step)
     int fold_cta_cost = 0;                   // TSD_FOLD_CTA_COST: frames with at least this many merge-band pairs go to the CTA fold (0 = by size only)
     // function attributes (dynamic shared memory opt-in) are set once per context: per-context flags, no process-wide statics
     int fold_per_sm[4] = {0, 0, 0, 0};       // resident CTAs per SM of the four k5_fold_warp instantiations (0 = not queried yet)
@@ -133,6 +136,20 @@ static int check_launch(tsd_ctx* c, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TSD_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
     c->launches++;
+    return TSD_OK;
+}
+
+// Event record / wait on c->cur that also works while the stream is being captured into a CUDA graph (external event nodes).
+static int ev_record(tsd_ctx* c, cudaEvent_t ev) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(c->cur, &st));
+    CU(cudaEventRecordWithFlags(ev, c->cur, st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return TSD_OK;
+}
+static int ev_wait(tsd_ctx* c, cudaEvent_t ev) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(c->cur, &st));
+    CU(cudaStreamWaitEvent(c->cur, ev, st == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault));
     return TSD_OK;
 }
 
@@ -191,6 +208,7 @@ static int create_impl(tsd_ctx* c, int device) {
         CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&c->os[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_slot_fork[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_w1[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
@@ -204,6 +222,8 @@ static int create_impl(tsd_ctx* c, int device) {
     { const char* e = getenv("TSD_GRAPH"); if (e) c->use_graph = atoi(e) != 0; }
     { const char* e = getenv("TSD_K2"); if (e) c->k2_tma = strcmp(e, "tma") == 0; }
     { const char* e = getenv("TSD_FOLD_CTA_COST"); if (e) c->fold_cta_cost = atoi(e); }
+    { const char* e = getenv("TSD_FOLD_PER_SM"); if (e) c->fold_per_sm_cap = atoi(e); }
+    { const char* e = getenv("TSD_STAGGER"); if (e) c->stagger = atoi(e); }
     {   // keep stream-ordered temporaries cached in the pool instead of returning them to the OS at every synchronise
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -315,6 +335,7 @@ int tsd_destroy(tsd_ctx* c) {
     for (int i = 0; i < 2; i++) {
         if (c->ev_slot_fork[i]) cudaEventDestroy(c->ev_slot_fork[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+        if (c->ev_w1[i]) cudaEventDestroy(c->ev_w1[i]);
         if (c->os[i]) cudaStreamDestroy(c->os[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
@@ -368,7 +389,7 @@ int64_t tsd_launch_count(tsd_ctx* c) { return c ? c->launches : 0; }
 int tsd_set_profiling(tsd_ctx* c, int on) {
     if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
     TRY(join_pending(c));
-    c->profiling = on != 0;
+    c->profiling = on;                                       // 1: per-stage times, batches serialised; 2: timeline, batches overlapped as usual (both without CUDA graphs)
     c->ev_used = 0;                                          // (re)start accumulating
     return TSD_OK;
 }
@@ -393,6 +414,23 @@ int tsd_stage_times(tsd_ctx* c, const char** names, float* ms, int cap) {
     }
     int n = 0;
     for (size_t k = 0; k < uniq.size() && n < cap; k++, n++) { names[n] = uniq[k].c_str(); ms[n] = sum[k]; }
+    return n;
+}
+
+// tsd_set_profiling(ctx, 2): every mark since then as (name, milliseconds after the first mark), in enqueue order -- the batches
+// keep overlapping, so this is the timeline of the two-slot pipeline.  Synchronises.
+int tsd_timeline(tsd_ctx* c, const char** names, float* ms, int cap) {
+    if (!c) return fail(TSD_E_INVALID, "ctx is NULL");
+    cudaSetDevice(c->device);
+    TRY(join_pending(c));
+    cudaStreamSynchronize(c->stream);
+    int n = 0;
+    for (int i = 0; i < c->ev_used && n < cap; i++, n++) {
+        float t = 0;
+        if (i) cudaEventElapsedTime(&t, c->ev[0], c->ev[i]);
+        names[n] = c->ev_names[i].c_str();
+        ms[n] = t;
+    }
     return n;
 }
 
@@ -638,7 +676,11 @@ static int launch_folds(tsd_ctx* c, int variant, const FoldParams& P, int nframe
     // frames predicted to merge often go to the CTA fold too (batches large enough for a straggler to matter)
     const int cost_min = (cost && nframes >= 256) ? c->fold_cta_cost : 0;
     int grid = cdiv(nframes, warps);
-    if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
+    // Resident fold CTAs per SM: each holds 16 K registers and ~56 KB of shared memory, so the four that fit take the WHOLE SM and the
+    // kernels of the other batch (two-slot overlap) cannot run beside them; a cap leaves room (the fold is bound by latency, not by
+    // the number of its warps: one batch needs ~1100 warp-milliseconds spread over the ~2.6 ms the other batch's kernels take).
+    const int cap_sm = (c->fold_per_sm_cap > 0 && c->fold_per_sm_cap < per_sm) ? c->fold_per_sm_cap : per_sm;
+    if (grid > cap_sm * c->sm_count) grid = cap_sm * c->sm_count;
     k5_fold_warp_kernel<256, CAP><<<grid, warps * 32, smem, c->cur>>>(P, nframes, M, RW, cut, order, counter, kFoldCtaMin, cost_sorted, cost_min);
     TRY(check_launch(c, "k5_fold_warp"));
     if (max_n > kFoldCtaMin || cost_min > 0) {
@@ -658,7 +700,7 @@ static inline size_t todo_capacity(int nframes, int max_n) {
 
 static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint32_t* entries, WinMeta* meta, const int32_t* offsets, int nframes,
                     int npx, int do_hist, int do_coords, double hist_tol, double coord_tol, int32_t* list, uint8_t* flags, int32_t* out_count,
-                    int max_n, uint32_t* M, int32_t* todo, float* E_T, int64_t e_stride, int32_t* surv_offsets) {
+                    int max_n, uint32_t* M, int32_t* todo, float* E_T, int64_t e_stride, int32_t* surv_offsets, cudaEvent_t front_done = nullptr) {
     FoldParams P;
     P.windows = windows; P.coords = (int4*)coords; P.entries = entries; P.meta = meta; P.offsets = offsets;
     P.list = list; P.flags = flags; P.out_count = out_count; P.simtab = c->d_simtab; P.simtab_n = c->simtab_n; P.tab = c->d_tab;
@@ -723,6 +765,7 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
         }
         mark(c, "k5_pairs");
     }
+    if (front_done) TRY(ev_record(c, front_done));           // the next batch's front half may start (enqueue_chain)
     TRY(npx <= 640 ? launch_folds<640>(c, 0, P, nframes, M, RW, cut, cost, max_n) : launch_folds<1024>(c, 1, P, nframes, M, RW, cut, cost, max_n));
     // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
@@ -1273,6 +1316,12 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     DetRec* det = (DetRec*)c->b_det.p + wo;
     c->order_off = (size_t)fo;
     const int32_t* d_nwin = winoff + cf;
+    // Two-slot overlap: consecutive batches run on two streams so that the latency-bound fold of one hides under the throughput-bound
+    // front half (K1, K2, histograms, pair classes) of the next.  Left alone the two streams share the GPU evenly, drift into
+    // phase and end up folding at the same time (3.24 ms per 4096-frame step against 2.6 ms of kernel work); making the front
+    // half of a batch wait for the previous batch's keeps them a half period apart.
+    const bool stagger = B.in_slot && c->stagger;
+    if (stagger) TRY(ev_wait(c, c->ev_w1[B.sidx ^ 1]));
     mark(c, "start");
     // K1: candidate loop of MSERTrafficSignDetector (DET:116-120)
     TRY(dev_windows_index(c, d_boxes, d_box_offsets, cf, H, W, c->cfg.enlarge, cnt, winoff, coords, winframe));
@@ -1299,7 +1348,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap, survoff));
+                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap, survoff, stagger ? c->ev_w1[B.sidx] : nullptr));
     k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
     TRY(check_launch(c, "k5_gather"));
     mark(c, "k5_fold");
@@ -1368,7 +1417,7 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
     const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
                                        (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
                                        (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
-                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->stage_gran, (uint64_t)c->k2_tma};
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->fold_per_sm_cap, (uint64_t)c->stagger, (uint64_t)c->stage_gran, (uint64_t)c->k2_tma};
     c->graph_clock++;
     for (auto& g : c->graphs)
         if (g.key == key) {
@@ -1433,7 +1482,7 @@ static int enqueue_impl(tsd_ctx* c, int mode, const uint8_t* d_frames, int nfram
     const size_t need_w = (((size_t)(nb > 0 ? nb : 1) + 3) & ~(size_t)3);
     const size_t need_todo = 2 * todo_capacity(nframes, max_boxes_per_frame);      // work lists of k5_pairs and k5_gram_big
     size_t cap = need_w, fcap = (size_t)nframes + 2, mwords = need_w * 2 * RW, m_off = 0, todo_words = need_todo, todo_off = 0;
-    const bool ov = c->overlap && !c->profiling;
+    const bool ov = c->overlap && c->profiling != 1;
     if (ov) {                                                // this batch lives in slot `slot` of doubled scratch buffers
         c->slot ^= 1;
         const size_t sw = (need_w + 63) & ~(size_t)63, sf = ((size_t)nframes + 2 + 63) & ~(size_t)63;

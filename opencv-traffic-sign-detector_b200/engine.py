@@ -367,7 +367,13 @@ class Context:
         return tp, fp
 
     def set_profiling(self, on=True):
-        check(self._L.tsd_set_profiling(self._h, int(bool(on))))
+        """1 / True: per-stage times (batches serialised); 2: timeline of the overlapped batches (timeline())."""
+        check(self._L.tsd_set_profiling(self._h, int(on)))
+
+    def timeline(self, cap=4096):
+        names = (C.c_char_p * cap)(); ms = (C.c_float * cap)()
+        n = self._L.tsd_timeline(self._h, names, ms, cap)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def stage_times(self):
         names = (C.c_char_p * 32)(); ms = (C.c_float * 32)()

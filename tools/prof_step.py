@@ -16,6 +16,7 @@ ap.add_argument("--boxes", type=int, default=200)
 ap.add_argument("--H", type=int, default=800)
 ap.add_argument("--W", type=int, default=1360)
 ap.add_argument("--times", action="store_true")
+ap.add_argument("--timeline", action="store_true", help="stage boundaries of the overlapped batches (ms after the first)")
 ap.add_argument("--wall", action="store_true", help="CUDA-event time of the steps enqueued back to back (no per-stage events)")
 ap.add_argument("--real", action="store_true", help="the three stored real test frames with their real cv2.MSER boxes, tiled to --frames (bench.py's real_mser_frames)")
 ap.add_argument("--mode", default="det", choices=["det", "rec"], help="det: K1 K2 K5 K3 K4 (x1.30, 25x25); rec: K1 K2 K5 K6 K7 K8 (x1.15, 32x32)")
@@ -53,6 +54,11 @@ if a.times:
         one()
     ctx.synchronize()
     ctx.set_profiling(True)
+if a.timeline:
+    for _ in range(4):
+        one()
+    ctx.synchronize()
+    ctx.set_profiling(2)
 if a.wall:
     for _ in range(3):
         one()
@@ -70,5 +76,15 @@ if a.wall:
     print("ms_per_step %.4f" % (e0.elapsed_time(e1) / a.steps))
 if a.times:
     print({k: round(v / a.steps, 4) for k, v in ctx.stage_times()})
+if a.timeline:
+    tl = ctx.timeline()
+    b = -1
+    for name, t in tl:
+        if name == "start":
+            b += 1
+            print("\nbatch %d (slot %d): start %.3f" % (b, b & 1, t), end="")
+        else:
+            print("  %s %.3f" % (name.replace("k5_", "").replace("_crop_resize", "").replace("_expand_filter", ""), t), end="")
+    print()
 det, counts = ctx.fetch_detections(int(off[-1]))
 print("counts", counts.tolist(), "ndet", len(det))
