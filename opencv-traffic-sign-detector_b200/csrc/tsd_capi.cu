@@ -72,7 +72,9 @@ struct tsd_ctx {
     int zero_copy = 1;                       // page-locked host frames are read in place over PCIe (TSD_ZEROCOPY=0: always copy whole frames)
     int stage_rois = 1;                      // ... by the mark + copy kernels, each touched 32-byte sector once, into a device mirror K2 reads
                                              // (TSD_STAGE=0: K2 itself gathers from host memory, round 1's path)
-    DevBuf b_mirror, b_stagemap;
+    DevBuf b_mirror[2], b_stagemap[2];       // per scratch slot (consecutive batches of a chunked tsd_detect_frames call overlap)
+    int stage_chunk = 256;                   // TSD_STAGE_CHUNK: frames per chunk of tsd_detect_frames on page-locked host frames (0 = one batch)
+    int stage_ctas = 2;                      // TSD_STAGE_CTAS: CTAs per SM of the staging copy (PCIe-bound: 2 keep the link as busy as 8 and leave the SMs to the other chunk's chain)
     int stage_gran = 1;                      // TSD_STAGE_GRAN = 32 | 64 | 128 bytes: unit the marked spans are widened to (sectors: 1, 2, 4)
     unsigned long long* d_staged = nullptr;  // bytes the staging copy moved over PCIe (tsd_stat_staged_bytes)
     int chunk_frames = 32;                   // TSD_CHUNK_FRAMES: frames per H2D chunk of the host-buffer path
@@ -217,6 +219,8 @@ static int create_impl(tsd_ctx* c, int device) {
     { const char* e = getenv("TSD_STAGE"); if (e) c->stage_rois = e[0] != '0'; }
     { const char* e = getenv("TSD_STAGE_GRAN"); if (e) { const int g = atoi(e); c->stage_gran = g >= 128 ? 4 : g >= 64 ? 2 : 1; } }
     { const char* e = getenv("TSD_CHUNK_FRAMES"); if (e && atoi(e) > 0) c->chunk_frames = atoi(e); }
+    { const char* e = getenv("TSD_STAGE_CHUNK"); if (e) c->stage_chunk = atoi(e); }
+    { const char* e = getenv("TSD_STAGE_CTAS"); if (e && atoi(e) > 0) c->stage_ctas = atoi(e); }
     { const char* e = getenv("TSD_KEEP_MASKS"); if (e) c->keep_masks = atoi(e); }
     { const char* e = getenv("TSD_GRAM"); if (e) c->use_gram = atoi(e) != 0; }
     { const char* e = getenv("TSD_GRAPH"); if (e) c->use_graph = atoi(e) != 0; }
@@ -330,7 +334,7 @@ int tsd_destroy(tsd_ctx* c) {
     DevBuf* bufs[] = {&c->b_coords, &c->b_winframe, &c->b_windows, &c->b_entries, &c->b_meta, &c->b_list, &c->b_flags, &c->b_cnt,
                       &c->b_winoff, &c->b_survcnt, &c->b_survoff, &c->b_slots, &c->b_pairs, &c->b_energy, &c->b_red, &c->b_blue, &c->b_bits, &c->b_id, &c->b_hund,
                       &c->b_emit, &c->b_detcnt, &c->b_detoff, &c->b_det, &c->b_gray, &c->b_hog, &c->b_labels, &c->b_scores,
-                      &c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_mirror, &c->b_stagemap, &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
+                      &c->b_stage[0], &c->b_stage[1], &c->b_hboxes, &c->b_hoff, &c->b_summary, &c->b_order, &c->b_gramdone, &c->b_mirror[0], &c->b_mirror[1], &c->b_stagemap[0], &c->b_stagemap[1], &c->b_pgray, &c->b_pluts, &c->b_pin, &c->b_pout};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; i++) {
         if (c->ev_slot_fork[i]) cudaEventDestroy(c->ev_slot_fork[i]);
@@ -1329,16 +1333,19 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     if (host_src) {                                          // every 32-byte sector the ROIs touch crosses PCIe once, into the mirror
         const int wpr = (cdiv((int64_t)W * 3, 32) + 31) / 32;
         const int64_t nwords = (int64_t)cf * H * wpr;
-        CU(cudaMemsetAsync(c->b_stagemap.p, 0, (size_t)nwords * 4, c->cur));
+        uint32_t* stagemap = (uint32_t*)c->b_stagemap[B.sidx].p;
+        CU(cudaMemsetAsync(stagemap, 0, (size_t)nwords * 4, c->cur));
         if (nb > 0) {
-            stage_mark_kernel<<<cdiv((int64_t)nb * 32, 128), 128, 0, c->cur>>>((const int4*)coords, winframe, d_nwin, nb, H, W, D, wpr, c->stage_gran, (uint32_t*)c->b_stagemap.p);
+            stage_mark_kernel<<<cdiv((int64_t)nb * 32, 128), 128, 0, c->cur>>>((const int4*)coords, winframe, d_nwin, nb, H, W, D, wpr, c->stage_gran, stagemap);
             TRY(check_launch(c, "stage_mark"));
             int g = cdiv(nwords, 256);
-            if (g > c->sm_count * 8) g = c->sm_count * 8;
-            stage_copy_kernel<<<g, 256, 0, c->cur>>>(host_src, row_stride, frame_stride, H, W * 3, wpr, nwords, (const uint32_t*)c->b_stagemap.p,
+            if (g > c->sm_count * c->stage_ctas) g = c->sm_count * c->stage_ctas;
+            stage_copy_kernel<<<g, 256, 0, c->cur>>>(host_src, row_stride, frame_stride, H, W * 3, wpr, nwords, stagemap,
                                                      (uint8_t*)d_frames, c->d_staged);
             TRY(check_launch(c, "stage_copy"));
         }
+        // PCIe is the serial resource of a host-staged batch: the next batch's staging may start as soon as this one's has ended
+        if (stagger) TRY(ev_record(c, c->ev_w1[B.sidx]));
         mark(c, "stage_h2d");
     }
     // K2 (DET:123-124)
@@ -1348,7 +1355,7 @@ static int enqueue_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, i
     TRY(dev_hist(c, windows, d_nwin, nb, npx, ws, entries, meta, energy, (int64_t)cap));
     mark(c, "k5_hist");
     TRY(dev_fold(c, windows, ws, coords, entries, meta, winoff, cf, npx, 1, 1, c->cfg.hist_tol, c->cfg.coord_tol,
-                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap, survoff, stagger ? c->ev_w1[B.sidx] : nullptr));
+                 list, flags, survcnt, maxb, M, todo, energy, (int64_t)cap, survoff, (stagger && !host_src) ? c->ev_w1[B.sidx] : nullptr));
     k5_gather_kernel<<<cf, 32, 0, c->cur>>>(windows, (int4*)coords, winoff, list, survoff, cf, nbytes, ws, nullptr, nullptr, slots);
     TRY(check_launch(c, "k5_gather"));
     mark(c, "k5_fold");
@@ -1417,7 +1424,7 @@ static int run_chain(tsd_ctx* c, int mode, const uint8_t* d_frames, int H, int W
     const std::vector<uint64_t> key = {(uint64_t)mode, (uint64_t)(uintptr_t)d_frames, (uint64_t)B.nframes, (uint64_t)H, (uint64_t)W, (uint64_t)row_stride,
                                        (uint64_t)frame_stride, (uint64_t)(uintptr_t)d_boxes, (uint64_t)(uintptr_t)d_box_offsets, (uint64_t)B.nbcap, (uint64_t)maxb,
                                        (uint64_t)B.wo, (uint64_t)B.fo, (uint64_t)B.sidx, (uint64_t)(uintptr_t)M, (uint64_t)(uintptr_t)todo,
-                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->fold_per_sm_cap, (uint64_t)c->stagger, (uint64_t)c->stage_gran, (uint64_t)c->k2_tma};
+                                       (uint64_t)c->ticket_base, c->gen, (uint64_t)c->keep_masks, (uint64_t)c->use_gram, (uint64_t)(uintptr_t)host_src, (uint64_t)c->fold_cta_cost, (uint64_t)c->fold_per_sm_cap, (uint64_t)c->stagger, (uint64_t)c->stage_ctas, (uint64_t)c->stage_gran, (uint64_t)c->k2_tma};
     c->graph_clock++;
     for (auto& g : c->graphs)
         if (g.key == key) {
@@ -1543,9 +1550,10 @@ static int enqueue_impl(tsd_ctx* c, int mode, const uint8_t* d_frames, int nfram
     TRY(ensure(c, c->b_pairs, mwords * sizeof(uint32_t)));
     if (host_src) {
         const int wpr = (cdiv((int64_t)W * 3, 32) + 31) / 32;
-        TRY(ensure(c, c->b_mirror, (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3 + 64));
-        TRY(ensure(c, c->b_stagemap, (size_t)nframes * H * wpr * 4));
-        d_frames = (const uint8_t*)c->b_mirror.p;
+        const int ms_slot = ov ? c->slot : 0;                // (a grow frees + reallocates: cudaFree waits for the device)
+        TRY(ensure(c, c->b_mirror[ms_slot], (size_t)frame_stride * (nframes - 1) + (size_t)row_stride * (H - 1) + (size_t)W * 3 + 64));
+        TRY(ensure(c, c->b_stagemap[ms_slot], (size_t)nframes * H * wpr * 4));
+        d_frames = (const uint8_t*)c->b_mirror[ms_slot].p;
     }
     uint32_t* M = (uint32_t*)c->b_pairs.p + m_off;
     int32_t* todo = (int32_t*)c->b_gramdone.p + todo_off;
@@ -1722,6 +1730,35 @@ int tsd_detect_frames(tsd_ctx* c, int mode, const uint8_t* frames, int nframes, 
         if (cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
             const uint8_t* hp = (const uint8_t*)at.devicePointer;
             const bool stage = c->stage_rois && ((uintptr_t)hp % 16 == 0) && row_stride % 16 == 0 && frame_stride % 16 == 0 && ((int64_t)W * 3) % 16 == 0;
+            const int SC = c->stage_chunk;
+            if (stage && c->overlap && c->profiling != 1 && SC > 0 && nframes >= 2 * SC) {
+                // Chunks of SC frames through the two scratch slots: the staging copy of chunk k+1 (PCIe-bound, a few resident warps)
+                // runs beside the chain of chunk k; the records of chunk k are read once chunk k+1 is enqueued.
+                int rc_chunks = TSD_OK, f_prev = -1;
+                const int nchunks = nframes / SC < 4 ? nframes / SC : 4;     // (at most 4: every chunk shape is one cached CUDA graph)
+                const int CFc = (nframes + nchunks - 1) / nchunks;
+                for (int f0 = 0; f0 < nframes; f0 += CFc) {
+                    const int cf = nframes - f0 < CFc ? nframes - f0 : CFc;
+                    TRY(run_chunk(nullptr, f0, cf, hp + (size_t)f0 * frame_stride));
+                    if (f_prev >= 0) {
+                        int32_t nd = 0, cnt[4];
+                        const int room = det_cap - nd_total;
+                        const int rc = tsd_fetch_previous(c, det ? det + nd_total : nullptr, room > 0 ? room : 0, &nd, cnt);
+                        if (rc != TSD_OK && rc != TSD_E_NOMEM) return rc;
+                        if (rc == TSD_E_NOMEM) rc_chunks = rc;
+                        else for (int i = 0; i < nd; i++) det[nd_total + i].frame += f_prev;
+                        nd_total += nd;
+                        for (int i = 0; i < 4; i++) tot[i] += cnt[i];
+                    }
+                    f_prev = f0;
+                }
+                const int rc = fetch_chunk(f_prev);
+                *ndet = nd_total;
+                if (counts) for (int i = 0; i < 4; i++) counts[i] = tot[i];
+                if (rc != TSD_OK) return rc;
+                if (rc_chunks != TSD_OK) return fail(TSD_E_NOMEM, "det_cap %d < %d detections", det_cap, nd_total);
+                return TSD_OK;
+            }
             TRY(stage ? run_chunk(nullptr, 0, nframes, hp) : run_chunk(hp, 0, nframes));
             const int rc = fetch_chunk(0);
             *ndet = nd_total;
