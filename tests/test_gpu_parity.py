@@ -463,6 +463,18 @@ def test_host_paths_agree(tsd, templates, oracle, monkeypatch):
             ctx.unpin(pinned)
     # page-locked frames: only the sectors the ROIs touch cross the bus -- far fewer bytes than the frames, at least the ROIs' own
     assert 0 < staged < pinned.nbytes // 3
+    # the same frames in CHUNKS through the two scratch slots (staging of chunk k+1 beside the chain of chunk k, records of chunk k
+    # read after chunk k+1 is enqueued; TSD_STAGE_CHUNK=3 -> 3 chunks of 4, 4 and 2 frames), called twice (graph replay)
+    monkeypatch.setenv("TSD_STAGE_CHUNK", "3")
+    with tsd.Context(0, "det") as ctx:
+        ctx.set_templates(red6, blue6)
+        ctx.pin(pinned)
+        try:
+            for _ in range(3):
+                d_chunked, c_chunked = ctx.detect_frames(pinned, boxes, off)
+                assert _records(d_chunked) == exp and c_chunked.tolist() == c_pinned.tolist()
+        finally:
+            ctx.unpin(pinned)
     monkeypatch.setenv("TSD_STAGE", "0")                                  # round 1's path: K2 itself gathers from host memory
     with tsd.Context(0, "det") as ctx:
         ctx.set_templates(red6, blue6)
