@@ -575,6 +575,12 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": traffic.get(dom, {}).get("dram_bytes_per_window", 0) * npass or None,
                          "traffic_source": traffic.get(dom, {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom, 0),
                          "kernel_ms_per_launch": per_stage.get(dom)},
+            # the same figure for every stage (the fold is latency-bound and mostly hidden under the next batch's kernels; K2 is the
+            # heaviest mover of bytes and the kernel the round-1 review named)
+            "roofline_stages": {k: {"achieved": alg.get(k, 0) / (v * 1e-3) / 1e9, "frac": alg.get(k, 0) / (v * 1e-3) / 1e9 / peak, "ms": v,
+                                    "algorithmic_bytes_per_launch": alg.get(k, 0),
+                                    "traffic": traffic.get(k, {}).get("dram_bytes_per_window", 0) * npass or None}
+                                for k, v in per_stage.items() if v > 0},
             "stages_ms_per_step": per_stage, "ms_per_step_serialised": ms_serial / args.steps,
             "stages_alg_gbs": {k: alg.get(k, 0) / (v * 1e-3) / 1e9 for k, v in per_stage.items() if v > 0},
             "chain": {"algorithmic_bytes_per_step": fused_bytes, "gbs": fused_bytes / (ms / args.steps * 1e-3) / 1e9,

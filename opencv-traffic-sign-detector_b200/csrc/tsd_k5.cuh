@@ -1437,7 +1437,7 @@ __device__ __forceinline__ bool fold_goes_to_cta(int n, int cost, int n_skip, in
 
 // n_skip / cost_min: see fold_goes_to_cta (k5_fold_cta is launched beside this kernel on the same order list).
 template <int RMAX, int CAP>
-__global__ void __launch_bounds__(kFoldWarps * 32) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
+__global__ void __launch_bounds__(kFoldWarps * 32, TSD_FOLD_MINB) k5_fold_warp_kernel(FoldParams P, int nframes, uint32_t* M, int RW, int sim_cut,
                                                                        const int32_t* __restrict__ order, int32_t* counter, int n_skip,
                                                                        const int32_t* __restrict__ frame_cost_sorted, int cost_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

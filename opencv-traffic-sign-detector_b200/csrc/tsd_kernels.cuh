@@ -25,6 +25,9 @@
 #ifndef TSD_FOLD_WARPS
 #define TSD_FOLD_WARPS 4         // warps (= frames in flight) per CTA of the warp-per-frame fold
 #endif
+#ifndef TSD_FOLD_MINB
+#define TSD_FOLD_MINB 1          // min resident CTAs per SM of the warp-per-frame fold (register budget: 1 -> as many as it likes, 128)
+#endif
 #ifndef TSD_HIST_UNROLL
 #define TSD_HIST_UNROLL 8        // pixels per lane in flight in the two histogram passes (measured: 2: .266, 4: .274, 5: .283, 7-8: .259, 10: .310, 20: .369 ms)
 #endif

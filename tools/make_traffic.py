@@ -1,6 +1,6 @@
 """profiles/traffic.json from an .ncu-rep (`ncu --set full`): per stage, DRAM bytes (read + write) per aspect-passing window.
 
-    python tools/make_traffic.py gpurun_out/<rep>.ncu-rep <aspect_passing_windows_of_that_run> <label>
+    python tools/make_traffic.py gpurun_out/<rep>.ncu-rep <aspect_passing_windows_of_that_run> <label> [output.json]
 """
 import csv
 import json
@@ -30,6 +30,6 @@ final = {}
 for st, ks in res.items():
     per_step = sum(b / n for b, n in ks.values())
     final[st] = {"dram_bytes_per_window": per_step / nwin, "kernel": " + ".join(ks), "source": "%s (%d aspect-passing windows)" % (label, nwin)}
-p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+p = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 json.dump(final, open(p, "w"), indent=1)
 print(json.dumps(final, indent=1))

@@ -13,5 +13,6 @@ for k in $lines; do
   python tools/ncu_lines.py gpurun_out/$name.$k.source.csv 45 > gpurun_out/$name.$k.lines.txt 2>&1
   rm -f gpurun_out/$name.$k.source.csv
 done
+[ -n "$TRAFFIC_WINDOWS" ] && python tools/make_traffic.py gpurun_out/$name.ncu-rep "$TRAFFIC_WINDOWS" "ncu --set full, $*, profiles/${TRAFFIC_LABEL:-$name}" gpurun_out/$name.traffic.json > /dev/null 2>&1
 [ "$KEEP_REP" = "1" ] || rm -f gpurun_out/$name.ncu-rep
 tail -3 gpurun_out/$name.ncu.log
