@@ -43,6 +43,13 @@ def test_k2_resize_sweep(ctx_det, ctx_rec, oracle):
         got = ctx.crop_resize(frame, coords, wf, D)
         for i, (c, f) in enumerate(zip(coords, wf)):
             assert np.array_equal(got[i], oracle.crop_resize(frame[f], c, D)), (D, c)
+        # a frame whose rows are not 4-byte aligned (637 px = 1911 bytes): the aligned 32-bit tap loads of the general path do
+        # not apply, every window takes the byte loads
+        odd = np.ascontiguousarray(frame[:, :, :637])
+        keep = np.flatnonzero(coords[:, 0] < 630)[::5]                       # (crops that start inside the narrower frame)
+        got_odd = ctx.crop_resize(odd, coords[keep], wf[keep], D)
+        for i, (c, f) in enumerate(zip(coords[keep], wf[keep])):
+            assert np.array_equal(got_odd[i], oracle.crop_resize(odd[f], c, D)), (D, c, "odd width")
         gray = np.ascontiguousarray(frame[..., 1])
         got1 = ctx.crop_resize(gray, coords[::3], wf[::3], D)
         for i, (c, f) in enumerate(zip(coords[::3], wf[::3])):
