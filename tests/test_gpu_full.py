@@ -281,3 +281,47 @@ def test_k2_tma_variant_bit_identical(tsd, oracle, templates, det_full150, jpeg2
             ctx.set_lda(r["lda_W"], r["lda_b"])
             res.append(ctx.detect_frames(frames, boxes, off, mode=tsd.RUN_RECOGNIZE))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_timeline_and_stagger_switch(tsd, oracle, templates, monkeypatch):
+    """tsd_set_profiling(ctx, 2) + tsd_timeline: the batches keep overlapping (two slots), every stage boundary comes back in
+    enqueue order with non-decreasing times inside a batch; and the records of back-to-back batches do not depend on whether the
+    front halves of consecutive batches are staggered (TSD_STAGGER) or how many fold CTAs may share an SM (TSD_FOLD_PER_SM)."""
+    import torch
+    red6, blue6 = templates
+    dev = torch.device("cuda", 0)
+    F, N = 24, 200
+    frames = tsd.synth.make_frames(8, seed=tsd.synth.FRAME_SEED + 90)
+    boxes, off = tsd.synth.make_boxes(F, N, seed=tsd.synth.BOX_SEED + 90)
+    exp = []
+    for f in range(F):
+        o = oracle.detect_frame(frames[f % 8], boxes[off[f]:off[f + 1]], red6, blue6)
+        exp += [(f,) + tuple(int(v) for v in c) + (int(i), int(h)) for c, i, h in zip(o["coords"], o["ids"], o["hundredths"])]
+    d_frames = torch.from_numpy(frames).to(dev)[torch.arange(F, device=dev) % 8].contiguous()
+    d_boxes, d_off = torch.from_numpy(boxes).to(dev), torch.from_numpy(off).to(dev)
+    rec = lambda det: [(int(d["frame"]), int(d["x1"]), int(d["y1"]), int(d["x2"]), int(d["y2"]), int(d["id"]), int(d["hundredths"])) for d in det]
+    for stagger, cap in (("1", "2"), ("0", "0"), ("1", "1")):
+        monkeypatch.setenv("TSD_STAGGER", stagger)
+        monkeypatch.setenv("TSD_FOLD_PER_SM", cap)
+        with tsd.Context(0, "det") as ctx:
+            ctx.set_templates(red6, blue6)
+            one = lambda: ctx.enqueue_frames(d_frames.data_ptr(), F, 800, 1360, d_boxes.data_ptr(), d_off.data_ptr(), int(off[-1]), max_boxes_per_frame=N)
+            for _ in range(4):                               # eager, captured, replayed, replayed (CUDA graph with external event nodes)
+                one()
+            prev, _ = ctx.fetch_detections(int(off[-1]), previous=True)
+            last, _ = ctx.fetch_detections(int(off[-1]))
+            assert rec(prev) == exp and rec(last) == exp, (stagger, cap)
+            ctx.set_profiling(2)
+            for _ in range(3):
+                one()
+            tl = ctx.timeline()
+            ctx.set_profiling(False)
+            det, _ = ctx.fetch_detections(int(off[-1]))
+            assert rec(det) == exp
+            starts = [i for i, (name, _) in enumerate(tl) if name == "start"]
+            assert len(starts) == 3 and tl[0][1] == 0.0
+            for a, b in zip(starts, starts[1:] + [len(tl)]):
+                names = [n for n, _ in tl[a:b]]
+                times = [t for _, t in tl[a:b]]
+                assert names[:4] == ["start", "k1_expand_filter", "k2_crop_resize", "k5_hist"] and names[-1] == "detections"
+                assert all(t1 >= t0 for t0, t1 in zip(times, times[1:]))
