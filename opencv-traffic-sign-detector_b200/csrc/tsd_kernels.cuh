@@ -293,9 +293,10 @@ __global__ void __launch_bounds__(128) k2_crop_resize_kernel(
 // K2 v2: same arithmetic, restructured for instruction count (v1 was issue-bound at ~100 instructions per output
 // byte-iteration).  One warp per window, lane = destination column; the x coefficients live in registers, the y
 // coefficients are computed by lane dy and broadcast through shared memory; each lane walks the D destination rows and reads its
-// 2 x 2 taps x C channels straight from the frame (L1-coalesced across the warp: one row segment per load).
-// (Variants that lost on B200 -- crop staged in shared memory with cp.async, row reuse + staged output, aligned 32-bit tap loads,
-// one CTA per frame -- are documented with their measurements in DESIGN.md section 8 and live in the git history of round 1.)
+// 2 x 2 taps x C channels straight from the frame through L1 (one row segment per load): as aligned 32-bit words + IDP.2A for
+// BGR frames with 4-byte aligned rows (k2_rows_wide), as byte loads otherwise (k2_rows).  Persistent warps stride over the windows.
+// (Variants that lost on B200 -- crop staged in shared memory with cp.async or by TMA, row reuse + staged output, one CTA per
+// frame, L2 prefetch of the ROI -- are documented with their measurements in DESIGN.md section 8.)
 // Which windows the TMA-staged resize kernel takes (tsd_k2_tma.cuh): crops whose byte span, widened to whole 16-byte units in front
 // and 64-byte units in total, and whose rows, in boxes of 8, fit the per-warp staging buffer.  cx = clipped x1, cw / ch = clipped size.
 constexpr int kTmaStageBytes = 10240;
