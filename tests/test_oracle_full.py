@@ -127,3 +127,39 @@ def test_gray_descriptor_classifiers_oracle(oracle, rec_golden, rec_gray_golden)
     assert np.max(np.abs(lg - g["logits"]) / np.maximum(1.0, np.abs(g["logits"]))) < 1e-9 and np.array_equal(lab, g["pred_lda"])
     Z, lk = oracle.knn_predict(X[:300], g["knn_xbar"], g["knn_scalings"], g["knn_Ztrain"], g["knn_ytrain"])
     assert np.max(np.abs(Z - g["knn_Zq"][:300]) / np.maximum(1.0, np.abs(g["knn_Zq"][:300]))) < 1e-9 and np.array_equal(lk, g["pred_knn"][:300])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_install_rebinds_the_reference_modules_call_compatibly():
+    """The drop-in boundary on the live reference modules (no GPU needed: nothing is called): every name source_det / source_rec
+    patch exists in the reference's own `source` module with the same positional parameters, is really looked up through the module's
+    globals by the reference's code (so rebinding it reroutes the reference's own drivers and helpers), and install() rebinds
+    exactly those names and nothing else."""
+    import inspect
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import refload
+    import tsd_b200
+    for load, mirror in ((refload.load_det, tsd_b200.source_det), (refload.load_rec, tsd_b200.source_rec)):
+        ref, _ = load()
+        before = dict(vars(ref))
+        used = set()
+        for obj in before.values():
+            if inspect.isfunction(obj) and obj.__module__ == ref.__name__:
+                used |= set(obj.__code__.co_names)
+        for name in mirror._PATCHED:
+            assert name in before and inspect.isfunction(before[name]), name
+            ours = getattr(mirror, name)
+            p_ref = list(inspect.signature(before[name]).parameters.values())
+            p_our = list(inspect.signature(ours).parameters.values())
+            required = [p for p in p_our if p.default is inspect.Parameter.empty]
+            # callable exactly the way the reference calls its own function (positionally, with its number of arguments)
+            assert len(required) <= len(p_ref) <= len(p_our), (name, [p.name for p in p_ref], [p.name for p in p_our])
+            assert name in used, name + " is not called through the module's globals"
+        mirror.install(ref)
+        after = vars(ref)
+        for name in mirror._PATCHED:
+            assert after[name] is getattr(mirror, name)
+        changed = {k for k in after if k in before and after[k] is not before[k]}
+        assert changed == set(mirror._PATCHED)
+        for name, obj in before.items():                                          # (restore: the loader caches the modules)
+            setattr(ref, name, obj)
