@@ -16,6 +16,7 @@ SIGNALLIST = ['prohibicion', 'peligro', 'stop', 'direccionProhibida', 'cedaPaso'
 
 _ctx = None
 _templates_key = None
+_installed_into = None            # the reference module install() patched last
 
 
 def context():
@@ -89,8 +90,12 @@ def calculateMeanMasks(train_path=None):
     resize, running average and masks on the GPU."""
     import cv2
     if train_path is None:
-        import constants                                       # the reference's module (DET/constants.py), when patched in
-        train_path = constants.TRAIN_PATH
+        # the reference reads its module global constants.TRAIN_PATH (set by test(), DET:612): the `constants` the patched
+        # module itself imported, or -- called without install() from the reference's directory -- the importable one
+        consts = getattr(_installed_into, "constants", None)
+        if consts is None:
+            import constants as consts
+        train_path = consts.TRAIN_PATH
     crops = []
     for dirs in SIGN_GROUPS:
         t = []
@@ -265,6 +270,8 @@ _PATCHED = ("calculateMeanMasks", "grayAndEnhanceContrast", "makeWindowBiggerOrD
 
 def install(reference_source_module):
     """Monkey-patch the reference's DET `source` module so its own `test()` driver runs the GPU path."""
+    global _installed_into
+    _installed_into = reference_source_module
     for name in _PATCHED:
         setattr(reference_source_module, name, globals()[name])
     return reference_source_module

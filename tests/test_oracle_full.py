@@ -163,3 +163,38 @@ def test_install_rebinds_the_reference_modules_call_compatibly():
         assert changed == set(mirror._PATCHED)
         for name, obj in before.items():                                          # (restore: the loader caches the modules)
             setattr(ref, name, obj)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_reference_driver_through_install(tmp_path, monkeypatch, resultado150):
+    """The reference's OWN driver `test()` (DET/source.py:611-853) run through source_det.install(), on the 150 test frames, in the
+    container where the reference tree exists -- which has no GPU, so the engine behind the mirrors is a test double answered by
+    the CPU oracle (tests/oracle_context.py).  What this pins is everything between the driver and the engine: the patched
+    names, their argument / return conventions as the driver uses them (Python-int tuples, float scores, [(mask, name)] lists,
+    (detections, counts, images) triples), the directory walks.  resultado.txt must equal the reference's own, line for line."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    sys.path.insert(0, os.path.dirname(__file__))
+    import refload
+    import tsd_b200
+    from oracle_context import OracleContext
+    src, _ = refload.load_det()
+    before = dict(vars(src))
+    fake = OracleContext()
+    monkeypatch.setattr(tsd_b200.source_det, "_ctx", fake)
+    monkeypatch.setattr(tsd_b200.source_det, "_templates_key", None)
+    for d in ("train_jpg", "test_alumnos_jpg"):
+        os.symlink(os.path.join(refload.DET_DIR, d), tmp_path / d)
+    monkeypatch.chdir(tmp_path)
+    try:
+        tsd_b200.source_det.install(src)
+        src.tqdm = lambda it=None, *a, **k: it
+        src.sleep = lambda *_: None
+        src.test("train_jpg", "test_alumnos_jpg", (7, 200, 2000, 0.15))
+    finally:
+        for name, obj in before.items():
+            setattr(src, name, obj)
+    got = (tmp_path / "resultado.txt").read_text().splitlines()
+    assert sorted(got) == sorted(resultado150) and len(got) == 192
+    # the driver really went through the mirrors
+    assert fake.calls["windows"] == 150 and fake.calls["dedup"] >= 150 and fake.calls["score_masks"] >= 192 and fake.calls["mean_windows"] == 1
+    assert len(os.listdir(tmp_path / "resultado_imgs")) == 150
