@@ -776,7 +776,8 @@ static int dev_fold(tsd_ctx* c, uint8_t* windows, int ws, int32_t* coords, uint3
     TRY(npx <= 640 ? launch_folds<640>(c, 0, P, nframes, M, RW, cut, cost, max_n) : launch_folds<1024>(c, 1, P, nframes, M, RW, cut, cost, max_n));
     // Frames the warp fold flagged (more windows than its variant or the caller's max_boxes_per_frame bound allows) are redone by the
     // general fold.  Always launched: it costs ~10 us when nothing is flagged and makes a too-small caller bound harmless.
-    k5_fold_kernel<<<nframes, kFoldThreads, 0, c->cur>>>(P, nframes, 1, surv_offsets, c->d_tickets + c->ticket_base + 1);
+    // (its CTAs stride over the frames: a few per SM check the flags of a large batch in ~5 us instead of one CTA per frame in ~20)
+    k5_fold_kernel<<<std::min(nframes, 4 * c->sm_count), kFoldThreads, 0, c->cur>>>(P, nframes, 1, surv_offsets, c->d_tickets + c->ticket_base + 1);
     return check_launch(c, "k5_fold");
 }
 
