@@ -11,7 +11,7 @@ its own batch (weak scaling), no collective on the hot path, one small gather of
 
 Prints ONE JSON line (rank 0).  `value` = raw candidate windows/s, inputs resident in HBM; `e2e` = the same metric
 through the public host-buffer API (pinned host frames, H2D + D2H inside the timed region); `roofline` = the dominant
-kernel against the measured HBM peak; `cpu_baseline` = the reference pipeline (oracle/ref_port.py: cv2 + the
+kernel (largest stage time) against the measured HBM peak, `roofline_stages` = the same figure for every stage; `cpu_baseline` = the reference pipeline (oracle/ref_port.py: cv2 + the
 reference's Python loops) on the host cores over a bounded sample.
 """
 import argparse
