@@ -580,8 +580,9 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
                            const int32_t* win_frame, const int32_t* n_ptr, int n_max, int D, uint8_t* windows, int out_stride, int nframes = 0) {
     if (n_max == 0) return TSD_OK;
     if (rs * (int64_t)H >= ((int64_t)1 << 31)) return fail(TSD_E_INVALID, "a frame must span less than 2 GiB (row offsets are 32-bit)");
-    int g4 = cdiv(n_max, 4);
-    if (c->k2_grid > 0 && g4 > c->k2_grid * c->sm_count) g4 = c->k2_grid * c->sm_count;     // persistent warps (the kernels stride over the windows)
+    const int g4_all = cdiv(n_max, 4);                       // one window per warp (the generic kernel does not loop)
+    int g4 = g4_all;
+    if (c->k2_grid > 0 && g4 > c->k2_grid * c->sm_count) g4 = c->k2_grid * c->sm_count;     // persistent warps (the v2 / TMA kernels stride over the windows)
     int skip_tma = 0;
 #define K2_ARGS frames, H, W, rs, fs, (const int4*)coords, win_frame, n_ptr, n_max
     // TSD_K2=tma: ROI staged by the Tensor Memory Accelerator (internal 16-byte window layout, BGR, D = 25 / 32, TMA-legal frame layout)
@@ -609,8 +610,8 @@ static int dev_crop_resize(tsd_ctx* c, const uint8_t* frames, int H, int W, int6
     else if (ch == 3 && D == 32) k2_crop_resize_v2_kernel<3, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, skip_tma, wide_last);
     else if (ch == 1 && D == 25) k2_crop_resize_v2_kernel<1, 25><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0, -2);
     else if (ch == 1 && D == 32) k2_crop_resize_v2_kernel<1, 32><<<g4, 128, 0, c->cur>>>(K2_ARGS, windows, out_stride, 0, -2);
-    else if (ch == 3) k2_crop_resize_kernel<3><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
-    else k2_crop_resize_kernel<1><<<g4, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
+    else if (ch == 3) k2_crop_resize_kernel<3><<<g4_all, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);      // other window sizes: generic kernel
+    else k2_crop_resize_kernel<1><<<g4_all, 128, 0, c->cur>>>(K2_ARGS, D, windows, out_stride);
 #undef K2_ARGS
     return check_launch(c, "k2_crop_resize");
 }
