@@ -624,3 +624,19 @@ def test_lda_tensor_core_evaluation(ctx_rec, rec_golden):
     z1, lab1, _ = ctx_rec.lda_predict_tf32(X, split=1)
     assert np.array_equal(lab3, lab64) and np.abs(z3 - z64).max() < 1e-3
     assert np.abs(z1 - z64).max() < 0.5 and np.abs(z1 - z64).max() > 1e-3
+
+
+def test_k2_more_windows_than_persistent_warps(ctx_det, oracle):
+    """More windows than the persistent K2 grid has warps (256 CTAs x 4 warps per SM): the 25x25 kernel strides over them; a window
+    size without a specialised kernel (16x16) takes the generic kernel, which keeps one window per warp.  Sampled against the oracle
+    (incl. the first and last windows)."""
+    rng = np.random.default_rng(77)
+    frame = rng.integers(0, 256, (1, 96, 128, 3), dtype=np.uint8)
+    n = 160000
+    x0 = rng.integers(0, 100, n); y0 = rng.integers(0, 70, n)
+    coords = np.stack([x0, y0, x0 + rng.integers(3, 28, n), y0 + rng.integers(3, 26, n)], 1).astype(np.int32)
+    pick = np.unique(np.concatenate([[0, 1, n - 2, n - 1], rng.integers(0, n, 300), np.arange(151500, 151600)]))
+    for D in (25, 16):
+        got = ctx_det.crop_resize(frame, coords, np.zeros(n, np.int32), D)
+        for i in pick:
+            assert np.array_equal(got[i], oracle.crop_resize(frame[0], coords[i], D)), (D, i)
