@@ -81,11 +81,16 @@ TSD_API int tsd_synchronize(tsd_ctx *ctx);
 /* Consecutive tsd_enqueue_frames calls alternate between two scratch slots and two internal streams, so the latency-bound fold
  * of one batch runs under the throughput-bound kernels of the next (TSD_OVERLAP=0 in the environment turns this off).  The
  * context's stream therefore waits for a batch only when the NEXT batch is enqueued, or when tsd_flush / tsd_synchronize /
- * tsd_fetch_detections is called: tsd_flush makes tsd_stream() wait for everything enqueued so far without blocking the host. */
+ * tsd_fetch_detections is called: tsd_flush makes tsd_stream() wait for everything enqueued so far without blocking the host.
+ * The front half of a batch (K1, K2, histograms, pair classes) starts only when the previous batch's has ended, which keeps the
+ * two streams half a period apart (TSD_STAGGER=0 turns that off); the kernel sequence of a batch shape is replayed as a CUDA
+ * graph from its third sighting on (TSD_GRAPH=0: eager launches). */
 TSD_API int tsd_flush(tsd_ctx *ctx);
 /* Page-lock a caller-owned host buffer (cudaHostRegister, mapped).  tsd_detect_frames with TSD_MEM_HOST reads page-locked
  * frames IN PLACE over PCIe (only the 32-byte sectors the candidate ROIs touch are transferred, each once per batch, into a
- * device-resident mirror of the frames); pageable frames are copied whole, in chunks that overlap the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */
+ * device-resident mirror of the frames; batches of 512 frames or more run as up to four chunks whose transfers overlap the
+ * previous chunk's kernels, TSD_STAGE_CHUNK=0 turns the chunking off); pageable frames are copied whole, in chunks that overlap
+ * the kernels.  Buffers from cudaHostAlloc / torch pin_memory() are already page-locked. */
 TSD_API int tsd_host_register(void *p, int64_t bytes);
 TSD_API int tsd_host_unregister(void *p);
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
@@ -261,7 +266,8 @@ TSD_API int tsd_stat_staged_bytes(tsd_ctx *ctx, int64_t *total, int reset);
 TSD_API int tsd_set_profiling(tsd_ctx *ctx, int on);
 TSD_API int tsd_stage_times(tsd_ctx *ctx, const char **names, float *ms, int cap);
 /* tsd_set_profiling(ctx, 2) keeps consecutive tsd_enqueue_frames calls overlapped (two scratch slots, two streams) and
- * tsd_timeline returns every stage boundary recorded since then, in enqueue order, as milliseconds after the first one. */
+ * tsd_timeline returns every stage boundary recorded since then, in enqueue order, as milliseconds after the first one
+ * (names[i] stay valid until the next call on the context).  Synchronises. */
 TSD_API int tsd_timeline(tsd_ctx *ctx, const char **names, float *ms, int cap);
 
 #ifdef __cplusplus
