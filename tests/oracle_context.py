@@ -14,10 +14,9 @@ from oracle import oracle as O
 
 
 class OracleContext:
-    D = 25
-    cfg = types.SimpleNamespace(enlarge=1.30)
-
-    def __init__(self):
+    def __init__(self, flavour="det"):
+        self.D = 25 if flavour == "det" else 32
+        self.cfg = types.SimpleNamespace(enlarge=1.30 if flavour == "det" else 1.15, proba_tol=0.5)
         self.red6 = self.blue6 = None
         self.calls = {}
 
@@ -118,3 +117,31 @@ class OracleContext:
                 ids[i], hs[i] = kb + 1, sc[i, 1, kb]
             em[i] = hs[i] > 55
         return dict(scores=sc if want_scores else None, id=ids, hundredths=hs, emit=em)
+
+    # ---- recognition flavour ------------------------------------------------------------------------------------------
+    def bgr2gray(self, bgr):
+        self._count("bgr2gray")
+        return O.bgr2gray(np.asarray(bgr, np.uint8))
+
+    def hog(self, gray):
+        self._count("hog")
+        gray = np.asarray(gray, np.uint8).reshape(-1, 32, 32)
+        return np.stack([O.hog32(g) for g in gray]) if len(gray) else np.zeros((0, 324), np.float32)
+
+    def set_lda(self, W, b):
+        self._count("set_lda")
+        self.W, self.b = np.asarray(W, np.float64), np.asarray(b, np.float64)
+
+    def lda_predict(self, X, tol=None, want_logits=True):
+        self._count("lda_predict")
+        lg, lab = O.lda_predict(np.asarray(X, np.float32), self.W, self.b, self.cfg.proba_tol if tol is None else tol)
+        return (lg if want_logits else None), lab
+
+    def set_knn(self, xbar, scalings, Ztrain, ytrain, k=4):
+        self._count("set_knn")
+        self.knn = (np.asarray(xbar, np.float64), np.asarray(scalings, np.float64), np.asarray(Ztrain, np.float64), np.asarray(ytrain, np.int32), int(k))
+
+    def knn_predict(self, X, want_Z=True):
+        self._count("knn_predict")
+        Z, lab = O.knn_predict(np.asarray(X, np.float32), *self.knn)
+        return (Z if want_Z else None), lab

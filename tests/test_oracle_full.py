@@ -198,3 +198,76 @@ def test_reference_driver_through_install(tmp_path, monkeypatch, resultado150):
     # the driver really went through the mirrors
     assert fake.calls["windows"] == 150 and fake.calls["dedup"] >= 150 and fake.calls["score_masks"] >= 192 and fake.calls["mean_windows"] == 1
     assert len(os.listdir(tmp_path / "resultado_imgs")) == 150
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("classifier", ["LDABAYES", "KNN"])
+def test_reference_recognition_driver_through_install(tmp_path, monkeypatch, classifier):
+    """The reference's own `testValidation()` (REC/source.py:646-809) on a reduced training directory (8 real train frames that
+    hold at least three signs of every type + their gt.txt lines; MSER (7, 200, 2000, 1.0) as in the reference), run twice from
+    the same seeds: UNPATCHED (pure reference: cv2 + scikit-learn) and through source_rec.install() with the engine behind the
+    mirrors replaced by the oracle-backed test double (no GPU in the container that holds the reference tree).  The training-window
+    cache MSERTrain.val (grey 32x32 pixels and coordinates, in order) and the predicted / true labels of the validation split
+    must be identical: this pins the glue of every patched REC function as the driver uses it (window extraction, negatives,
+    descriptors, weights read out of the fitted sklearn objects, the LDA-Bayes and KNN decisions)."""
+    import pickle
+    import random
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    sys.path.insert(0, os.path.dirname(__file__))
+    import refload
+    import tsd_b200
+    from oracle_context import OracleContext
+    src, _ = refload.load_rec()
+    files = ["00073.jpg", "00177.jpg", "00307.jpg", "00097.jpg", "00200.jpg", "00004.jpg", "00010.jpg", "00020.jpg"]
+    train = tmp_path / "train_small"
+    train.mkdir()
+    for f in files:
+        os.symlink(os.path.join(refload.REC_DIR, "train_jpg", f), train / f)
+    stems = {f.split(".")[0] for f in files}
+    with open(train / "gt.txt", "w") as out:
+        for line in open(os.path.join(refload.REC_DIR, "train_jpg", "gt.txt")):
+            if line.split(".")[0] in stems:
+                out.write(line)
+    before = dict(vars(src))
+    fakes = {}
+
+    def run(patched):
+        cwd = tmp_path / ("patched" if patched else "reference")
+        cwd.mkdir()
+        monkeypatch.chdir(cwd)                               # (MSERTrain.val is a cwd-relative cache: one directory per run)
+        for k, v in before.items():
+            setattr(src, k, v)
+        src.tqdm = lambda it=None, *a, **k: it
+        src.sleep = lambda *_: None
+        if patched:
+            fakes["det"], fakes["rec"] = OracleContext("det"), OracleContext("rec")
+            monkeypatch.setattr(tsd_b200.source_det, "_ctx", fakes["det"])
+            monkeypatch.setattr(tsd_b200.source_rec, "_ctx", fakes["rec"])
+            monkeypatch.setattr(tsd_b200.source_rec, "_lda_key", None)
+            monkeypatch.setattr(tsd_b200.source_rec, "_knn_key", None)
+            tsd_b200.source_rec.install(src)
+        rec = {}
+        inner = src.predictProbability
+
+        def spy(*a, **k):
+            r = inner(*a, **k)
+            rec["pred"], rec["true"] = [int(v) for v in r[0]], [int(v) for v in r[1]]
+            return r
+        src.predictProbability = spy
+        random.seed(0); np.random.seed(0)
+        src.testValidation(str(train), (7, 200, 2000, 1.0), ("HOG", "LDA", classifier), 0.1, 0.5)
+        rec["val"] = pickle.load(open("MSERTrain.val", "rb"))
+        return rec
+    try:
+        ref, got = run(False), run(True)
+    finally:
+        for k, v in before.items():
+            setattr(src, k, v)
+    assert len(ref["pred"]) > 20 and got["pred"] == ref["pred"] and got["true"] == ref["true"]
+    assert list(got["val"].keys()) == list(ref["val"].keys())
+    for k in ref["val"]:
+        assert len(got["val"][k]) == len(ref["val"][k]) > 0
+        for a, b in zip(got["val"][k], ref["val"][k]):
+            assert np.array_equal(a[0], b[0]) and tuple(a[1]) == tuple(b[1]) and a[2:] == b[2:]
+    assert fakes["rec"].calls["windows"] >= 1 and fakes["rec"].calls["hog"] >= 2
+    assert fakes["rec"].calls.get("lda_predict" if classifier == "LDABAYES" else "knn_predict", 0) == 1
