@@ -201,15 +201,16 @@ def test_reference_driver_through_install(tmp_path, monkeypatch, resultado150):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
-@pytest.mark.parametrize("classifier", ["LDABAYES", "KNN"])
-def test_reference_recognition_driver_through_install(tmp_path, monkeypatch, classifier):
+@pytest.mark.parametrize("descriptor,classifier", [("HOG", "LDABAYES"), ("HOG", "KNN"), ("GRAY", "LDABAYES"), ("GRAY", "KNN")])
+def test_reference_recognition_driver_through_install(tmp_path, monkeypatch, descriptor, classifier):
     """The reference's own `testValidation()` (REC/source.py:646-809) on a reduced training directory (8 real train frames that
     hold at least three signs of every type + their gt.txt lines; MSER (7, 200, 2000, 1.0) as in the reference), run twice from
     the same seeds: UNPATCHED (pure reference: cv2 + scikit-learn) and through source_rec.install() with the engine behind the
     mirrors replaced by the oracle-backed test double (no GPU in the container that holds the reference tree).  The training-window
     cache MSERTrain.val (grey 32x32 pixels and coordinates, in order) and the predicted / true labels of the validation split
     must be identical: this pins the glue of every patched REC function as the driver uses it (window extraction, negatives,
-    descriptors, weights read out of the fitted sklearn objects, the LDA-Bayes and KNN decisions)."""
+    descriptors, weights read out of the fitted sklearn objects, the LDA-Bayes and KNN decisions), for the four classifier strings
+    of REC/constants.py:10-12 (HOG / GRAY descriptor x LDA-Bayes / KNN)."""
     import pickle
     import random
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
@@ -255,7 +256,7 @@ def test_reference_recognition_driver_through_install(tmp_path, monkeypatch, cla
             return r
         src.predictProbability = spy
         random.seed(0); np.random.seed(0)
-        src.testValidation(str(train), (7, 200, 2000, 1.0), ("HOG", "LDA", classifier), 0.1, 0.5)
+        src.testValidation(str(train), (7, 200, 2000, 1.0), (descriptor, "LDA", classifier), 0.1, 0.5)
         rec["val"] = pickle.load(open("MSERTrain.val", "rb"))
         return rec
     try:
@@ -269,5 +270,5 @@ def test_reference_recognition_driver_through_install(tmp_path, monkeypatch, cla
         assert len(got["val"][k]) == len(ref["val"][k]) > 0
         for a, b in zip(got["val"][k], ref["val"][k]):
             assert np.array_equal(a[0], b[0]) and tuple(a[1]) == tuple(b[1]) and a[2:] == b[2:]
-    assert fakes["rec"].calls["windows"] >= 1 and fakes["rec"].calls["hog"] >= 2
+    assert fakes["rec"].calls["windows"] >= 1 and (descriptor == "GRAY" or fakes["rec"].calls["hog"] >= 2)
     assert fakes["rec"].calls.get("lda_predict" if classifier == "LDABAYES" else "knn_predict", 0) == 1
